@@ -1,0 +1,78 @@
+"""Generates tests/golden/*.npz from the UNMODIFIED reference (authoring container only).
+
+Run:  python tests/golden/make_golden.py
+It imports /root/reference/models/*.py through oracle/ref_import.py (stub modules + the restated
+CompressAI subset), fills the reference modules with the name-keyed deterministic weights of
+oracle/weights.py, runs them on the seeded inputs of oracle/inputs.py and stores the outputs.
+The GPU box has no /root/reference: there the fixtures pin the oracle restatement
+(tests/test_oracle_golden.py) which in turn checks the CUDA product.
+
+Provenance of every array: produced by reference code (models/raw2bit.py, LiteISP.py, groupmix.py)
+-- except the entropy-coder bytes/tables, which come from the restated CompressAI subset the
+reference was run against ("parity unpinned" vs upstream CompressAI, see oracle/cai.py).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import inputs, ref_import, weights  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    ref = ref_import.import_reference()
+    torch.set_grad_enabled(False)
+
+    # ---- raw_compression_tcm_final, T=256 (raw2bit.py:1614-2027)
+    m = ref.raw2bit.raw_compression_tcm_final().eval()
+    weights.fill_(m, seed=0)
+    x = inputs.make_inputs(256, seed=1234)
+    out = m(x)
+    m.update(force=True)
+    c = m.compress(x)
+    d = m.decompress(c["strings"], c["shape"])
+    gc, eb = m.gaussian_conditional, m.entropy_bottleneck
+    np.savez_compressed(
+        os.path.join(OUT, "final_T256.npz"),
+        weights_abs_sum=np.float64(weights.checksum(m.state_dict())["abs_sum"]),
+        raw_sum=np.float64(x[0].double().sum()), cond_sum=np.float64(x[1].double().sum()),
+        y=out["y"].numpy(), means=out["para"]["means"].numpy(), scales=out["para"]["scales"].numpy(),
+        lik_y=out["likelihoods"]["y"].numpy(), lik_z=out["likelihoods"]["z"].numpy(),
+        lft=out["lft"].numpy(), lsc_sub=out["lsc"][:, ::8, ::16, ::16].numpy(),
+        x_hat_sub=out["x_hat"][:, :, ::4, ::4].numpy(), x_hat_abs_sum=np.float64(out["x_hat"].double().abs().sum()),
+        dec_x_hat_sub=d["x_hat"][:, :, ::4, ::4].numpy(),
+        y_string=np.frombuffer(c["strings"][0][0], dtype=np.uint8),
+        z_string=np.frombuffer(c["strings"][1][0], dtype=np.uint8), shape=np.asarray(c["shape"]),
+        gc_cdf_rows=gc.quantized_cdf[[0, 1, 31, 63]].numpy(), gc_cdf_sum=np.int64(gc.quantized_cdf.long().sum()),
+        gc_cdf_length=gc.cdf_length.numpy(), gc_offset=gc.offset.numpy(), scale_table=gc.scale_table.numpy(),
+        eb_cdf=eb.quantized_cdf.numpy(), eb_cdf_length=eb.cdf_length.numpy(), eb_offset=eb.offset.numpy(),
+    )
+    print("final_T256: y bytes", len(c["strings"][0][0]), "z bytes", len(c["strings"][1][0]))
+
+    # ---- LiteISPNet_GFM_LSC, BASELINE config 1 (LiteISP.py:1924-2035)
+    m = ref.LiteISP.LiteISPNet_GFM_LSC().eval()
+    weights.fill_(m, seed=0)
+    x = inputs.make_inputs(256, seed=1235)
+    o = m(x)
+    np.savez_compressed(os.path.join(OUT, "liteisp_T256.npz"), out_sub=o[:, :, ::2, ::2].numpy(),
+                        out_abs_sum=np.float64(o.double().abs().sum()),
+                        weights_abs_sum=np.float64(weights.checksum(m.state_dict())["abs_sum"]))
+
+    # ---- GMA_Block, the two dims the reference instantiates (raw2bit.py:4362-4363)
+    for dim in (80, 200):
+        g = ref.groupmix.GMA_Block(dim, 8).eval()
+        weights.fill_(g, seed=0)
+        gen = torch.Generator().manual_seed(77 + dim)
+        xx = torch.randn(2, 24 * 16, dim, generator=gen)
+        o = g(xx, (24, 16))
+        np.savez_compressed(os.path.join(OUT, f"gma_dim{dim}.npz"), x=xx.numpy(), out=o.numpy())
+    print("done")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,107 @@
+"""Pins the restated range coder (oracle/rans.py, oracle/rans_c.c) with hand-derived known answers.
+
+The reference has no test for this path and CompressAI is absent (parity unpinned vs
+upstream); the KATs below are derived by hand from the published rANS64 recurrences.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cai, rans, refpath
+
+
+def test_empty_stream_is_initial_state():
+    # flush of an empty buffer writes x = 2**31 as (low word, high word)
+    assert rans.encode_with_indexes([], [], [[0, 65536]], [2], [0]) == bytes([0, 0, 0, 0x80, 0, 0, 0, 0])
+
+
+def test_single_symbol_known_answer():
+    # cdf over 2 symbols + sentinel bin: [0, 32768, 65535, 65536]; encode symbol 1 (start 32768, freq 32767)
+    cdf = [[0, 32768, 65535, 65536]]
+    x0 = 1 << 31
+    f, s = 32767, 32768
+    x1 = ((x0 // f) << 16) + (x0 % f) + s  # no renormalisation: x0 < 2**47 * f
+    want = np.asarray([x1 & 0xFFFFFFFF, x1 >> 32], dtype="<u4").tobytes()
+    got = rans.encode_with_indexes([1], [0], cdf, [4], [0])
+    assert got == want
+    assert rans.decode_with_indexes(got, [0], cdf, [4], [0]) == [1]
+
+
+def test_bypass_known_answer():
+    # value 5 with max_value = 2 -> sentinel bin 2 then bypass: raw = 2*(5-2) = 6 -> n = 1 nibble;
+    # coding order: sentinel(start 65535,freq 1), nibble n=1, nibble 6 ; encoder runs in reverse
+    cdf = [[0, 32768, 65535, 65536]]
+    x = 1 << 31
+    x = (x << 4) | 6
+    x = (x << 4) | 1
+    words = []
+    if x >= ((1 << 15) << 32) * 1:
+        words.append(x & 0xFFFFFFFF)
+        x >>= 32
+    x = ((x // 1) << 16) + 0 + 65535
+    want = np.asarray([x & 0xFFFFFFFF, x >> 32] + words[::-1], dtype="<u4").tobytes()
+    got = rans.encode_with_indexes([5], [0], cdf, [4], [0])
+    assert got == want
+    assert rans.decode_with_indexes(got, [0], cdf, [4], [0]) == [5]
+    got = rans.encode_with_indexes([-3], [0], cdf, [4], [0])
+    assert rans.decode_with_indexes(got, [0], cdf, [4], [0]) == [-3]
+
+
+def _tables():
+    gc = cai.GaussianConditional(None)
+    gc.update_scale_table(cai.get_scale_table())
+    return gc
+
+
+def test_gaussian_tables_invariants():
+    gc = _tables()
+    st = gc.scale_table
+    assert abs(st[0].item() - 0.11) < 1e-7 and abs(st[-1].item() - 256) < 1e-3
+    assert abs(st[1].item() - 0.124404) < 1e-5
+    assert tuple(gc.quantized_cdf.shape) == (64, 3133)
+    assert gc.cdf_length.min().item() == 5 and gc.cdf_length.max().item() == 3133
+    assert gc.offset.min().item() == -1565 and gc.offset.max().item() == -1
+    q = gc.quantized_cdf.numpy()
+    for i in range(64):
+        row = q[i, : gc.cdf_length[i]]
+        assert row[0] == 0 and row[-1] == 65536 and np.all(np.diff(row) > 0)
+
+
+def test_fresh_bottleneck_tables():
+    torch.manual_seed(0)
+    eb = cai.EntropyBottleneck(192)
+    eb.update()
+    assert tuple(eb.quantized_cdf.shape) == (192, 23)
+    assert int(eb.cdf_length.min()) == 23 and int(eb.offset.min()) == -10 and int(eb.offset.max()) == -10
+    q = eb.quantized_cdf.numpy()
+    assert np.all(q[:, 0] == 0) and np.all(q[:, -1] == 65536) and np.all(np.diff(q, axis=1) > 0)
+
+
+def test_pmf_to_quantized_cdf_steals_from_narrowest():
+    cdf = rans.pmf_to_quantized_cdf([0.5, 0.0, 0.25, 0.25, 0.0], 16)
+    assert cdf[0] == 0 and cdf[-1] == 65536 and all(b > a for a, b in zip(cdf, cdf[1:]))
+    assert len(cdf) == 6
+
+
+@pytest.mark.parametrize("rate", ["low", "mid", "high"])
+def test_roundtrip_python_equals_c(rate):
+    gc = _tables()
+    g = np.random.default_rng({"low": 1, "mid": 2, "high": 3}[rate])
+    lo, hi = {"low": (0.11, 0.5), "mid": (0.5, 4.0), "high": (4.0, 64.0)}[rate]
+    n = 20000
+    sigma = np.exp(g.uniform(np.log(lo), np.log(hi), n)).astype(np.float32)
+    sigma[g.random(n) < 0.001] = 256.0
+    sym = np.round(sigma * g.standard_normal(n)).astype(np.int32)
+    out = g.random(n) < 0.0005
+    sym[out] = g.choice([-5000, 5000, -70000, 70000], size=int(out.sum()))
+    idx = gc.build_indexes(torch.from_numpy(sigma)).numpy().astype(np.int32)
+    cdf, sizes, offs = refpath._tables(gc)
+    b_py = rans.encode_with_indexes(sym, idx, cdf.tolist(), sizes, offs)
+    b_c = refpath.encode_stream(sym, idx, gc)
+    assert refpath._c() is not None, "oracle/rans_c.c failed to build"
+    assert b_py == b_c
+    dec = refpath.StreamDecoder(b_c, gc)
+    a = dec.decode(idx[: n // 2])
+    b = dec.decode(idx[n // 2:])
+    assert np.array_equal(np.concatenate([a, b]), sym)
+    assert rans.decode_with_indexes(b_py, idx, cdf.tolist(), sizes, offs) == sym.tolist()
