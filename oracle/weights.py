@@ -108,7 +108,7 @@ def checksum(sd) -> dict:
     tot, n = 0.0, 0
     for k in sorted(sd.keys()):
         t = sd[k]
-        if torch.is_floating_point(t):
+        if torch.is_floating_point(t) and not any(x in k for x in _SKIP):
             tot += float(t.double().abs().sum())
             n += t.numel()
     return {"abs_sum": tot, "numel": n, "tensors": len(sd)}

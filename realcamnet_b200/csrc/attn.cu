@@ -1,0 +1,179 @@
+// LayerNorm over channels and Swin window attention (W-MSA / SW-MSA), NHWC fp32.
+#include "common.cuh"
+
+namespace rcn {
+namespace {
+
+// one warp per pixel; C <= 32*NIT
+template <int NIT>
+__global__ void layernorm_kernel(const float* __restrict__ x, long long npix, int C, int ldx,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 float* __restrict__ y, int ldy, int act) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (pix >= npix) return;
+    const float* xr = x + pix * ldx;
+    float v[NIT];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+        const int c = lane + 32 * i;
+        v[i] = (c < C) ? xr[c] : 0.f;
+        s += v[i];
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+        const float d = (lane + 32 * i < C) ? v[i] - mean : 0.f;
+        q += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)C + eps);
+    float* yr = y + pix * ldy;
+#pragma unroll
+    for (int i = 0; i < NIT; ++i) {
+        const int c = lane + 32 * i;
+        if (c < C) yr[c] = act_apply((v[i] - mean) * rstd * gamma[c] + beta[c], act, 0.f);
+    }
+}
+
+// Window attention. One thread per (query token, head); blockDim = (P, HPB) with P = WS*WS tokens.
+// K and V of the head are staged in shared memory (broadcast reads), scores live in registers.
+template <int WS, int HD>
+__global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, int ldq, int shifted,
+                            const float* __restrict__ relpos, float* __restrict__ out, int ldo, int nheads) {
+    constexpr int P = WS * WS;
+    extern __shared__ float sm[];  // [HPB][2][P][HD]
+    const int t = threadIdx.x;     // token in window
+    const int hl = threadIdx.y;    // head within block
+    const int head = blockIdx.y * blockDim.y + hl;
+    const int nww = W / WS, nwh = H / WS;
+    const int win = blockIdx.x;
+    const int n = win / (nwh * nww);
+    const int wrem = win - n * nwh * nww;
+    const int wy = wrem / nww, wx = wrem - wy * nww;
+    const int sh = shifted ? WS / 2 : 0;
+    const int py = t / WS, px = t - py * WS;
+    const int gy = (wy * WS + py + sh) % H, gx = (wx * WS + px + sh) % W;
+    const bool active = head < nheads;
+    const float* base = qkv + ((long long)(n * H + gy) * W + gx) * ldq;
+    float* ks = sm + (size_t)hl * 2 * P * HD;
+    float* vs = ks + P * HD;
+    float q[HD];
+    if (active) {
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(base + head * HD + d);
+            const float4 b = *reinterpret_cast<const float4*>(base + C + head * HD + d);
+            const float4 c = *reinterpret_cast<const float4*>(base + 2 * C + head * HD + d);
+            q[d] = a.x; q[d + 1] = a.y; q[d + 2] = a.z; q[d + 3] = a.w;
+            *reinterpret_cast<float4*>(ks + t * HD + d) = b;
+            *reinterpret_cast<float4*>(vs + t * HD + d) = c;
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const float scale = rsqrtf((float)HD);
+    const bool rq = shifted && (wy == nwh - 1) && (py >= WS - sh);
+    const bool cq = shifted && (wx == nww - 1) && (px >= WS - sh);
+    const float* rp = relpos + (size_t)head * (2 * WS - 1) * (2 * WS - 1);
+    float s[P];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a = fmaf(q[d], ks[j * HD + d], a);
+        const int jy = j / WS, jx = j - jy * WS;
+        a = a * scale + rp[(py - jy + WS - 1) * (2 * WS - 1) + (px - jx + WS - 1)];
+        if (shifted) {
+            const bool rk = (wy == nwh - 1) && (jy >= WS - sh);
+            const bool ck = (wx == nww - 1) && (jx >= WS - sh);
+            if (rk != rq || ck != cq) a = -INFINITY;
+        }
+        s[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float den = 0.f;
+#pragma unroll
+    for (int j = 0; j < P; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+    const float inv = 1.f / den;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const float pj = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, vs[j * HD + d], o[d]);
+    }
+    float* op = out + ((long long)(n * H + gy) * W + gx) * ldo + head * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+}
+
+template <int WS, int HD>
+int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shifted, const float* relpos,
+                float* out, int ldo, cudaStream_t s) {
+    constexpr int P = WS * WS;
+    const int nheads = C / HD;
+    int hpb = 256 / P;
+    if (hpb > nheads) hpb = nheads;
+    if (hpb < 1) hpb = 1;
+    dim3 block(P, hpb);
+    dim3 grid((unsigned)(N * (H / WS) * (W / WS)), (nheads + hpb - 1) / hpb);
+    const size_t smem = (size_t)hpb * 2 * P * HD * sizeof(float);
+    auto kern = wmsa_kernel<WS, HD>;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, block, smem, s>>>(qkv, H, W, C, ldq, shifted, relpos, out, ldo, nheads);
+    return 0;
+}
+
+}  // namespace
+}  // namespace rcn
+
+extern "C" int rcn_layernorm(const float* x, long long npix, int C, int ldx, const float* gamma, const float* beta,
+                             float eps, float* y, int ldy, int act, void* stream) {
+    using namespace rcn;
+    RCN_CHECK_ARG(x && y && gamma && beta && npix > 0, "rcn_layernorm: bad arguments");
+    RCN_CHECK_ARG(C > 0 && C <= 1024, "rcn_layernorm: C=%d unsupported (1..1024)", C);
+    const int wpb = 8;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int grid = cdiv(npix, wpb);
+    if (C <= 32) layernorm_kernel<1><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    else if (C <= 64) layernorm_kernel<2><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    else if (C <= 128) layernorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    else if (C <= 256) layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    else layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_layernorm");
+    return RCN_OK;
+}
+
+extern "C" int rcn_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int head_dim, int ws, int shifted,
+                        const float* relpos, float* out, int ldo, void* stream) {
+    using namespace rcn;
+    RCN_CHECK_ARG(qkv && relpos && out, "rcn_wmsa: null pointer");
+    RCN_CHECK_ARG(H % ws == 0 && W % ws == 0, "rcn_wmsa: map %dx%d not divisible by window %d", H, W, ws);
+    RCN_CHECK_ARG(C % head_dim == 0 && ldq % 4 == 0 && ldo % 4 == 0, "rcn_wmsa: bad channel layout");
+    RCN_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "rcn_wmsa: pointers must be 16-byte aligned");
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = -1;
+    if (ws == 8 && head_dim == 8) rc = launch_wmsa<8, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    else if (ws == 8 && head_dim == 16) rc = launch_wmsa<8, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    else if (ws == 8 && head_dim == 32) rc = launch_wmsa<8, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    else if (ws == 4 && head_dim == 32) rc = launch_wmsa<4, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    else if (ws == 4 && head_dim == 16) rc = launch_wmsa<4, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    else if (ws == 4 && head_dim == 8) rc = launch_wmsa<4, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    if (rc != 0) {
+        set_error("rcn_wmsa: (window %d, head_dim %d) unsupported", ws, head_dim);
+        return RCN_ERR_UNSUPPORTED;
+    }
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_wmsa");
+    return RCN_OK;
+}

@@ -1,0 +1,50 @@
+// Shared helpers for the realcamnet_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/rcn_b200.h"
+
+namespace rcn {
+
+void set_error(const char* fmt, ...);
+
+#define RCN_CHECK_ARG(cond, ...)                  \
+    do {                                          \
+        if (!(cond)) {                            \
+            rcn::set_error(__VA_ARGS__);          \
+            return RCN_ERR_INVALID;               \
+        }                                         \
+    } while (0)
+
+#define RCN_CHECK_LAUNCH(name)                                                         \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            rcn::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__));    \
+            return RCN_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+// count of kernel launches issued by this library (bench.py's "gpu_launches")
+extern unsigned long long g_launches;
+inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+    switch (act) {
+        case RCN_ACT_RELU: return v > 0.f ? v : 0.f;
+        case RCN_ACT_LRELU: return v > 0.f ? v : v * slope;
+        case RCN_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+        case RCN_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case RCN_ACT_HALF_TANH: return 0.5f * tanhf(v);
+        case RCN_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);
+        case RCN_ACT_HSWISH: return v * fminf(fmaxf(v + 3.f, 0.f), 6.f) * (1.f / 6.f);
+        default: return v;
+    }
+}
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace rcn

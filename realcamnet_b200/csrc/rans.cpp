@@ -1,0 +1,229 @@
+// Host-side range coder of the product: rANS with a 64-bit state, 32-bit renormalisation words,
+// 16-bit probabilities and 4-bit bypass nibbles -- stream-compatible with what the reference
+// obtains from CompressAI's C++ coder (BufferedRansEncoder / RansDecoder, call sites
+// models/raw2bit.py:1921,1956-1957,1996-1997,2013; models/tcm.py:531,566-567,606-607,621).
+//
+// The encoder walks the symbol list BACKWARDS and emits each symbol's coding events in reverse
+// (raw nibbles high->low, nibble-count digits, then the CDF bin), writing words from the end of
+// the buffer, so no intermediate event list is materialised.  The decoder keeps its state in an
+// object so the five-slice loop can pull one slice at a time from a single stream.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "../../include/rcn_b200.h"
+
+namespace rcn {
+void set_error(const char* fmt, ...);
+}
+
+namespace {
+
+constexpr uint32_t kProbBits = 16;
+constexpr uint32_t kNibbleBits = 4;
+constexpr uint32_t kNibbleMax = 15;
+constexpr uint64_t kLow = 1ull << 31;
+
+struct Writer {
+    uint32_t* cur;  // next free slot is cur - 1
+    uint64_t x = kLow;
+    inline void bin(uint32_t start, uint32_t freq) {
+        const uint64_t limit = ((kLow >> kProbBits) << 32) * (uint64_t)freq;
+        if (x >= limit) { *--cur = (uint32_t)x; x >>= 32; }
+        x = ((x / freq) << kProbBits) + (x % freq) + start;
+    }
+    inline void nibble(uint32_t v) {
+        const uint64_t limit = ((kLow >> kProbBits) << 32) << (kProbBits - kNibbleBits);
+        if (x >= limit) { *--cur = (uint32_t)x; x >>= 32; }
+        x = (x << kNibbleBits) | v;
+    }
+};
+
+struct Classified {
+    int bin;        // index into the CDF row
+    uint32_t raw;   // bypass payload when bin == sentinel
+    bool escaped;
+};
+
+inline Classified classify(int symbol, int offset, int sentinel) {
+    Classified c;
+    int v = symbol - offset;
+    c.raw = 0;
+    if (v < 0) { c.raw = (uint32_t)(-2 * (int64_t)v - 1); v = sentinel; }
+    else if (v >= sentinel) { c.raw = (uint32_t)(2 * ((int64_t)v - sentinel)); v = sentinel; }
+    c.bin = v;
+    c.escaped = (v == sentinel);
+    return c;
+}
+
+inline int nibble_count(uint32_t raw) {
+    int n = 0;
+    while (n < 8 && (raw >> (n * kNibbleBits)) != 0) ++n;
+    return n;
+}
+
+}  // namespace
+
+extern "C" long long rcn_rans_encode(const int32_t* symbols, const int32_t* indexes, long long n, const int32_t* cdfs,
+                                     int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* out,
+                                     long long out_cap) {
+    if ((n > 0 && (!symbols || !indexes)) || !cdfs || !cdf_sizes || !offsets || !out || n < 0) {
+        rcn::set_error("rcn_rans_encode: bad arguments");
+        return RCN_ERR_INVALID;
+    }
+    // upper bound on emitted words: one per coding event + the two state words
+    long long events = 0;
+    for (long long i = 0; i < n; ++i) {
+        const int ci = indexes[i];
+        const Classified c = classify(symbols[i], offsets[ci], cdf_sizes[ci] - 2);
+        events += 1;
+        if (c.escaped) { const int nb = nibble_count(c.raw); events += nb + nb / (int)kNibbleMax + 1; }
+    }
+    std::vector<uint32_t> buf;
+    try { buf.resize((size_t)events + 2); } catch (const std::bad_alloc&) {
+        rcn::set_error("rcn_rans_encode: out of host memory");
+        return RCN_ERR_NOMEM;
+    }
+    Writer w;
+    w.cur = buf.data() + buf.size();
+    for (long long i = n - 1; i >= 0; --i) {
+        const int ci = indexes[i];
+        const int32_t* row = cdfs + (long long)ci * cdf_stride;
+        const int sentinel = cdf_sizes[ci] - 2;
+        const Classified c = classify(symbols[i], offsets[ci], sentinel);
+        if (c.escaped) {
+            const int nb = nibble_count(c.raw);
+            for (int j = nb - 1; j >= 0; --j) w.nibble((c.raw >> (j * kNibbleBits)) & kNibbleMax);
+            // count is written as 15,15,...,r in coding order -> reversed here: r first, then the 15s
+            w.nibble((uint32_t)(nb % (int)kNibbleMax));
+            for (int k = 0; k < nb / (int)kNibbleMax; ++k) w.nibble(kNibbleMax);
+        }
+        w.bin((uint32_t)row[c.bin], (uint32_t)(row[c.bin + 1] - row[c.bin]));
+    }
+    *--w.cur = (uint32_t)(w.x >> 32);
+    *--w.cur = (uint32_t)w.x;
+    const long long nbytes = (long long)(buf.data() + buf.size() - w.cur) * 4;
+    if (nbytes > out_cap) {
+        rcn::set_error("rcn_rans_encode: output buffer too small (%lld > %lld)", nbytes, out_cap);
+        return RCN_ERR_NOMEM;
+    }
+    memcpy(out, w.cur, (size_t)nbytes);
+    return nbytes;
+}
+
+struct rcn_rans_decoder {
+    std::vector<uint32_t> words;
+    size_t pos;
+    uint64_t x;
+    inline void refill() {
+        if (x < kLow) { x = (x << 32) | (pos < words.size() ? words[pos] : 0u); ++pos; }
+    }
+    inline uint32_t nibble() {
+        const uint32_t v = (uint32_t)(x & kNibbleMax);
+        x >>= kNibbleBits;
+        refill();
+        return v;
+    }
+};
+
+extern "C" rcn_rans_decoder* rcn_rans_decoder_create(const uint8_t* stream, long long nbytes) {
+    if (!stream || nbytes < 8 || (nbytes & 3)) {
+        rcn::set_error("rcn_rans_decoder_create: stream must hold at least the 8-byte state and be word aligned in length");
+        return nullptr;
+    }
+    rcn_rans_decoder* d = new (std::nothrow) rcn_rans_decoder();
+    if (!d) return nullptr;
+    d->words.resize((size_t)nbytes / 4);
+    memcpy(d->words.data(), stream, (size_t)nbytes);
+    d->x = (uint64_t)d->words[0] | ((uint64_t)d->words[1] << 32);
+    d->pos = 2;
+    return d;
+}
+
+extern "C" void rcn_rans_decoder_destroy(rcn_rans_decoder* d) { delete d; }
+
+extern "C" int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long long n, const int32_t* cdfs, int cdf_stride,
+                               const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out) {
+    if (!d || !indexes || !cdfs || !cdf_sizes || !offsets || !out || n < 0) {
+        rcn::set_error("rcn_rans_decode: bad arguments");
+        return RCN_ERR_INVALID;
+    }
+    for (long long i = 0; i < n; ++i) {
+        const int ci = indexes[i];
+        const int32_t* row = cdfs + (long long)ci * cdf_stride;
+        const int size = cdf_sizes[ci], sentinel = size - 2;
+        const uint32_t cum = (uint32_t)(d->x & 0xFFFFu);
+        // first entry strictly greater than cum, minus one (rows are strictly increasing)
+        const int32_t* it = std::upper_bound(row, row + size, (int32_t)cum);
+        const int s = (int)(it - row) - 1;
+        const uint32_t start = (uint32_t)row[s], freq = (uint32_t)(row[s + 1] - row[s]);
+        d->x = (uint64_t)freq * (d->x >> kProbBits) + cum - start;
+        d->refill();
+        int v = s;
+        if (s == sentinel) {
+            uint32_t digit = d->nibble();
+            int nb = (int)digit;
+            while (digit == kNibbleMax) { digit = d->nibble(); nb += (int)digit; }
+            uint32_t raw = 0;
+            for (int j = 0; j < nb; ++j) raw |= d->nibble() << (j * kNibbleBits);
+            v = (int)(raw >> 1);
+            v = (raw & 1u) ? -v - 1 : v + sentinel;
+        }
+        out[i] = v + offsets[ci];
+    }
+    return RCN_OK;
+}
+
+// pmf (float32) -> strictly increasing 16-bit CDF of length n+1 (CompressAI _CXX.pmf_to_quantized_cdf semantics,
+// used by EntropyBottleneck.update / GaussianConditional.update behind raw2bit.py:1759-1764).
+extern "C" int rcn_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf) {
+    if (!pmf || !cdf || n <= 0 || precision < 1 || precision > 16) {
+        rcn::set_error("rcn_pmf_to_quantized_cdf: bad arguments");
+        return RCN_ERR_INVALID;
+    }
+    const uint32_t one = 1u << precision;
+    std::vector<uint32_t> c((size_t)n + 1, 0u);
+    uint32_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        const float p = pmf[i];
+        if (!(p >= 0.f) || !std::isfinite(p)) {
+            rcn::set_error("rcn_pmf_to_quantized_cdf: pmf[%d] is negative or not finite", i);
+            return RCN_ERR_INVALID;
+        }
+        c[(size_t)i + 1] = (uint32_t)std::round(p * (float)one);
+        total += c[(size_t)i + 1];
+    }
+    if (total == 0) {
+        rcn::set_error("rcn_pmf_to_quantized_cdf: pmf sums to zero");
+        return RCN_ERR_INVALID;
+    }
+    uint32_t run = 0;
+    for (size_t i = 0; i < c.size(); ++i) {
+        run += (uint32_t)(((uint64_t)one * c[i]) / total);
+        c[i] = run;
+    }
+    c.back() = one;
+    const int m = n + 1;
+    for (int i = 0; i + 1 < m; ++i) {
+        if (c[i] != c[i + 1]) continue;
+        uint32_t narrowest = ~0u;
+        int donor = -1;
+        for (int j = 0; j + 1 < m; ++j) {
+            const uint32_t f = c[j + 1] - c[j];
+            if (f > 1 && f < narrowest) { narrowest = f; donor = j; }
+        }
+        if (donor < 0) {
+            rcn::set_error("rcn_pmf_to_quantized_cdf: cannot make the CDF strictly increasing");
+            return RCN_ERR_INVALID;
+        }
+        if (donor < i) for (int j = donor + 1; j <= i; ++j) c[j]--;
+        else for (int j = i + 1; j <= donor; ++j) c[j]++;
+    }
+    for (int i = 0; i < m; ++i) cdf[i] = (int32_t)c[i];
+    return RCN_OK;
+}

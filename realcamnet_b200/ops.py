@@ -1,0 +1,325 @@
+"""Tensor-level wrappers over the C ABI (include/rcn_b200.h).
+
+PyTorch is used for device memory (torch.empty), the current CUDA stream and parameter storage
+only; every arithmetic op on the path is a kernel of librcn_b200.so.  Internal activations are
+NHWC fp32 torch tensors (N,H,W,C) -- possibly channel-slice views of a wider buffer, which is
+how torch.cat/torch.split of the reference are expressed without copies.
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import torch
+
+from . import _C
+
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_GELU, ACT_SIGMOID, ACT_HALF_TANH, ACT_HSWISH, ACT_CLAMP01 = range(8)
+EPI_NONE, EPI_GDN, EPI_IGDN, EPI_MUL_AUXP1, EPI_MULP1_AUX, EPI_SIGMOID_GATE = range(6)
+STORE_NHWC, STORE_PS2, STORE_NCHW, STORE_PS2_NCHW = range(4)
+
+_vp = ctypes.c_void_p
+
+
+def _stream():
+    return _vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return _vp(t.data_ptr()) if t is not None else _vp(0)
+
+
+def _chk(t, name="tensor"):
+    if not (t.is_cuda and t.dtype == torch.float32):
+        raise TypeError(f"{name}: expected a CUDA float32 tensor, got {t.device} {t.dtype}")
+
+
+def geom(t, name="tensor"):
+    """(N, H, W, C, ld) of an NHWC tensor / channel-slice view."""
+    _chk(t, name)
+    if t.dim() != 4:
+        raise ValueError(f"{name}: expected 4 dims (N,H,W,C), got {tuple(t.shape)}")
+    N, H, W, C = t.shape
+    if C > 1 and t.stride(3) != 1:
+        raise ValueError(f"{name}: channel dim must be contiguous")
+    if W > 1:
+        ld = t.stride(2)
+    elif H > 1:
+        ld = t.stride(1)
+    elif N > 1:
+        ld = t.stride(0)
+    else:
+        ld = C
+    if (H > 1 and t.stride(1) != W * ld) or (N > 1 and t.stride(0) != H * W * ld) or ld < C:
+        raise ValueError(f"{name}: not an NHWC tensor or channel slice (shape {tuple(t.shape)}, strides {t.stride()})")
+    return N, H, W, C, ld
+
+
+def empty(N, H, W, C, like=None, device=None):
+    dev = like.device if like is not None else device
+    return torch.empty((N, H, W, C), device=dev, dtype=torch.float32)
+
+
+def launch_count() -> int:
+    return int(_C.lib().rcn_launch_count())
+
+
+# ----------------------------------------------------------------------------- weights
+class PackedConv:
+    __slots__ = ("w", "bias", "k", "cin", "cout")
+
+    def __init__(self, w, bias, k, cin, cout):
+        self.w, self.bias, self.k, self.cin, self.cout = w, bias, k, cin, cout
+
+
+_pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
+
+
+def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
+    """OIHW conv weight or (O,I) linear weight -> [k*k*Cin][Cout] on the device."""
+    _chk(weight, "weight")
+    w = weight.detach()
+    if w.dim() == 2:
+        cout, cin, k = w.shape[0], w.shape[1], 1
+    else:
+        cout, cin, k = w.shape[0], w.shape[1], w.shape[2]
+        assert w.shape[2] == w.shape[3]
+    w = w.contiguous()
+    out = torch.empty((k * k * cin, cout), device=w.device, dtype=torch.float32)
+    _C.check(_C.lib().rcn_pack_conv_weight(_ptr(w), cout, cin, k, _ptr(out), _stream()), "rcn_pack_conv_weight")
+    b = bias.detach().contiguous() if bias is not None else None
+    return PackedConv(out, b, k, cin, cout)
+
+
+def pack(module) -> PackedConv:
+    """Cached packing of an nn.Conv2d / nn.Linear parameter holder (re-packed if the weights change)."""
+    w, b = module.weight, getattr(module, "bias", None)
+    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), str(w.device))
+    hit = _pack_cache.get(module)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    pc = pack_weight(w, b)
+    _pack_cache[module] = (key, pc)
+    return pc
+
+
+# ----------------------------------------------------------------------------- conv / linear
+def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
+           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0):
+    N, H, W, Cin, ldx = geom(x, "conv2d.x")
+    if Cin != pc.cin:
+        raise ValueError(f"conv2d: input has {Cin} channels, weight expects {pc.cin}")
+    pad = pc.k // 2
+    Ho = (H + 2 * pad - pc.k) // stride + 1
+    Wo = (W + 2 * pad - pc.k) // stride + 1
+    ps = store in (STORE_PS2, STORE_PS2_NCHW)
+    Hs, Ws, Cs = (2 * Ho, 2 * Wo, pc.cout // 4) if ps else (Ho, Wo, pc.cout)
+    if out is None:
+        if store in (STORE_NCHW, STORE_PS2_NCHW):
+            out = torch.empty((N, Cs, Hs, Ws), device=x.device, dtype=torch.float32)
+        else:
+            out = torch.empty((N, Hs, Ws, Cs), device=x.device, dtype=torch.float32)
+    if store in (STORE_NCHW, STORE_PS2_NCHW):
+        if tuple(out.shape) != (N, Cs, Hs, Ws) or not out.is_contiguous():
+            raise ValueError("conv2d: NCHW output must be contiguous with the right shape")
+        ldy = 0
+    else:
+        oN, oH, oW, oC, ldy = geom(out, "conv2d.out")
+        if (oN, oH, oW, oC) != (N, Hs, Ws, Cs):
+            raise ValueError(f"conv2d: output shape {tuple(out.shape)} != {(N, Hs, Ws, Cs)}")
+    d = _C.ConvDesc()
+    d.x, d.N, d.H, d.W, d.Cin, d.ldx = x.data_ptr(), N, H, W, Cin, ldx
+    d.w = pc.w.data_ptr()
+    d.bias = pc.bias.data_ptr() if (bias and pc.bias is not None) else None
+    d.k, d.stride, d.Cout, d.in_square = pc.k, stride, pc.cout, int(in_square)
+    d.y, d.ldy, d.store = out.data_ptr(), ldy, store
+    d.epi = epi
+    if epi != EPI_NONE:
+        aN, aH, aW, aC, lda = geom(aux, "conv2d.aux")
+        if (aN, aH, aW, aC) != (N, Ho, Wo, pc.cout):
+            raise ValueError("conv2d: aux must have the conv output geometry")
+        d.aux, d.ldaux = aux.data_ptr(), lda
+    if cscale is not None:
+        _chk(cscale), _chk(cshift)
+        assert cscale.is_contiguous() and cshift.is_contiguous() and cscale.numel() == N * pc.cout == cshift.numel()
+        d.cscale, d.cshift = cscale.data_ptr(), cshift.data_ptr()
+    if res is not None:
+        rN, rH, rW, rC, ldr = geom(res, "conv2d.res")
+        if (rN, rH, rW, rC) != (N, Hs, Ws, Cs):
+            raise ValueError(f"conv2d: residual shape {tuple(res.shape)} != {(N, Hs, Ws, Cs)}")
+        d.res, d.ldres, d.res_pre = res.data_ptr(), ldr, int(res_pre)
+    d.act, d.slope, d.res_scale = act, float(slope), float(res_scale)
+    _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")
+    return out
+
+
+def layernorm(x, weight, bias, eps=1e-5, out=None, act=ACT_NONE):
+    N, H, W, C, ldx = geom(x, "layernorm.x")
+    if out is None:
+        out = empty(N, H, W, C, like=x)
+    _, _, _, _, ldy = geom(out, "layernorm.out")
+    _C.check(_C.lib().rcn_layernorm(_ptr(x), N * H * W, C, ldx, _ptr(weight), _ptr(bias), eps, _ptr(out), ldy, act,
+                                    _stream()), "rcn_layernorm")
+    return out
+
+
+def wmsa(qkv, relpos, head_dim, ws, shifted, out=None):
+    N, H, W, C3, ldq = geom(qkv, "wmsa.qkv")
+    C = C3 // 3
+    if out is None:
+        out = empty(N, H, W, C, like=qkv)
+    _, _, _, _, ldo = geom(out, "wmsa.out")
+    _chk(relpos)
+    assert relpos.is_contiguous() and tuple(relpos.shape) == (C // head_dim, 2 * ws - 1, 2 * ws - 1)
+    _C.check(_C.lib().rcn_wmsa(_ptr(qkv), N, H, W, C, ldq, head_dim, ws, int(shifted), _ptr(relpos), _ptr(out), ldo,
+                               _stream()), "rcn_wmsa")
+    return out
+
+
+# ----------------------------------------------------------------------------- layout
+def to_nhwc(x, out=None):
+    _chk(x, "to_nhwc.x")
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    if out is None:
+        out = empty(N, H, W, C, like=x)
+    _, _, _, _, ldy = geom(out)
+    _C.check(_C.lib().rcn_nchw_to_nhwc(_ptr(x), N, C, H, W, _ptr(out), ldy, _stream()), "rcn_nchw_to_nhwc")
+    return out
+
+
+def to_nchw(x):
+    N, H, W, C, ldx = geom(x, "to_nchw.x")
+    out = torch.empty((N, C, H, W), device=x.device, dtype=torch.float32)
+    _C.check(_C.lib().rcn_nhwc_to_nchw(_ptr(x), ldx, N, C, H, W, _ptr(out), _stream()), "rcn_nhwc_to_nchw")
+    return out
+
+
+def copy_channels(x, out):
+    N, H, W, C, ldx = geom(x)
+    oN, oH, oW, oC, ldy = geom(out)
+    assert (N, H, W, C) == (oN, oH, oW, oC)
+    _C.check(_C.lib().rcn_copy_channels(_ptr(x), ldx, N * H * W, C, _ptr(out), ldy, _stream()), "rcn_copy_channels")
+    return out
+
+
+# ----------------------------------------------------------------------------- pooling / gating
+def channel_mean(x):
+    """AdaptiveAvgPool2d(1) -> (N,1,1,C)"""
+    N, H, W, C, ldx = geom(x, "channel_mean.x")
+    mean = empty(N, 1, 1, C, like=x)
+    wsf = N * min(1024, max(1, (H * W) // 64)) * C
+    ws = torch.empty((wsf,), device=x.device, dtype=torch.float32)
+    _C.check(_C.lib().rcn_channel_mean(_ptr(x), N, H * W, C, ldx, _ptr(mean), _ptr(ws), wsf, _stream()), "rcn_channel_mean")
+    return mean
+
+
+def instance_norm(x, gamma, beta, eps=1e-5):
+    N, H, W, C, ldx = geom(x, "instance_norm.x")
+    mean = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    var = torch.empty((N, C), device=x.device, dtype=torch.float32)
+    _C.check(_C.lib().rcn_channel_meanvar(_ptr(x), N, H * W, C, ldx, _ptr(mean), _ptr(var), _stream()), "rcn_channel_meanvar")
+    out = empty(N, H, W, C, like=x)
+    _C.check(_C.lib().rcn_norm_apply(_ptr(x), ldx, N, H * W, C, _ptr(mean), _ptr(var), _ptr(gamma), _ptr(beta), eps,
+                                     _ptr(out), C, _stream()), "rcn_norm_apply")
+    return out
+
+
+def scale_add(x, g, b=None, per_n=True, res=None, out=None, act=ACT_NONE):
+    """out = act(x * g + b) + res, g/b per (n,c) or per c."""
+    N, H, W, C, ldx = geom(x, "scale_add.x")
+    if out is None:
+        out = empty(N, H, W, C, like=x)
+    _, _, _, _, ldy = geom(out)
+    ldr = geom(res)[4] if res is not None else 0
+    assert g.is_contiguous() and g.numel() == (N * C if per_n else C)
+    _C.check(_C.lib().rcn_scale_add(_ptr(x), ldx, N, H * W, C, _ptr(g), _ptr(b), int(per_n), _ptr(res), ldr, _ptr(out), ldy,
+                                    act, _stream()), "rcn_scale_add")
+    return out
+
+
+def avgpool3s2_lrelu(x, slope):
+    N, H, W, C, ldx = geom(x)
+    Ho, Wo = (H + 2 - 3) // 2 + 1, (W + 2 - 3) // 2 + 1
+    out = empty(N, Ho, Wo, C, like=x)
+    _C.check(_C.lib().rcn_avgpool3s2_lrelu(_ptr(x), N, H, W, C, ldx, slope, _ptr(out), C, _stream()), "rcn_avgpool3s2_lrelu")
+    return out
+
+
+def upsample_bilinear2x(x, out=None):
+    N, H, W, C, ldx = geom(x)
+    if out is None:
+        out = empty(N, 2 * H, 2 * W, C, like=x)
+    assert tuple(out.shape) == (N, 2 * H, 2 * W, C)
+    ldy = geom(out)[4]
+    _C.check(_C.lib().rcn_upsample_bilinear2x(_ptr(x), N, H, W, C, ldx, _ptr(out), ldy, _stream()), "rcn_upsample_bilinear2x")
+    return out
+
+
+def dwt_forward(x, out=None):
+    N, H, W, C, ldx = geom(x)
+    if out is None:
+        out = empty(N, H // 2, W // 2, 4 * C, like=x)
+    _C.check(_C.lib().rcn_dwt_forward(_ptr(x), N, H, W, C, ldx, _ptr(out), geom(out)[4], _stream()), "rcn_dwt_forward")
+    return out
+
+
+def dwt_inverse(x, out=None):
+    N, H, W, C4, ldx = geom(x)
+    if out is None:
+        out = empty(N, 2 * H, 2 * W, C4 // 4, like=x)
+    _C.check(_C.lib().rcn_dwt_inverse(_ptr(x), N, H, W, C4, ldx, _ptr(out), geom(out)[4], _stream()), "rcn_dwt_inverse")
+    return out
+
+
+def depthwise_conv(x, w_taps, bias, k, add_input=False, mul=None, out=None):
+    """w_taps: [k*k][C] (tap-major) device tensor."""
+    N, H, W, C, ldx = geom(x)
+    if out is None:
+        out = empty(N, H, W, C, like=x)
+    ldm = geom(mul)[4] if mul is not None else 0
+    _C.check(_C.lib().rcn_depthwise_conv(_ptr(x), N, H, W, C, ldx, _ptr(w_taps), _ptr(bias), k, int(add_input), _ptr(mul), ldm,
+                                         _ptr(out), geom(out)[4], _stream()), "rcn_depthwise_conv")
+    return out
+
+
+# ----------------------------------------------------------------------------- entropy
+def eb_forward(z, params, medians, want_zhat=True, want_lik=True, want_symbols=False, lik_bound=1e-9):
+    N, H, W, C, ldz = geom(z, "eb_forward.z")
+    z_hat = empty(N, H, W, C, like=z) if want_zhat else None
+    lik = empty(N, H, W, C, like=z) if want_lik else None
+    sym = torch.empty((N, C, H, W), device=z.device, dtype=torch.int32) if want_symbols else None
+    _C.check(_C.lib().rcn_eb_forward(_ptr(z), ldz, N, H * W, C, _ptr(params), _ptr(medians), _ptr(z_hat), C, _ptr(lik), C,
+                                     _ptr(sym), lik_bound, _stream()), "rcn_eb_forward")
+    return z_hat, lik, sym
+
+
+def eb_dequantize(symbols, medians):
+    N, C, H, W = symbols.shape
+    assert symbols.dtype == torch.int32 and symbols.is_contiguous()
+    z_hat = torch.empty((N, H, W, C), device=symbols.device, dtype=torch.float32)
+    _C.check(_C.lib().rcn_eb_dequantize(_ptr(symbols), N, H * W, C, _ptr(medians), _ptr(z_hat), C, _stream()), "rcn_eb_dequantize")
+    return z_hat
+
+
+def gaussian_conditional(y, mu, scale, table, y_hat=None, lik=None, symbols=None, indexes=None, scale_bound=0.11,
+                         lik_bound=1e-9):
+    N, H, W, C, ldy = geom(y, "gaussian.y")
+    ldm, lds = geom(mu)[4], geom(scale)[4]
+    ldyh = geom(y_hat)[4] if y_hat is not None else 0
+    ldl = geom(lik)[4] if lik is not None else 0
+    _C.check(_C.lib().rcn_gaussian_conditional(
+        _ptr(y), ldy, _ptr(mu), ldm, _ptr(scale), lds, N, H * W, C, _ptr(table), table.numel(), scale_bound, lik_bound,
+        _ptr(y_hat), ldyh, _ptr(lik), ldl, _ptr(symbols), _ptr(indexes), _stream()), "rcn_gaussian_conditional")
+
+
+def build_indexes(scale, table, indexes, scale_bound=0.11):
+    N, H, W, C, lds = geom(scale)
+    _C.check(_C.lib().rcn_build_indexes(_ptr(scale), lds, N, H * W, C, _ptr(table), table.numel(), scale_bound, _ptr(indexes),
+                                        _stream()), "rcn_build_indexes")
+
+
+def gaussian_dequantize(symbols, mu, y_hat):
+    N, H, W, C, ldm = geom(mu)
+    _C.check(_C.lib().rcn_gaussian_dequantize(_ptr(symbols), _ptr(mu), ldm, N, H * W, C, _ptr(y_hat), geom(y_hat)[4], _stream()),
+             "rcn_gaussian_dequantize")

@@ -1,0 +1,495 @@
+"""Host-side mirror of the reference's ``models/raw2bit.py`` (hot-path classes).
+
+  CALayer 238-253, ResidualBlockWithCA 257-289, ConvTransBlock_mzj 292-328,
+  HyCondMod{Conv,Enc,Dec}Block 730-814, HybridConditionModule 817-858,
+  SpatialFeatureTransform 860-886, raw_compression_tcm_final 1614-2027 (THE paper model).
+  GMABlock / GMAAtten / ConvGMABlock (168-184, 209-234, 330-355) wrap the GroupMix block.
+
+Same constructor arguments, parameter names and forward()/compress()/decompress()/update()
+signatures as the reference; every tensor op runs in librcn_b200.so.  Inference (eval) only.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .entropy_models import CompressionModel, EntropyBottleneck, GaussianConditional, RansDecoder, rans_encode
+from .groupmix import GMA_Block  # noqa: F401  (re-exported like the reference's copy, raw2bit.py:98-142)
+from .layers import (AttentionBlock, Conv2d, Linear, ResidualBlock, ResidualBlockUpsample, ResidualBlockWithStride,
+                     conv, conv1x1, conv3x3, subpel_conv3x3)
+from .LiteISP import Color_Condition_GFM, Lens_Shading_Correction, Res_GFM
+from .ops import (ACT_CLAMP01, ACT_GELU, ACT_HALF_TANH, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_MUL_AUXP1,
+                  EPI_MULP1_AUX, STORE_NCHW, STORE_PS2_NCHW)
+from .tcm import Block, ConvTransBlock, SWAtten, SwinBlock, get_scale_table  # noqa: F401
+
+
+class CALayer(nn.Module):
+    """models/raw2bit.py:238-253 (bias-free squeeze/excite over Linear layers)."""
+
+    def __init__(self, channel, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.fc = nn.Sequential(Linear(channel, channel // reduction, bias=False), nn.ReLU(inplace=True),
+                                Linear(channel // reduction, channel, bias=False), nn.Sigmoid())
+
+    def _f(self, x, res=None, out=None):
+        g = ops.channel_mean(x)
+        g = self.fc[2]._f(self.fc[0]._f(g, act=ACT_RELU), act=ACT_SIGMOID)
+        return ops.scale_add(x, g.reshape(-1), per_n=True, res=res, out=out)
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+class ResidualBlockWithCA(nn.Module):
+    """models/raw2bit.py:257-289."""
+
+    def __init__(self, in_ch: int, out_ch: int, redution=8):
+        super().__init__()
+        self.conv1 = conv3x3(in_ch, out_ch)
+        self.leaky_relu = nn.LeakyReLU(inplace=True)
+        self.conv2 = conv3x3(out_ch, out_ch)
+        self.ca = CALayer(out_ch, redution)
+        self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
+
+    def _f(self, x, out=None):
+        t = self.conv2._f(self.conv1._f(x, act=ACT_LRELU, slope=0.01))
+        identity = x if self.skip is None else self.skip._f(x)
+        return self.ca._f(t, res=identity, out=out)
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+class SpatialFeatureTransform(nn.Module):
+    """models/raw2bit.py:860-886: x*scale(cond) + shift(cond) (+ x)."""
+
+    def __init__(self, cond_channels=64, n_features=64, ada_method='vanilla', residual=True):
+        super().__init__()
+        assert ada_method == 'vanilla'
+        self.cond_scale = nn.Sequential(Conv2d(cond_channels, n_features, 3, stride=1, padding=1), nn.ReLU(inplace=True),
+                                        Conv2d(n_features, n_features, 3, stride=1, padding=1))
+        self.cond_shift = nn.Sequential(Conv2d(cond_channels, n_features, 3, stride=1, padding=1), nn.ReLU(inplace=True),
+                                        Conv2d(n_features, n_features, 3, stride=1, padding=1))
+        self.residual = residual
+
+    def _f(self, x, cond, extra=None, out=None):
+        """x*scale + shift + x (+ extra); both element-wise steps are conv epilogues."""
+        if not self.residual:
+            raise NotImplementedError("residual=False is never used by the reference")
+        s = self.cond_scale[0]._f(cond, act=ACT_RELU)
+        t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra)      # (scale + 1) * x (+ extra)
+        h = self.cond_shift[0]._f(cond, act=ACT_RELU)
+        return self.cond_shift[2]._f(h, res=t, out=out)                        # shift + ...
+
+    def forward(self, x, cond):
+        return ops.to_nchw(self._f(ops.to_nhwc(x), ops.to_nhwc(cond)))
+
+
+class ConvTransBlock_mzj(nn.Module):
+    """Conv (CA + local RAW feature transform) || Swin block, models/raw2bit.py:292-328.
+    forward([x, cond]) -> (x, cond)."""
+
+    def __init__(self, conv_dim, trans_dim, head_dim, window_size, drop_path, type='W'):
+        super().__init__()
+        assert type in ['W', 'SW']
+        self.conv_dim, self.trans_dim, self.head_dim = conv_dim, trans_dim, head_dim
+        self.num_head = trans_dim // head_dim
+        self.window_size, self.drop_path, self.type = window_size, drop_path, type
+        self.trans_block = Block(trans_dim, trans_dim, head_dim, window_size, drop_path, type)
+        self.conv1_1 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
+        self.conv1_2 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
+        self.conv_block = ResidualBlockWithCA(conv_dim, conv_dim, 8)
+        self.spatial_transform = SpatialFeatureTransform(cond_channels=conv_dim, n_features=conv_dim)
+
+    def _f(self, x, cond, out=None):
+        cd = self.conv_dim
+        both = self.conv1_1._f(x)
+        cat = torch.empty_like(both)
+        conv_identity = both[..., :cd]
+        cx = self.conv_block._f(conv_identity)
+        self.spatial_transform._f(cx, cond, extra=conv_identity, out=cat[..., :cd])
+        self.trans_block._f(both[..., cd:], out=cat[..., cd:])
+        return self.conv1_2._f(cat, res=x, out=out)
+
+    def forward(self, xx):
+        x, cond = xx[0], xx[1]
+        return ops.to_nchw(self._f(ops.to_nhwc(x), ops.to_nhwc(cond))), cond
+
+
+class HyCondModConvBlock(nn.Module):
+    """models/raw2bit.py:730-744."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=1, act='relu'):
+        super().__init__()
+        self.conv = Conv2d(in_channels, out_channels, kernel_size, stride, padding)
+        if act == 'lrelu':
+            self.act, self._act = nn.LeakyReLU(0.2, inplace=True), (ACT_LRELU, 0.2)
+        elif act == 'prelu':
+            raise NotImplementedError("prelu is never selected by the reference")
+        else:
+            self.act, self._act = nn.ReLU(inplace=True), (ACT_RELU, 0.0)
+
+    def _f(self, x, out=None):
+        return self.conv._f(x, act=self._act[0], slope=self._act[1], out=out)
+
+
+class HyCondModEncBlock(nn.Module):
+    """models/raw2bit.py:746-768 (stride downscale only, the reference default)."""
+
+    def __init__(self, in_channels, out_channels, downscale_method='stride'):
+        super().__init__()
+        assert downscale_method == 'stride'
+        self.down = HyCondModConvBlock(in_channels, out_channels, stride=2)
+        self.conv = HyCondModConvBlock(out_channels, out_channels)
+
+    def _f(self, x, out=None):
+        return self.conv._f(self.down._f(x), out=out)
+
+
+class HyCondModDecBlock(nn.Module):
+    """models/raw2bit.py:782-814 (bilinear x2, align_corners=True)."""
+
+    def __init__(self, in_channels, out_channels, upscale_method='bilinear'):
+        super().__init__()
+        assert upscale_method == 'bilinear'
+        self.up = nn.Sequential(nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True),
+                                HyCondModConvBlock(in_channels, out_channels))
+        self.conv = HyCondModConvBlock(in_channels, out_channels)
+
+    def _f(self, x1, cat, out=None):
+        """cat: (N,2H,2W,2*out) buffer whose first half already holds the skip tensor x2."""
+        oc = cat.shape[-1] // 2
+        self.up[1]._f(ops.upsample_bilinear2x(x1), out=cat[..., oc:])
+        return self.conv._f(cat, out=out)
+
+
+class HybridConditionModule(nn.Module):
+    """Local RAW condition UNet, models/raw2bit.py:817-858.  forward(x) -> [cond@1/2, cond@1/4, cond@1/8]."""
+
+    def __init__(self, in_channels=4, out_channels=64, init_mid_channels=16, down_method='stride', up_method='bilinear'):
+        super().__init__()
+        m = init_mid_channels
+        self.in_conv = HyCondModConvBlock(in_channels, m)
+        self.enc_1 = HyCondModEncBlock(m, m * 2, down_method)
+        self.enc_2 = HyCondModEncBlock(m * 2, m * 4, down_method)
+        self.enc_3 = HyCondModEncBlock(m * 4, m * 8, down_method)
+        self.dec_1 = HyCondModDecBlock(m * 8, m * 4, up_method)
+        self.dec_2 = HyCondModDecBlock(m * 4, m * 2, up_method)
+        self.dec_3 = HyCondModDecBlock(m * 2, m, up_method)
+        self.out_conv = HyCondModConvBlock(m, out_channels)
+        oc = out_channels
+        self.CondNet1 = nn.Sequential(Conv2d(oc, oc, 3, 2, 1), nn.LeakyReLU(0.1, True), Conv2d(oc, oc, 1))
+        self.CondNet2 = nn.Sequential(Conv2d(oc, oc, 3, 2, 1), nn.LeakyReLU(0.1, True), Conv2d(oc, oc, 3, 2, 1))
+        self.CondNet3 = nn.Sequential(Conv2d(oc, oc, 3, 2, 1), nn.LeakyReLU(0.1, True), Conv2d(oc, oc, 3, 2, 1),
+                                      nn.LeakyReLU(0.1, True), Conv2d(oc, oc, 3, 2, 1))
+        self._m = m
+
+    def _f(self, x):
+        N, H, W, _ = x.shape
+        m = self._m
+        # skip tensors are produced straight into the first half of the decoder concat buffers
+        cat3 = ops.empty(N, H, W, 2 * m, like=x)
+        cat2 = ops.empty(N, H // 2, W // 2, 4 * m, like=x)
+        cat1 = ops.empty(N, H // 4, W // 4, 8 * m, like=x)
+        x1 = self.in_conv._f(x, out=cat3[..., :m])
+        x2 = self.enc_1._f(x1, out=cat2[..., :2 * m])
+        x3 = self.enc_2._f(x2, out=cat1[..., :4 * m])
+        x4 = self.enc_3._f(x3)
+        y = self.dec_1._f(x4, cat1)
+        y = self.dec_2._f(y, cat2)
+        y = self.dec_3._f(y, cat3)
+        y = self.out_conv._f(y)
+        c1 = self.CondNet1[2]._f(self.CondNet1[0]._f(y, act=ACT_LRELU, slope=0.1))
+        c2 = self.CondNet2[2]._f(self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1))
+        c3 = self.CondNet3[0]._f(y, act=ACT_LRELU, slope=0.1)
+        c3 = self.CondNet3[2]._f(c3, act=ACT_LRELU, slope=0.1)
+        c3 = self.CondNet3[4]._f(c3)
+        return [c1, c2, c3]
+
+    def forward(self, x):
+        return [ops.to_nchw(c) for c in self._f(ops.to_nhwc(x))]
+
+
+class RBU(nn.Module):
+    """models/raw2bit.py:3181-3206 (ResidualBlockUpsample without IGDN)."""
+
+    def __init__(self, in_ch: int, out_ch: int, upsample: int = 2):
+        super().__init__()
+        self.subpel_conv = subpel_conv3x3(in_ch, out_ch, upsample)
+        self.leaky_relu = nn.LeakyReLU(inplace=True)
+        self.conv = conv3x3(out_ch, out_ch)
+        self.upsample = subpel_conv3x3(in_ch, out_ch, upsample)
+
+    def _f(self, x, out=None):
+        t = self.conv._f(self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01))
+        return self.upsample._f(x, res=t, out=out)
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+def _cc_transform(in_ch, out_ch):
+    return nn.Sequential(conv(in_ch, 224, stride=1, kernel_size=3), nn.GELU(), conv(224, 128, stride=1, kernel_size=3),
+                         nn.GELU(), conv(128, out_ch, stride=1, kernel_size=3))
+
+
+def _run_cc(seq, x, **last):
+    h = seq[0]._f(x, act=ACT_GELU)
+    h = seq[2]._f(h, act=ACT_GELU)
+    return seq[4]._f(h, **last)
+
+
+class raw_compression_tcm_final(CompressionModel):
+    """The paper model (models/raw2bit.py:1614-2027).
+
+    forward(x=[raw(B,4,H,W), cond(B,4,h',w'), coord(B,2,H,W)]) -> dict(x_hat, y, lft, lsc, likelihoods{y,z},
+    para{means,scales,y});  compress(x) -> {"strings": [[y_bytes], [z_bytes]*B], "shape"};
+    decompress(strings, shape) -> {"x_hat"};  update(scale_table=None, force=False).
+    """
+
+    def __init__(self, config=[2, 2, 2, 2, 2, 2, 2], head_dim=[8, 16, 32, 32, 16, 8, 8], drop_path_rate=0, N=64, M=320,
+                 num_slices=5, max_support_slices=5, **kwargs):
+        super().__init__()
+        if drop_path_rate:
+            raise NotImplementedError("inference path: drop_path_rate must be 0")
+        self.config, self.head_dim, self.window_size = config, head_dim, 8
+        self.num_slices, self.max_support_slices = num_slices, max_support_slices
+        dim, self.M, self.N = N, M, N
+        ws = self.window_size
+        cond_c, modulation_blocks = 128, 1
+        self.classifier = Color_Condition_GFM(in_channels=4, out_c=cond_c)
+        self.lsc = Lens_Shading_Correction(in_channels=2, out_c=2 * N, nf=2 * N)
+        self.local_condition = HybridConditionModule(out_channels=N, init_mid_channels=16)
+        self.conv_first = conv3x3(4, 2 * N)
+        self.conv_down = ResidualBlockWithStride(2 * N, 2 * N, 2)
+
+        def typ(i):
+            return 'W' if not i % 2 else 'SW'
+
+        def gfm():
+            return nn.Sequential(*[Res_GFM(in_nc=2 * N, chan=2 * N, cond_c=cond_c, nf=4 * N) for _ in range(modulation_blocks)])
+
+        self.gfm1 = gfm()
+        self.m_down1 = nn.Sequential(*[ConvTransBlock_mzj(dim, dim, head_dim[0], ws, 0, typ(i)) for i in range(config[0])])
+        self.m_down1_down = ResidualBlockWithStride(2 * N, 2 * N, stride=2)
+        self.gfm2 = gfm()
+        self.m_down2 = nn.Sequential(*[ConvTransBlock_mzj(dim, dim, head_dim[1], ws, 0, typ(i)) for i in range(config[1])])
+        self.m_down2_down = ResidualBlockWithStride(2 * N, 2 * N, stride=2)
+        self.gfm3 = gfm()
+        self.m_down3 = nn.Sequential(*[ConvTransBlock_mzj(dim, dim, head_dim[2], ws, 0, typ(i)) for i in range(config[2])])
+        self.m_down3_down = conv3x3(2 * N, M, stride=2)
+
+        m_up1 = [ConvTransBlock(dim, dim, head_dim[3], ws, 0, typ(i)) for i in range(config[3])] + [ResidualBlockUpsample(2 * N, 2 * N, 2)]
+        m_up2 = [ConvTransBlock(dim, dim, head_dim[4], ws, 0, typ(i)) for i in range(config[4])] + [ResidualBlockUpsample(2 * N, 2 * N, 2)]
+        m_up3 = [ConvTransBlock(dim, dim, head_dim[5], ws, 0, typ(i)) for i in range(config[5])] + [subpel_conv3x3(2 * N, 2 * N, 2)]
+        tail = [ResidualBlock(2 * N, 2 * N), subpel_conv3x3(2 * N, 3, 2)]
+        self.g_s = nn.Sequential(*[ResidualBlockUpsample(M, 2 * N, 2)] + m_up1 + m_up2 + m_up3 + tail)
+
+        self.h_a = nn.Sequential(*[ResidualBlockWithStride(320, 2 * N, 2)] +
+                                 [ConvTransBlock(N, N, 32, 4, 0, typ(i)) for i in range(config[0])] + [conv3x3(2 * N, 192, stride=2)])
+        self.h_mean_s = nn.Sequential(*[ResidualBlockUpsample(192, 2 * N, 2)] +
+                                      [ConvTransBlock(N, N, 32, 4, 0, typ(i)) for i in range(config[3])] + [subpel_conv3x3(2 * N, 320, 2)])
+        self.h_scale_s = nn.Sequential(*[ResidualBlockUpsample(192, 2 * N, 2)] +
+                                       [ConvTransBlock(N, N, 32, 4, 0, typ(i)) for i in range(config[3])] + [subpel_conv3x3(2 * N, 320, 2)])
+
+        sl = 320 // num_slices
+        self.atten_mean = nn.ModuleList(nn.Sequential(SWAtten(320 + sl * min(i, 5), 320 + sl * min(i, 5), 16, ws, 0, inter_dim=128))
+                                        for i in range(num_slices))
+        self.atten_scale = nn.ModuleList(nn.Sequential(SWAtten(320 + sl * min(i, 5), 320 + sl * min(i, 5), 16, ws, 0, inter_dim=128))
+                                         for i in range(num_slices))
+        self.cc_mean_transforms = nn.ModuleList(_cc_transform(320 + sl * min(i, 5), sl) for i in range(num_slices))
+        self.cc_scale_transforms = nn.ModuleList(_cc_transform(320 + sl * min(i, 5), sl) for i in range(num_slices))
+        self.lrp_transforms = nn.ModuleList(_cc_transform(320 + sl * min(i + 1, 6), sl) for i in range(num_slices))
+        self.entropy_bottleneck = EntropyBottleneck(192)
+        self.gaussian_conditional = GaussianConditional(None)
+
+    # ------------------------------------------------------------------------------ host logic
+    def update(self, scale_table=None, force=False):
+        if scale_table is None:
+            scale_table = get_scale_table()
+        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
+        updated |= super().update(force=force)
+        return updated
+
+    def load_state_dict(self, state_dict, strict=True):
+        """models/raw2bit.py:1857-1864: size the CDF buffers from the checkpoint first."""
+        gc = self.gaussian_conditional
+        for name in ("_quantized_cdf", "_offset", "_cdf_length", "scale_table"):
+            key = f"gaussian_conditional.{name}"
+            if key not in state_dict:
+                continue
+            buf = getattr(gc, name)
+            if buf.numel() == 0:
+                buf.resize_(state_dict[key].size())
+        eb = self.entropy_bottleneck
+        for name in ("_quantized_cdf", "_offset", "_cdf_length"):
+            key = f"entropy_bottleneck.{name}"
+            if key in state_dict and getattr(eb, name).numel() == 0:
+                getattr(eb, name).resize_(state_dict[key].size())
+        return super().load_state_dict(state_dict, strict=strict)
+
+    def _scale_table_dev(self):
+        gc = self.gaussian_conditional
+        if gc.scale_table.numel() == 0:  # forward() before update(): likelihoods do not need the table
+            gc.scale_table = get_scale_table().to(gc.scale_bound.device)
+        return gc.scale_table
+
+    # ------------------------------------------------------------------------------ transforms (NHWC)
+    def _analysis(self, x):
+        """models/raw2bit.py:1771-1796 (and 1877-1901 in compress)."""
+        raw, cond, coord = ops.to_nhwc(x[0]), ops.to_nhwc(x[1]), ops.to_nhwc(x[2])
+        vec = self.classifier._f(cond)                                  # (B,1,1,128) gfm_vector
+        lsc_fea = self.lsc._f(coord)
+        local = self.local_condition._f(raw)
+        fea = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea)   # conv_first(x) * (lsc + 1)
+        fea = self.conv_down._f(fea)
+        for lvl, (gfm, blocks, down) in enumerate(((self.gfm1, self.m_down1, self.m_down1_down),
+                                                   (self.gfm2, self.m_down2, self.m_down2_down),
+                                                   (self.gfm3, self.m_down3, self.m_down3_down))):
+            for g in gfm:
+                fea = g._f(fea, vec)
+            for blk in blocks:
+                fea = blk._f(fea, local[lvl])
+            fea = down._f(fea)
+        return fea, lsc_fea, local
+
+    def _h_a(self, y):
+        z = self.h_a[0]._f(y)
+        for blk in list(self.h_a)[1:-1]:
+            z = blk._f(z)
+        return self.h_a[-1]._f(z)
+
+    def _h_s(self, net, z_hat, out):
+        h = net[0]._f(z_hat)
+        for blk in list(net)[1:-1]:
+            h = blk._f(h)
+        return net[-1]._f(h, out=out)
+
+    def _g_s(self, y_hat, clamp=False):
+        h = y_hat
+        mods = list(self.g_s)
+        for m in mods[:-1]:
+            h = m._f(h)
+        return mods[-1]._f(h, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
+
+    def _alloc_supports(self, z_hat):
+        N, hz, wz, _ = z_hat.shape
+        h, w = hz * 4, wz * 4
+        tot = 320 + (320 // self.num_slices) * self.num_slices
+        ms = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_means] + y_hat_slices)
+        ss = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_scales] + y_hat_slices)
+        self._h_s(self.h_scale_s, z_hat, ss[..., :320])
+        self._h_s(self.h_mean_s, z_hat, ms[..., :320])
+        return ms, ss, h, w
+
+    def _slice_params(self, i, ms, ss):
+        """raw2bit.py:1818-1828: returns (lrp_support buffer, mu, scale)."""
+        sl = 320 // self.num_slices
+        cin = 320 + sl * min(i, self.max_support_slices if self.max_support_slices >= 0 else i)
+        N, h, w, _ = ms.shape
+        lrp_sup = ops.empty(N, h, w, cin + sl, like=ms)                 # cat([mean_support, y_hat_slice])
+        mean_support = self.atten_mean[i][0]._f(ms[..., :cin], out=lrp_sup[..., :cin])
+        mu = _run_cc(self.cc_mean_transforms[i], mean_support)
+        scale_support = self.atten_scale[i][0]._f(ss[..., :cin])
+        scale = _run_cc(self.cc_scale_transforms[i], scale_support)
+        return lrp_sup, cin, mu, scale
+
+    def _finish_slice(self, i, lrp_sup, cin, ms, ss):
+        """y_hat_slice += 0.5*tanh(lrp(...)) written into both support buffers (raw2bit.py:1835-1840)."""
+        sl = 320 // self.num_slices
+        dst = ms[..., 320 + sl * i: 320 + sl * (i + 1)]
+        _run_cc(self.lrp_transforms[i], lrp_sup, act=ACT_HALF_TANH, res=lrp_sup[..., cin:], out=dst)
+        ops.copy_channels(dst, ss[..., 320 + sl * i: 320 + sl * (i + 1)])
+
+    # ------------------------------------------------------------------------------ public API
+    @torch.no_grad()
+    def forward(self, x, emit_strings=False):
+        if self.training:
+            raise NotImplementedError("inference path only: call .eval() (train mode adds quantisation noise)")
+        y, lsc_fea, local = self._analysis(x)
+        z = self._h_a(y)
+        z_hat, z_lik, z_sym = self.entropy_bottleneck._f(z, want_symbols=emit_strings)
+        ms, ss, h, w = self._alloc_supports(z_hat)
+        N = y.shape[0]
+        sl = 320 // self.num_slices
+        table = self._scale_table_dev()
+        gc = self.gaussian_conditional
+        means = ops.empty(N, h, w, 320, like=y)
+        scales = ops.empty(N, h, w, 320, like=y)
+        y_lik = ops.empty(N, h, w, 320, like=y)
+        if emit_strings:
+            sym = torch.empty((self.num_slices, N * sl * h * w), device=y.device, dtype=torch.int32)
+            idx = torch.empty_like(sym)
+        for i in range(self.num_slices):
+            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
+            ops.copy_channels(mu, means[..., sl * i: sl * (i + 1)])
+            ops.copy_channels(scale, scales[..., sl * i: sl * (i + 1)])
+            ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
+                                     lik=y_lik[..., sl * i: sl * (i + 1)],
+                                     symbols=sym[i] if emit_strings else None, indexes=idx[i] if emit_strings else None,
+                                     scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound)
+            self._finish_slice(i, lrp_sup, cin, ms, ss)
+        x_hat = self._g_s(ms[..., 320:])
+        y_nchw = ops.to_nchw(y)
+        out = {"x_hat": x_hat, "y": y_nchw, "lft": ops.to_nchw(local[2]), "lsc": ops.to_nchw(lsc_fea),
+               "likelihoods": {"y": ops.to_nchw(y_lik), "z": ops.to_nchw(z_lik)},
+               "para": {"means": ops.to_nchw(means), "scales": ops.to_nchw(scales), "y": y_nchw}}
+        if emit_strings:
+            out["strings"] = [[self._encode_y(sym, idx)], self.entropy_bottleneck.compress_symbols(z_sym)]
+            out["shape"] = torch.Size(z.shape[1:3])
+        return out
+
+    def _encode_y(self, sym, idx):
+        cdf, length, offset = self.gaussian_conditional.host_tables()
+        return rans_encode(sym.cpu().numpy().reshape(-1), idx.cpu().numpy().reshape(-1), cdf, length, offset)
+
+    @torch.no_grad()
+    def compress(self, x):
+        """models/raw2bit.py:1876-1960."""
+        if self.gaussian_conditional._offset.numel() == 0:
+            raise RuntimeError("call update() before compress()")
+        y, _, _ = self._analysis(x)
+        z = self._h_a(y)
+        z_hat, _, z_sym = self.entropy_bottleneck._f(z, want_symbols=True, want_lik=False)
+        z_strings = self.entropy_bottleneck.compress_symbols(z_sym)
+        ms, ss, h, w = self._alloc_supports(z_hat)
+        N = y.shape[0]
+        sl = 320 // self.num_slices
+        gc = self.gaussian_conditional
+        table = self._scale_table_dev()
+        sym = torch.empty((self.num_slices, N * sl * h * w), device=y.device, dtype=torch.int32)
+        idx = torch.empty_like(sym)
+        for i in range(self.num_slices):
+            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
+            ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
+                                     symbols=sym[i], indexes=idx[i], scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound)
+            self._finish_slice(i, lrp_sup, cin, ms, ss)
+        return {"strings": [[self._encode_y(sym, idx)], z_strings], "shape": torch.Size(z.shape[1:3])}
+
+    @torch.no_grad()
+    def decompress(self, strings, shape):
+        """models/raw2bit.py:1982-2027 (batch 1, like the reference)."""
+        if self.gaussian_conditional._offset.numel() == 0:
+            raise RuntimeError("call update() before decompress()")
+        z_hat = self.entropy_bottleneck._decompress_nhwc(strings[1], shape)
+        ms, ss, h, w = self._alloc_supports(z_hat)
+        N = z_hat.shape[0]
+        sl = 320 // self.num_slices
+        gc = self.gaussian_conditional
+        table = self._scale_table_dev()
+        cdf, length, offset = gc.host_tables()
+        dec = RansDecoder()
+        dec.set_stream(strings[0][0])
+        idx = torch.empty((N, sl, h, w), device=z_hat.device, dtype=torch.int32)
+        for i in range(self.num_slices):
+            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
+            ops.build_indexes(scale, table, idx, gc._scale_bound)
+            rv = dec.decode_stream(idx.cpu().numpy(), cdf, length, offset)
+            rv = torch.from_numpy(rv).to(z_hat.device)
+            ops.gaussian_dequantize(rv, mu, lrp_sup[..., cin:])
+            self._finish_slice(i, lrp_sup, cin, ms, ss)
+        dec.close()
+        return {"x_hat": self._g_s(ms[..., 320:], clamp=True)}

@@ -1,0 +1,119 @@
+"""CPU checks of the drop-in boundary: the C-ABI library loads and exports every symbol declared in
+include/rcn_b200.h, and the host mirrors expose the reference's parameter names/shapes."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rcn_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rcn_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from realcamnet_b200 import _C
+
+    lib = _C.lib()
+    names = _declared_symbols()
+    assert len(names) >= 30
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in rcn_b200.h but not exported"
+        assert n in _C.PROTOTYPES, f"{n} has no ctypes prototype"
+    assert lib.rcn_version() >= 100
+
+
+def test_host_range_coder_matches_oracle_bytes():
+    """The native C++ coder is host code: its bytes can be checked against the oracle without a GPU."""
+    import numpy as np
+
+    from oracle import cai, rans, refpath
+    from realcamnet_b200 import entropy_models as em
+
+    gc = cai.GaussianConditional(None)
+    gc.update_scale_table(cai.get_scale_table())
+    cdf, sizes, offs = refpath._tables(gc)
+    g = np.random.default_rng(5)
+    n = 50000
+    sigma = np.exp(g.uniform(np.log(0.11), np.log(64), n)).astype(np.float32)
+    sym = np.round(sigma * g.standard_normal(n)).astype(np.int32)
+    esc = g.random(n) < 0.001
+    sym[esc] = g.choice([-5000, 5000, -70000, 70000, 2 ** 30], size=int(esc.sum()))
+    idx = gc.build_indexes(torch.from_numpy(sigma)).numpy().astype(np.int32)
+    ours = em.rans_encode(sym, idx, cdf, sizes, offs)
+    assert ours == refpath.encode_stream(sym, idx, gc)
+    assert ours[:4096] == rans.encode_with_indexes(sym, idx, cdf.tolist(), sizes, offs)[:4096]
+    d = em.RansDecoder()
+    d.set_stream(ours)
+    a = d.decode_stream(idx[:1234], cdf, sizes, offs)
+    b = d.decode_stream(idx[1234:], cdf, sizes, offs)
+    assert np.array_equal(np.concatenate([a, b]), sym)
+    assert em.rans_encode(np.zeros(0, np.int32), np.zeros(0, np.int32), cdf, sizes, offs) == bytes([0, 0, 0, 0x80, 0, 0, 0, 0])
+
+
+def test_native_cdf_quantiser_matches_oracle():
+    import numpy as np
+
+    from oracle import rans
+    from realcamnet_b200 import entropy_models as em
+
+    g = np.random.default_rng(0)
+    for n in (3, 17, 200, 3131):
+        p = g.random(n).astype(np.float32) ** 8
+        p[g.random(n) < 0.3] = 0
+        p[0] = max(p[0], 1e-3)
+        p /= p.sum()
+        assert em.pmf_to_quantized_cdf(p).tolist() == rans.pmf_to_quantized_cdf(p)
+
+
+def test_update_builds_the_oracle_tables():
+    from oracle import cai, weights
+    from realcamnet_b200 import entropy_models as em
+    from realcamnet_b200.tcm import get_scale_table
+
+    gc = em.GaussianConditional(None)
+    gc.update_scale_table(get_scale_table())
+    ref = cai.GaussianConditional(None)
+    ref.update_scale_table(cai.get_scale_table())
+    assert torch.equal(gc.quantized_cdf, ref.quantized_cdf)
+    assert torch.equal(gc.cdf_length, ref.cdf_length) and torch.equal(gc.offset, ref.offset)
+    eb, reb = em.EntropyBottleneck(192), cai.EntropyBottleneck(192)
+    weights.fill_(eb, seed=3)
+    reb.load_state_dict(eb.state_dict())
+    eb.update(), reb.update()
+    assert torch.equal(eb.quantized_cdf, reb.quantized_cdf) and torch.equal(eb.offset, reb.offset)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference only exists in the authoring container")
+@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200"])
+def test_state_dict_names_match_reference(which):
+    from oracle import ref_import
+
+    ref = ref_import.import_reference()
+    from realcamnet_b200 import LiteISP, groupmix, raw2bit
+
+    if which == "final":
+        a, b = ref.raw2bit.raw_compression_tcm_final(), raw2bit.raw_compression_tcm_final()
+    elif which == "liteisp":
+        a, b = ref.LiteISP.LiteISPNet_GFM_LSC(), LiteISP.LiteISPNet_GFM_LSC()
+    else:
+        dim = int(which[3:])
+        a, b = ref.groupmix.GMA_Block(dim, 8), groupmix.GMA_Block(dim, 8)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa.keys()) == list(sb.keys())
+    for k in sa:
+        assert tuple(sa[k].shape) == tuple(sb[k].shape), k
+    b.load_state_dict(sa)  # a reference checkpoint loads into the mirror
+
+
+def test_product_fails_loudly_without_library(monkeypatch):
+    from realcamnet_b200 import _C
+
+    monkeypatch.setattr(_C, "_lib", None)
+    monkeypatch.setattr(_C, "LIB_PATH", "/nonexistent/librcn_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _C.lib()
