@@ -247,11 +247,17 @@ def _eb(sd, p="entropy_bottleneck"):
     return eb
 
 
+_GC_CACHE = []
+
+
 def _gc():
-    gc = _cai.GaussianConditional(None)
-    gc.update_scale_table(_cai.get_scale_table())
-    gc.eval()
-    return gc
+    """GaussianConditional with the default scale table; the tables are constants, so update() runs once."""
+    if not _GC_CACHE:
+        gc = _cai.GaussianConditional(None)
+        gc.update_scale_table(_cai.get_scale_table())
+        gc.eval()
+        _GC_CACHE.append(gc)
+    return _GC_CACHE[0]
 
 
 # ----------------------------------------------------------------------------- raw_compression_tcm_final
