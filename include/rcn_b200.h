@@ -194,6 +194,20 @@ int rcn_groupmix_attention(const float* q, int ldq, const float* k, int ldk, con
                            float* out, int ldo, float* kv_out, float* workspace, long long workspace_floats,
                            void* stream);
 
+/* ---- tcgen05 / TMA convolution engine ---------------------------------------------------------------- */
+/* Same contraction + fused epilogue as rcn_conv2d (d->x, d->w, d->in_square are ignored), but the operands
+ * are bf16 planes fetched by TMA and multiplied by tcgen05.mma with fp32 accumulators in TMEM.
+ *   x_hi/x_lo : (N,H,W,Cp) bf16 planes from rcn_split_bf16 (x = hi + lo; lo may be NULL when passes == 1)
+ *   w_hi/w_lo : [Cout][k*k][Cp] bf16 from rcn_pack_conv_weight_tc
+ *   passes    : 1 = bf16 (hi*hi) ; 3 = "bf16x3" (hi*hi + lo*hi + hi*lo, ~fp32-grade products)
+ * stride must be 1 (strided layers stay on rcn_conv2d); Cp is a multiple of 64. */
+int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                  int Cp, int passes, void* stream);
+/* fp32 NHWC (pixel stride ldx) -> zero-padded bf16 hi/lo planes; square != 0 feeds x*x (GDN norm pool) */
+int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream);
+/* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand) */
+int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

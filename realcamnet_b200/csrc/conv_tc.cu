@@ -1,0 +1,501 @@
+// tcgen05 / TMA implicit-GEMM convolution engine (sm_100a).
+//
+// GEMM view per CTA: D[128 pixels x Ntile channels] += A[128 x 64] * B[Ntile x 64]^T over
+// (tap, 64-channel chunk) k-iterations.  A tiles are 8x16-pixel boxes of the NHWC bf16 activation
+// planes fetched by TMA (one shifted box per filter tap -- im2col-free; out-of-image pixels are
+// zero-filled by the TMA unit = the conv's zero padding); B tiles come from the K-major packed
+// weights.  Both land in shared memory in the 128B-swizzled K-major canonical layout that
+// tcgen05.mma consumes directly; accumulators live in TMEM (fp32) and are drained with tcgen05.ld
+// into the same fused epilogue as the fp32 engine (conv.cu).
+//
+// Precision modes (passes): 1 = bf16 x bf16 (fp32 accumulate); 3 = "bf16x3": activations and
+// weights are split as x = hi + lo (two bf16 planes) and hi*hi + lo*hi + hi*lo is accumulated in
+// fp32 -- ~16 mantissa bits, which keeps the 1e-3 parity bar through the ~100-layer path.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  mbarrier ring: full[s] (TMA -> MMA),
+// empty[s] (tcgen05.commit -> TMA), tmem_full (last commit -> epilogue).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace rcn {
+namespace {
+
+constexpr int TILE_H = 8, TILE_W = 16, BLOCK_K = 64;
+constexpr int A_BYTES = 128 * BLOCK_K * 2;  // 16 KB
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    return d;
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TcParams {
+    rcn_conv_desc d;
+    int Cp;       // padded input channels (multiple of 64) of the bf16 planes / packed weights
+    int Ntile;    // output channels per CTA (multiple of 16, <= 128)
+    int tiles_x, tiles_y;
+    int passes;   // 1 or 3
+    int stages;
+    int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
+};
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const rcn_conv_desc& p = P.d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B_BYTES = P.Ntile * BLOCK_K * 2;
+    const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
+    // stage_bytes is a multiple of 1024 because Ntile % 16 == 0 -> B_BYTES % 2048 == 0
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* empty_bar = full_bar + P.stages;
+    uint64_t* tmem_full = empty_bar + P.stages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    // tile coordinates
+    int t = blockIdx.x;
+    const int tx = t % P.tiles_x; t /= P.tiles_x;
+    const int ty = t % P.tiles_y;
+    const int n = t / P.tiles_y;
+    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
+    const int n0 = blockIdx.y * P.Ntile;
+    const int pad = p.k >> 1;
+    const int chunks = P.Cp / BLOCK_K;
+    const int kiters = p.k * p.k * chunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            const uint32_t tx_bytes = (uint32_t)stage_bytes;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int it = 0; it < kiters; ++it) {
+                const int tap = it / chunks, ch = it - tap * chunks;
+                const int ky = tap / p.k, kx = tap - ky * p.k;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                const bool loadA = !(P.dbg & 4);
+                mbar_expect_tx(&full_bar[stage], loadA ? tx_bytes : (uint32_t)((P.passes == 3 ? 2 : 1) * B_BYTES));
+                if (loadA) tma_load_4d(sa, &map_a_hi, &full_bar[stage], ch * BLOCK_K, x0 + kx - pad, y0 + ky - pad, n);
+                tma_load_2d(sa + A_BYTES, &map_w_hi, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+                if (P.passes == 3) {
+                    if (loadA) tma_load_4d(sa + A_BYTES + B_BYTES, &map_a_lo, &full_bar[stage], ch * BLOCK_K, x0 + kx - pad, y0 + ky - pad, n);
+                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+                }
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            int nact = p.Cout - n0;
+            if (nact > P.Ntile) nact = P.Ntile;
+            nact = (nact + 15) & ~15;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int stage = 0;
+            uint32_t phase = 0;
+            uint32_t acc = 0;
+            for (int it = 0; it < kiters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                const uint64_t a_hi = make_sw128_desc(sa), b_hi = make_sw128_desc(sa + A_BYTES);
+                const uint64_t a_lo = make_sw128_desc(sa + A_BYTES + B_BYTES), b_lo = make_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int j = 0; j < ((P.dbg & 2) ? 0 : BLOCK_K / 16); ++j) {
+                    const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
+                    if (P.passes == 3) {
+                        umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, acc);
+                        acc = 1;
+                        umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
+                    }
+                    umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
+                    acc = 1;
+                }
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+            }
+            umma_commit(tmem_full);
+        }
+        __syncwarp();
+    } else {
+        // ================= epilogue: TMEM -> smem staging -> fused element-wise -> coalesced global =================
+        // The accumulator tile is first parked in shared memory (the operand ring is idle by now: every TMA write
+        // was consumed by an MMA that has retired), then re-read with lanes running along channels so that global
+        // loads/stores are full 128 B lines and the element-wise code is one compact loop (no 32x unrolled copy of
+        // the activation switch -> no instruction-cache thrash).
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int m = q * 32 + lane;
+        const int Ho = p.H, Wo = p.W;  // stride 1, same padding
+        mbar_wait(tmem_full, 0);
+        tc_fence_after();
+        int ncols = p.Cout - n0;
+        if (ncols > P.Ntile) ncols = P.Ntile;
+        const int NS = P.Ntile + 4;  // row pitch (floats): (NS/4) odd -> conflict-free float4 rows
+        float* stg = reinterpret_cast<float*>(smem);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
+            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            float4* dst = reinterpret_cast<float4*>(stg + m * NS + c0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c0 + 4 * i < P.Ntile)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                         __uint_as_float(v[4 * i + 3]));
+        }
+        tc_fence_before();
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+        const int et = threadIdx.x - 64;
+        const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
+        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? p.Cout / 4 : p.Cout;
+        const bool vec = !(P.dbg & 8) && (p.store == RCN_STORE_NHWC) && ((p.Cout & 3) == 0) && ((p.ldy & 3) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
+                         (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
+                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+        if (vec) {
+            const int groups = ncols >> 2;
+            const int total = 128 * groups;
+#pragma unroll 1
+            for (int e = et; e < total; e += 128) {
+                const int row = e / groups, g4 = (e - row * groups) * 4;
+                const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
+                if (ho >= Ho || wo >= Wo) continue;
+                const int c = n0 + g4;
+                const long long pix = ((long long)n * Ho + ho) * Wo + wo;
+                float4 a4 = *reinterpret_cast<const float4*>(stg + row * NS + g4);
+                float val[4] = {a4.x, a4.y, a4.z, a4.w};
+                if (p.bias) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                    val[0] += b4.x; val[1] += b4.y; val[2] += b4.z; val[3] += b4.w;
+                }
+                if (p.cscale) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c + j)) + __ldg(p.cshift + n * p.Cout + c + j);
+                }
+                if (p.epi != RCN_EPI_NONE) {
+                    const float4 x4 = *reinterpret_cast<const float4*>(p.aux + pix * p.ldaux + c);
+                    const float ax[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        switch (p.epi) {
+                            case RCN_EPI_GDN: val[j] = ax[j] * rsqrtf(val[j]); break;
+                            case RCN_EPI_IGDN: val[j] = ax[j] * sqrtf(val[j]); break;
+                            case RCN_EPI_MUL_AUXP1: val[j] = val[j] * (ax[j] + 1.f); break;
+                            case RCN_EPI_MULP1_AUX: val[j] = (val[j] + 1.f) * ax[j]; break;
+                            case RCN_EPI_SIGMOID_GATE: val[j] = ax[j] * (1.f / (1.f + expf(-val[j]))); break;
+                            default: break;
+                        }
+                    }
+                }
+                float rv[4] = {0.f, 0.f, 0.f, 0.f};
+                if (p.res) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldres + c);
+                    rv[0] = p.res_scale * r4.x; rv[1] = p.res_scale * r4.y; rv[2] = p.res_scale * r4.z; rv[3] = p.res_scale * r4.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (p.res && p.res_pre) val[j] += rv[j];
+                    val[j] = act_apply(val[j], p.act, p.slope);
+                    if (p.res && !p.res_pre) val[j] += rv[j];
+                }
+                if (!(P.dbg & 1)) *reinterpret_cast<float4*>(p.y + pix * p.ldy + c) = make_float4(val[0], val[1], val[2], val[3]);
+            }
+        } else if (!(P.dbg & 8)) {
+            const int total = 128 * ncols;
+#pragma unroll 1
+            for (int e = et; e < total; e += 128) {
+                const int row = e / ncols, col = e - row * ncols;
+                const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
+                if (ho >= Ho || wo >= Wo) continue;
+                const int c = n0 + col;
+                const long long mpix = ((long long)n * Ho + ho) * Wo + wo;
+                float val = stg[row * NS + col];
+                if (p.bias) val += __ldg(p.bias + c);
+                if (p.cscale) val = val * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
+                if (p.epi != RCN_EPI_NONE) {
+                    const float a = p.aux[mpix * p.ldaux + c];
+                    switch (p.epi) {
+                        case RCN_EPI_GDN: val = a * rsqrtf(val); break;
+                        case RCN_EPI_IGDN: val = a * sqrtf(val); break;
+                        case RCN_EPI_MUL_AUXP1: val = val * (a + 1.f); break;
+                        case RCN_EPI_MULP1_AUX: val = (val + 1.f) * a; break;
+                        case RCN_EPI_SIGMOID_GATE: val = a * (1.f / (1.f + expf(-val))); break;
+                        default: break;
+                    }
+                }
+                int hh = ho, ww = wo, cc = c;
+                if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
+                const long long pix = ((long long)n * Hs + hh) * Ws + ww;
+                float rv = 0.f;
+                if (p.res) rv = p.res_scale * p.res[pix * p.ldres + cc];
+                if (p.res && p.res_pre) val += rv;
+                val = act_apply(val, p.act, p.slope);
+                if (p.res && !p.res_pre) val += rv;
+                if (!(P.dbg & 1)) {
+                    if (p.store == RCN_STORE_NCHW || p.store == RCN_STORE_PS2_NCHW)
+                        p.y[(((long long)n * Cs + cc) * Hs + hh) * Ws + ww] = val;
+                    else
+                        p.y[pix * p.ldy + cc] = val;
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+    }
+}
+
+// ---------------------------------------------------------------- operand preparation
+// fp32 NHWC (ld) -> bf16 hi / lo planes (npix, Cp), zero-padded channels; optional x*x (GDN)
+__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long long npix, int C, int Cp, int square,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long total = npix * (Cp / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % (Cp / 4)) * 4;
+        const long long pix = i / (Cp / 4);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c4 + j;
+            float t = (c < C) ? x[pix * ldx + c] : 0.f;
+            v[j] = square ? t * t : t;
+        }
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            h[j] = __float2bfloat16_rn(v[j]);
+            l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+        }
+        *reinterpret_cast<uint2*>(hi + pix * Cp + c4) = *reinterpret_cast<uint2*>(h);
+        if (lo) *reinterpret_cast<uint2*>(lo + pix * Cp + c4) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// OIHW fp32 -> [Cout][k*k][Cp] bf16 hi / lo (K-major rows for the B operand)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp,
+                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const long long total = (long long)Cout * k * k * Cp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % Cp);
+        long long t = i / Cp;
+        const int tap = (int)(t % (k * k));
+        const int co = (int)(t / (k * k));
+        const float v = (c < Cin) ? w[((long long)co * Cin + c) * k * k + tap] : 0.f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+bool make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cp) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
+    cuuint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int Ntile) {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)Ntile};
+    cuuint32_t es[2] = {1, 1};
+    return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+}  // namespace rcn
+
+using namespace rcn;
+
+extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && Cp % 64 == 0, "rcn_split_bf16: bad arguments");
+    const long long total = npix * (Cp / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    split_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, npix, C, Cp, square, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_split_bf16");
+    return RCN_OK;
+}
+
+extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && Cp % 64 == 0, "rcn_pack_conv_weight_tc: bad arguments");
+    const long long total = (long long)Cout * k * k * Cp;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 4096) blocks = 4096;
+    pack_weight_tc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, k, Cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_pack_conv_weight_tc");
+    return RCN_OK;
+}
+
+extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int Cp,
+                             int passes, void* stream) {
+    RCN_CHECK_ARG(d && d->y && x_hi && w_hi, "rcn_conv2d_tc: null pointer");
+    RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
+    RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
+    RCN_CHECK_ARG(d->stride == 1, "rcn_conv2d_tc: stride %d unsupported (use rcn_conv2d)", d->stride);
+    RCN_CHECK_ARG(Cp % 64 == 0 && Cp >= d->Cin, "rcn_conv2d_tc: Cp must be a multiple of 64 >= Cin");
+    RCN_CHECK_ARG(d->epi == RCN_EPI_NONE || d->aux, "rcn_conv2d_tc: epilogue needs aux");
+    RCN_CHECK_ARG(get_encode() != nullptr, "rcn_conv2d_tc: cuTensorMapEncodeTiled is not available from the driver");
+    const bool ps = d->store == RCN_STORE_PS2 || d->store == RCN_STORE_PS2_NCHW;
+    RCN_CHECK_ARG(!ps || (d->Cout % 4 == 0), "rcn_conv2d_tc: pixel shuffle needs Cout %% 4 == 0");
+    TcParams P;
+    P.d = *d;
+    P.Cp = Cp;
+    P.passes = passes;
+    int nt = d->Cout >= 128 ? 128 : ((d->Cout + 15) & ~15);
+    P.Ntile = nt;
+    P.tiles_x = (d->W + TILE_W - 1) / TILE_W;
+    P.tiles_y = (d->H + TILE_H - 1) / TILE_H;
+    const int stage_bytes = (passes == 3 ? 2 : 1) * (A_BYTES + nt * BLOCK_K * 2);
+    int stages = (200 * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
+    if (stages < 2) stages = 2;
+    P.stages = stages;
+    {
+        const char* e = getenv("RCN_TC_DEBUG");
+        P.dbg = e ? atoi(e) : 0;
+        const char* st = getenv("RCN_TC_STAGES");
+        if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
+    }
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    const long long Ktot = (long long)d->k * d->k * Cp;
+    bool ok = make_act_map(&ma_hi, x_hi, d->N, d->H, d->W, Cp) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt);
+    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, d->N, d->H, d->W, Cp) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt);
+    else { ma_lo = ma_hi; mw_lo = mw_hi; }
+    RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    const long long gx = (long long)P.tiles_x * P.tiles_y * d->N;
+    RCN_CHECK_ARG(gx < 2147483647LL, "rcn_conv2d_tc: too many tiles");
+    dim3 grid((unsigned)gx, (d->Cout + nt - 1) / nt);
+    conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_conv2d_tc");
+    return RCN_OK;
+}

@@ -8,6 +8,7 @@ how torch.cat/torch.split of the reference are expressed without copies.
 from __future__ import annotations
 
 import ctypes
+import os
 import weakref
 
 import torch
@@ -64,12 +65,32 @@ def launch_count() -> int:
     return int(_C.lib().rcn_launch_count())
 
 
+# ----------------------------------------------------------------------------- conv engine selection
+# "fp32"   : CUDA-core FFMA implicit GEMM (rcn_conv2d) for every layer -- exact-parity engine
+# "bf16x3" : tcgen05 engine with hi/lo split operands (3 MMAs per product, ~fp32-grade) where eligible
+# "bf16"   : tcgen05 engine, single bf16 pass (fast mode; does NOT meet the 1e-3 parity bar end to end)
+_ENGINE = os.environ.get("RCN_CONV_ENGINE", "fp32")
+_TC_MIN_CIN = 16
+
+
+def set_engine(name: str):
+    global _ENGINE
+    if name not in ("fp32", "bf16x3", "bf16"):
+        raise ValueError(f"unknown conv engine {name!r}")
+    _ENGINE = name
+
+
+def get_engine() -> str:
+    return _ENGINE
+
+
 # ----------------------------------------------------------------------------- weights
 class PackedConv:
-    __slots__ = ("w", "bias", "k", "cin", "cout")
+    __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo")
 
-    def __init__(self, w, bias, k, cin, cout):
+    def __init__(self, w, bias, k, cin, cout, cp=0, w_hi=None, w_lo=None):
         self.w, self.bias, self.k, self.cin, self.cout = w, bias, k, cin, cout
+        self.cp, self.w_hi, self.w_lo = cp, w_hi, w_lo
 
 
 _pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
@@ -88,7 +109,16 @@ def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
     out = torch.empty((k * k * cin, cout), device=w.device, dtype=torch.float32)
     _C.check(_C.lib().rcn_pack_conv_weight(_ptr(w), cout, cin, k, _ptr(out), _stream()), "rcn_pack_conv_weight")
     b = bias.detach().contiguous() if bias is not None else None
-    return PackedConv(out, b, k, cin, cout)
+    pc = PackedConv(out, b, k, cin, cout)
+    if k in (1, 3) and cin >= _TC_MIN_CIN:
+        # tcgen05 operand: [Cout][k*k][Cp] bf16 hi/lo, Cp = Cin rounded up to the 64-channel K chunk
+        cp = (cin + 63) // 64 * 64
+        pc.cp = cp
+        pc.w_hi = torch.empty((cout, k * k * cp), device=w.device, dtype=torch.bfloat16)
+        pc.w_lo = torch.empty_like(pc.w_hi)
+        _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(w), cout, cin, k, cp, _ptr(pc.w_hi), _ptr(pc.w_lo), _stream()),
+                 "rcn_pack_conv_weight_tc")
+    return pc
 
 
 def pack(module) -> PackedConv:
@@ -105,7 +135,7 @@ def pack(module) -> PackedConv:
 
 # ----------------------------------------------------------------------------- conv / linear
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
-           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0):
+           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None):
     N, H, W, Cin, ldx = geom(x, "conv2d.x")
     if Cin != pc.cin:
         raise ValueError(f"conv2d: input has {Cin} channels, weight expects {pc.cin}")
@@ -149,6 +179,17 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
             raise ValueError(f"conv2d: residual shape {tuple(res.shape)} != {(N, Hs, Ws, Cs)}")
         d.res, d.ldres, d.res_pre = res.data_ptr(), ldr, int(res_pre)
     d.act, d.slope, d.res_scale = act, float(slope), float(res_scale)
+    eng = engine or _ENGINE
+    if eng != "fp32" and stride == 1 and pc.w_hi is not None:
+        # tcgen05 path: split the fp32 activations into bf16 hi/lo planes (x*x for the GDN pool), TMA + UMMA conv
+        passes = 3 if eng == "bf16x3" else 1
+        hi = torch.empty((N, H, W, pc.cp), device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if passes == 3 else None
+        _C.check(_C.lib().rcn_split_bf16(_ptr(x), ldx, N * H * W, Cin, pc.cp, int(in_square), _ptr(hi), _ptr(lo), _stream()),
+                 "rcn_split_bf16")
+        _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(hi), _ptr(lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
+                                        _stream()), "rcn_conv2d_tc")
+        return out
     _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")
     return out
 
