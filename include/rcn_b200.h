@@ -200,11 +200,14 @@ int rcn_groupmix_attention(const float* q, int ldq, const float* k, int ldk, con
  *   x_hi/x_lo : (N,H,W,Cp) bf16 planes from rcn_split_bf16 (x = hi + lo; lo may be NULL when passes == 1)
  *   w_hi/w_lo : [Cout][k*k][Cp] bf16 from rcn_pack_conv_weight_tc
  *   passes    : 1 = bf16 (hi*hi) ; 3 = "bf16x3" (hi*hi + lo*hi + hi*lo, ~fp32-grade products)
- * stride must be 1 (strided layers stay on rcn_conv2d); Cp is a multiple of 64. */
+ * stride 1: planes from rcn_split_bf16; stride 2 (even H, W): planes from rcn_split_bf16_s2.  Cp is a multiple of 64. */
 int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                   int Cp, int passes, void* stream);
 /* fp32 NHWC (pixel stride ldx) -> zero-padded bf16 hi/lo planes; square != 0 feeds x*x (GDN norm pool) */
 int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream);
+/* stride-2 layers: the four polyphase planes x[:, py::2, px::2, :] as (4N, H/2, W/2, Cp) bf16 hi/lo, plane index
+ * (py*2+px)*N + n -- each filter tap of a stride-2 conv then reads ONE plane at unit stride (TMA box per tap). */
+int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream);
 /* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand) */
 int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream);
 

@@ -35,6 +35,7 @@ PROTOTYPES = {
     "rcn_conv2d": (_I, [POINTER(ConvDesc), _P]),
     "rcn_conv2d_tc": (_I, [POINTER(ConvDesc), _P, _P, _P, _P, _I, _I, _P]),
     "rcn_split_bf16": (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
+    "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P]),

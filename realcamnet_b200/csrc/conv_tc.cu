@@ -109,13 +109,146 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
 struct TcParams {
     rcn_conv_desc d;
     int Cp;       // padded input channels (multiple of 64) of the bf16 planes / packed weights
-    int Ntile;    // output channels per CTA (multiple of 16, <= 128)
-    int tiles_x, tiles_y;
+    int Ntile;    // output channels per tile (multiple of 16, <= 128)
+    int tiles_x, tiles_y, tiles_n;
+    long long total_tiles;
     int passes;   // 1 or 3
     int stages;
+    int s2;       // stride-2 conv: A planes are the 4 polyphase components stacked on the batch axis ((py*2+px)*N + n)
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
 };
 
+constexpr int STG_COLS = 32;             // accumulator columns staged per epilogue round
+constexpr int STG_PITCH = STG_COLS + 4;  // floats; (pitch/4) odd -> conflict-free float4 rows
+constexpr int STG_BYTES = 128 * STG_PITCH * 4;
+
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v, int act, float slope) {
+    if constexpr (ACT < 0) return act_apply(v, act, slope);
+    else return act_apply(v, ACT, slope);  // constant-folds to the single selected branch
+}
+template <int EPI>
+__device__ __forceinline__ float epi_ct(float v, float a, int epi) {
+    const int e = (EPI < 0) ? epi : EPI;
+    switch (e) {
+        case RCN_EPI_GDN: return a * rsqrtf(v);
+        case RCN_EPI_IGDN: return a * sqrtf(v);
+        case RCN_EPI_MUL_AUXP1: return v * (a + 1.f);
+        case RCN_EPI_MULP1_AUX: return (v + 1.f) * a;
+        case RCN_EPI_SIGMOID_GATE: return a * (1.f / (1.f + expf(-v)));
+        default: return v;
+    }
+}
+
+// One staged slab (128 pixels x up to 32 channels starting at channel n0 + c0) -> fused element-wise -> global.
+// ACT / EPI are compile-time so the loop body only holds the math of the selected variant (a runtime switch
+// inside the loop gets if-converted into ALL branches executing predicated: ~1000 instructions per 4 elements).
+template <int ACT, int EPI>
+__device__ __forceinline__ void epilogue_slab(const rcn_conv_desc& p, int dbg, const float* __restrict__ stg, int cols, int n,
+                                              int c_base, int x0, int y0, int et, bool vec) {
+    const int Ho = p.H, Wo = p.W;
+    if (vec) {
+        const int groups = cols >> 2;
+        const int total = 128 * groups;
+#pragma unroll 2
+        for (int e = et; e < total; e += 128) {
+            const int row = e / groups, g4 = (e - row * groups) * 4;
+            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
+            if (ho >= Ho || wo >= Wo) continue;
+            const int c = c_base + g4;
+            const long long pix = ((long long)n * Ho + ho) * Wo + wo;
+            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + g4);
+            float val[4] = {a4.x, a4.y, a4.z, a4.w};
+            if (p.bias) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                val[0] += b4.x; val[1] += b4.y; val[2] += b4.z; val[3] += b4.w;
+            }
+            if (p.cscale) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c + j)) + __ldg(p.cshift + n * p.Cout + c + j);
+            }
+            if (EPI != 0) {
+                const float4 x4 = *reinterpret_cast<const float4*>(p.aux + pix * p.ldaux + c);
+                val[0] = epi_ct<EPI>(val[0], x4.x, p.epi); val[1] = epi_ct<EPI>(val[1], x4.y, p.epi);
+                val[2] = epi_ct<EPI>(val[2], x4.z, p.epi); val[3] = epi_ct<EPI>(val[3], x4.w, p.epi);
+            }
+            float rv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.res) {
+                const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldres + c);
+                rv[0] = p.res_scale * r4.x; rv[1] = p.res_scale * r4.y; rv[2] = p.res_scale * r4.z; rv[3] = p.res_scale * r4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (p.res && p.res_pre) val[j] += rv[j];
+                val[j] = act_ct<ACT>(val[j], p.act, p.slope);
+                if (p.res && !p.res_pre) val[j] += rv[j];
+            }
+            if (!(dbg & 1)) *reinterpret_cast<float4*>(p.y + pix * p.ldy + c) = make_float4(val[0], val[1], val[2], val[3]);
+        }
+    } else {
+        const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
+        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? p.Cout / 4 : p.Cout;
+        const int total = 128 * cols;
+#pragma unroll 1
+        for (int e = et; e < total; e += 128) {
+            const int row = e / cols, col = e - row * cols;
+            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
+            if (ho >= Ho || wo >= Wo) continue;
+            const int c = c_base + col;
+            const long long mpix = ((long long)n * Ho + ho) * Wo + wo;
+            float val = stg[row * STG_PITCH + col];
+            if (p.bias) val += __ldg(p.bias + c);
+            if (p.cscale) val = val * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
+            if (EPI != 0) val = epi_ct<EPI>(val, p.aux[mpix * p.ldaux + c], p.epi);
+            int hh = ho, ww = wo, cc = c;
+            if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
+            const long long pix = ((long long)n * Hs + hh) * Ws + ww;
+            float rv = 0.f;
+            if (p.res) rv = p.res_scale * p.res[pix * p.ldres + cc];
+            if (p.res && p.res_pre) val += rv;
+            val = act_ct<ACT>(val, p.act, p.slope);
+            if (p.res && !p.res_pre) val += rv;
+            if (!(dbg & 1)) {
+                if (p.store == RCN_STORE_NCHW || p.store == RCN_STORE_PS2_NCHW)
+                    p.y[(((long long)n * Cs + cc) * Hs + hh) * Ws + ww] = val;
+                else
+                    p.y[pix * p.ldy + cc] = val;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const rcn_conv_desc& p, int dbg, const float* stg, int cols, int n, int c_base,
+                                                  int x0, int y0, int et, bool vec) {
+#define RCN_EP(A, E) epilogue_slab<A, E>(p, dbg, stg, cols, n, c_base, x0, y0, et, vec)
+    if (p.epi == RCN_EPI_NONE) {
+        switch (p.act) {
+            case RCN_ACT_NONE: RCN_EP(RCN_ACT_NONE, 0); break;
+            case RCN_ACT_RELU: RCN_EP(RCN_ACT_RELU, 0); break;
+            case RCN_ACT_LRELU: RCN_EP(RCN_ACT_LRELU, 0); break;
+            case RCN_ACT_GELU: RCN_EP(RCN_ACT_GELU, 0); break;
+            case RCN_ACT_SIGMOID: RCN_EP(RCN_ACT_SIGMOID, 0); break;
+            case RCN_ACT_HALF_TANH: RCN_EP(RCN_ACT_HALF_TANH, 0); break;
+            case RCN_ACT_HSWISH: RCN_EP(RCN_ACT_HSWISH, 0); break;
+            default: RCN_EP(-1, 0); break;
+        }
+    } else if (p.act == RCN_ACT_NONE) {
+        switch (p.epi) {
+            case RCN_EPI_GDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_GDN); break;
+            case RCN_EPI_IGDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_IGDN); break;
+            case RCN_EPI_MUL_AUXP1: RCN_EP(RCN_ACT_NONE, RCN_EPI_MUL_AUXP1); break;
+            case RCN_EPI_MULP1_AUX: RCN_EP(RCN_ACT_NONE, RCN_EPI_MULP1_AUX); break;
+            default: RCN_EP(RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE); break;
+        }
+    } else {
+        RCN_EP(-1, -1);
+    }
+#undef RCN_EP
+}
+
+// Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; tile t -> (m-tile, n-tile).
+// TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 __global__ void __launch_bounds__(192, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
@@ -124,31 +257,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const rcn_conv_desc& p = P.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B_BYTES = P.Ntile * BLOCK_K * 2;
-    const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);
-    // stage_bytes is a multiple of 1024 because Ntile % 16 == 0 -> B_BYTES % 2048 == 0
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes);
+    const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);  // multiple of 1024 (Ntile % 16 == 0)
+    float* stg = reinterpret_cast<float*>(smem + (size_t)P.stages * stage_bytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES);
     uint64_t* empty_bar = full_bar + P.stages;
-    uint64_t* tmem_full = empty_bar + P.stages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_full = empty_bar + P.stages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;          // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
-    // tile coordinates
-    int t = blockIdx.x;
-    const int tx = t % P.tiles_x; t /= P.tiles_x;
-    const int ty = t % P.tiles_y;
-    const int n = t / P.tiles_y;
-    const int x0 = tx * TILE_W, y0 = ty * TILE_H;
-    const int n0 = blockIdx.y * P.Ntile;
     const int pad = p.k >> 1;
     const int chunks = P.Cp / BLOCK_K;
     const int kiters = p.k * p.k * chunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -159,190 +286,139 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const uint32_t tx_bytes = (uint32_t)stage_bytes;
+            const bool loadA = !(P.dbg & 4);
+            const uint32_t tx_bytes = loadA ? (uint32_t)stage_bytes : (uint32_t)((P.passes == 3 ? 2 : 1) * B_BYTES);
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < kiters; ++it) {
-                const int tap = it / chunks, ch = it - tap * chunks;
-                const int ky = tap / p.k, kx = tap - ky * p.k;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                const bool loadA = !(P.dbg & 4);
-                mbar_expect_tx(&full_bar[stage], loadA ? tx_bytes : (uint32_t)((P.passes == 3 ? 2 : 1) * B_BYTES));
-                if (loadA) tma_load_4d(sa, &map_a_hi, &full_bar[stage], ch * BLOCK_K, x0 + kx - pad, y0 + ky - pad, n);
-                tma_load_2d(sa + A_BYTES, &map_w_hi, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
-                if (P.passes == 3) {
-                    if (loadA) tma_load_4d(sa + A_BYTES + B_BYTES, &map_a_lo, &full_bar[stage], ch * BLOCK_K, x0 + kx - pad, y0 + ky - pad, n);
-                    tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+            for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
+                const int nt = (int)(t % P.tiles_n);
+                long long mt = t / P.tiles_n;
+                const int tx = (int)(mt % P.tiles_x); mt /= P.tiles_x;
+                const int ty = (int)(mt % P.tiles_y);
+                const int n = (int)(mt / P.tiles_y);
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * P.Ntile;
+                for (int it = 0; it < kiters; ++it) {
+                    const int tap = it / chunks, ch = it - tap * chunks;
+                    const int ky = tap / p.k, kx = tap - ky * p.k;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    mbar_expect_tx(&full_bar[stage], tx_bytes);
+                    // input box origin for this tap.  stride 1: shifted box of the same plane.  stride 2 (pad k/2):
+                    // input row 2y+ky-pad lives in polyphase plane py = (ky-pad)&1 at row y + floor((ky-pad)/2).
+                    int ax = x0 + kx - pad, ay = y0 + ky - pad, an = n;
+                    if (P.s2) {
+                        const int oy = ky - pad, ox = kx - pad;
+                        const int py = oy & 1, px = ox & 1;
+                        ay = y0 + ((oy - py) >> 1);
+                        ax = x0 + ((ox - px) >> 1);
+                        an = (py * 2 + px) * p.N + n;
+                    }
+                    if (loadA) tma_load_4d(sa, &map_a_hi, &full_bar[stage], ch * BLOCK_K, ax, ay, an);
+                    tma_load_2d(sa + A_BYTES, &map_w_hi, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+                    if (P.passes == 3) {
+                        if (loadA) tma_load_4d(sa + A_BYTES + B_BYTES, &map_a_lo, &full_bar[stage], ch * BLOCK_K, ax, ay, an);
+                        tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+                    }
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            int nact = p.Cout - n0;
-            if (nact > P.Ntile) nact = P.Ntile;
-            nact = (nact + 15) & ~15;
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t acc = 0;
-            for (int it = 0; it < kiters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
+            uint32_t local = 0;
+            for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++local) {
+                const int n0 = (int)(t % P.tiles_n) * P.Ntile;
+                int nact = p.Cout - n0;
+                if (nact > P.Ntile) nact = P.Ntile;
+                nact = (nact + 15) & ~15;
+                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+                const uint32_t ab = local & 1;
+                mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                const uint64_t a_hi = make_sw128_desc(sa), b_hi = make_sw128_desc(sa + A_BYTES);
-                const uint64_t a_lo = make_sw128_desc(sa + A_BYTES + B_BYTES), b_lo = make_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
+                const uint32_t tmem_d = tmem_base + ab * 128;
+                uint32_t acc = 0;
+                for (int it = 0; it < kiters; ++it) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+                    const uint64_t a_hi = make_sw128_desc(sa), b_hi = make_sw128_desc(sa + A_BYTES);
+                    const uint64_t a_lo = make_sw128_desc(sa + A_BYTES + B_BYTES), b_lo = make_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-                for (int j = 0; j < ((P.dbg & 2) ? 0 : BLOCK_K / 16); ++j) {
-                    const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
-                    if (P.passes == 3) {
-                        umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, acc);
+                    for (int j = 0; j < ((P.dbg & 2) ? 0 : BLOCK_K / 16); ++j) {
+                        const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
+                        if (P.passes == 3) {
+                            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, acc);
+                            acc = 1;
+                            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
+                        }
+                        umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
                         acc = 1;
-                        umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1);
                     }
-                    umma_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, acc);
-                    acc = 1;
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                umma_commit(&tmem_full[ab]);
             }
-            umma_commit(tmem_full);
         }
         __syncwarp();
     } else {
-        // ================= epilogue: TMEM -> smem staging -> fused element-wise -> coalesced global =================
-        // The accumulator tile is first parked in shared memory (the operand ring is idle by now: every TMA write
-        // was consumed by an MMA that has retired), then re-read with lanes running along channels so that global
-        // loads/stores are full 128 B lines and the element-wise code is one compact loop (no 32x unrolled copy of
-        // the activation switch -> no instruction-cache thrash).
+        // ================= epilogue: TMEM -> smem slab -> fused element-wise -> coalesced global =================
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int m = q * 32 + lane;
-        const int Ho = p.H, Wo = p.W;  // stride 1, same padding
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        int ncols = p.Cout - n0;
-        if (ncols > P.Ntile) ncols = P.Ntile;
-        const int NS = P.Ntile + 4;  // row pitch (floats): (NS/4) odd -> conflict-free float4 rows
-        float* stg = reinterpret_cast<float*>(smem);
-        for (int c0 = 0; c0 < ncols; c0 += 32) {
-            uint32_t v[32];
-            __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
-            tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-            float4* dst = reinterpret_cast<float4*>(stg + m * NS + c0);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-                if (c0 + 4 * i < P.Ntile)
-                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                         __uint_as_float(v[4 * i + 3]));
-        }
-        tc_fence_before();
-        asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
         const int et = threadIdx.x - 64;
-        const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
-        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? p.Cout / 4 : p.Cout;
         const bool vec = !(P.dbg & 8) && (p.store == RCN_STORE_NHWC) && ((p.Cout & 3) == 0) && ((p.ldy & 3) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
                          (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
                          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
-        if (vec) {
-            const int groups = ncols >> 2;
-            const int total = 128 * groups;
-#pragma unroll 1
-            for (int e = et; e < total; e += 128) {
-                const int row = e / groups, g4 = (e - row * groups) * 4;
-                const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
-                if (ho >= Ho || wo >= Wo) continue;
-                const int c = n0 + g4;
-                const long long pix = ((long long)n * Ho + ho) * Wo + wo;
-                float4 a4 = *reinterpret_cast<const float4*>(stg + row * NS + g4);
-                float val[4] = {a4.x, a4.y, a4.z, a4.w};
-                if (p.bias) {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                    val[0] += b4.x; val[1] += b4.y; val[2] += b4.z; val[3] += b4.w;
+        uint32_t local = 0;
+        for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++local) {
+            const int nt = (int)(t % P.tiles_n);
+            long long mt = t / P.tiles_n;
+            const int tx = (int)(mt % P.tiles_x); mt /= P.tiles_x;
+            const int ty = (int)(mt % P.tiles_y);
+            const int n = (int)(mt / P.tiles_y);
+            const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * P.Ntile;
+            int ncols = p.Cout - n0;
+            if (ncols > P.Ntile) ncols = P.Ntile;
+            const uint32_t ab = local & 1;
+            mbar_wait(&tmem_full[ab], (local >> 1) & 1);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncols; c0 += STG_COLS) {
+                uint32_t v[32];
+                __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
+                tmem_ld32(tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                if (c0 + STG_COLS >= ncols) {
+                    // last TMEM read of this tile by this warp: once all four warps are here the accumulator is free
+                    tc_fence_before();
                 }
-                if (p.cscale) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous slab fully consumed (and, on the last slab, TMEM drained)
+                if (c0 + STG_COLS >= ncols && et == 0) {
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
+                }
+                float4* dst = reinterpret_cast<float4*>(stg + m * STG_PITCH);
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c + j)) + __ldg(p.cshift + n * p.Cout + c + j);
-                }
-                if (p.epi != RCN_EPI_NONE) {
-                    const float4 x4 = *reinterpret_cast<const float4*>(p.aux + pix * p.ldaux + c);
-                    const float ax[4] = {x4.x, x4.y, x4.z, x4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        switch (p.epi) {
-                            case RCN_EPI_GDN: val[j] = ax[j] * rsqrtf(val[j]); break;
-                            case RCN_EPI_IGDN: val[j] = ax[j] * sqrtf(val[j]); break;
-                            case RCN_EPI_MUL_AUXP1: val[j] = val[j] * (ax[j] + 1.f); break;
-                            case RCN_EPI_MULP1_AUX: val[j] = (val[j] + 1.f) * ax[j]; break;
-                            case RCN_EPI_SIGMOID_GATE: val[j] = ax[j] * (1.f / (1.f + expf(-val[j]))); break;
-                            default: break;
-                        }
-                    }
-                }
-                float rv[4] = {0.f, 0.f, 0.f, 0.f};
-                if (p.res) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldres + c);
-                    rv[0] = p.res_scale * r4.x; rv[1] = p.res_scale * r4.y; rv[2] = p.res_scale * r4.z; rv[3] = p.res_scale * r4.w;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (p.res && p.res_pre) val[j] += rv[j];
-                    val[j] = act_apply(val[j], p.act, p.slope);
-                    if (p.res && !p.res_pre) val[j] += rv[j];
-                }
-                if (!(P.dbg & 1)) *reinterpret_cast<float4*>(p.y + pix * p.ldy + c) = make_float4(val[0], val[1], val[2], val[3]);
-            }
-        } else if (!(P.dbg & 8)) {
-            const int total = 128 * ncols;
-#pragma unroll 1
-            for (int e = et; e < total; e += 128) {
-                const int row = e / ncols, col = e - row * ncols;
-                const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
-                if (ho >= Ho || wo >= Wo) continue;
-                const int c = n0 + col;
-                const long long mpix = ((long long)n * Ho + ho) * Wo + wo;
-                float val = stg[row * NS + col];
-                if (p.bias) val += __ldg(p.bias + c);
-                if (p.cscale) val = val * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
-                if (p.epi != RCN_EPI_NONE) {
-                    const float a = p.aux[mpix * p.ldaux + c];
-                    switch (p.epi) {
-                        case RCN_EPI_GDN: val = a * rsqrtf(val); break;
-                        case RCN_EPI_IGDN: val = a * sqrtf(val); break;
-                        case RCN_EPI_MUL_AUXP1: val = val * (a + 1.f); break;
-                        case RCN_EPI_MULP1_AUX: val = (val + 1.f) * a; break;
-                        case RCN_EPI_SIGMOID_GATE: val = a * (1.f / (1.f + expf(-val))); break;
-                        default: break;
-                    }
-                }
-                int hh = ho, ww = wo, cc = c;
-                if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
-                const long long pix = ((long long)n * Hs + hh) * Ws + ww;
-                float rv = 0.f;
-                if (p.res) rv = p.res_scale * p.res[pix * p.ldres + cc];
-                if (p.res && p.res_pre) val += rv;
-                val = act_apply(val, p.act, p.slope);
-                if (p.res && !p.res_pre) val += rv;
-                if (!(P.dbg & 1)) {
-                    if (p.store == RCN_STORE_NCHW || p.store == RCN_STORE_PS2_NCHW)
-                        p.y[(((long long)n * Cs + cc) * Hs + hh) * Ws + ww] = val;
-                    else
-                        p.y[pix * p.ldy + cc] = val;
-                }
+                for (int i = 0; i < 8; ++i)
+                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                         __uint_as_float(v[4 * i + 3]));
+                asm volatile("bar.sync 2, 128;" ::: "memory");  // slab visible to the four epilogue warps
+                int cols = ncols - c0;
+                if (cols > STG_COLS) cols = STG_COLS;
+                if (!(P.dbg & 8)) epilogue_dispatch(p, P.dbg, stg, cols, n, n0 + c0, x0, y0, et, vec);
             }
         }
-        tc_fence_before();
     }
+    tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
     }
 }
+
 
 // ---------------------------------------------------------------- operand preparation
 // fp32 NHWC (ld) -> bf16 hi / lo planes (npix, Cp), zero-padded channels; optional x*x (GDN)
@@ -367,6 +443,33 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long lon
         }
         *reinterpret_cast<uint2*>(hi + pix * Cp + c4) = *reinterpret_cast<uint2*>(h);
         if (lo) *reinterpret_cast<uint2*>(lo + pix * Cp + c4) = *reinterpret_cast<uint2*>(l);
+    }
+}
+
+// polyphase split for stride-2 convs: out[((py*2+px)*N + n), i, j, c] = x[n, 2i+py, 2j+px, c]
+__global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N, int H, int W, int C, int Cp,
+                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+    const int H2 = H / 2, W2 = W / 2;
+    const long long total = (long long)N * H * W * (Cp / 4);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % (Cp / 4)) * 4;
+        long long t = i / (Cp / 4);
+        const int w = (int)(t % W); t /= W;
+        const int h = (int)(t % H);
+        const int n = (int)(t / H);
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (c4 + j < C) ? x[(((long long)n * H + h) * W + w) * ldx + c4 + j] : 0.f;
+        __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            hh[j] = __float2bfloat16_rn(v[j]);
+            ll[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hh[j]));
+        }
+        const long long plane = (long long)((h & 1) * 2 + (w & 1)) * N + n;
+        const long long o = ((plane * H2 + (h >> 1)) * W2 + (w >> 1)) * Cp + c4;
+        *reinterpret_cast<uint2*>(hi + o) = *reinterpret_cast<uint2*>(hh);
+        if (lo) *reinterpret_cast<uint2*>(lo + o) = *reinterpret_cast<uint2*>(ll);
     }
 }
 
@@ -438,6 +541,19 @@ extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, in
     return RCN_OK;
 }
 
+// stride-2 operand: the four polyphase planes (py,px) of x, each (N, H/2, W/2, Cp), stacked on the batch axis
+extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(x && hi && N > 0 && C > 0 && Cp >= C && Cp % 64 == 0, "rcn_split_bf16_s2: bad arguments");
+    RCN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "rcn_split_bf16_s2: H and W must be even");
+    const long long total = (long long)N * H * W * (Cp / 4);
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    split_bf16_s2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, H, W, C, Cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_split_bf16_s2");
+    return RCN_OK;
+}
+
 extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream) {
     RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && Cp % 64 == 0, "rcn_pack_conv_weight_tc: bad arguments");
     const long long total = (long long)Cout * k * k * Cp;
@@ -454,7 +570,8 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     RCN_CHECK_ARG(d && d->y && x_hi && w_hi, "rcn_conv2d_tc: null pointer");
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
-    RCN_CHECK_ARG(d->stride == 1, "rcn_conv2d_tc: stride %d unsupported (use rcn_conv2d)", d->stride);
+    RCN_CHECK_ARG(d->stride == 1 || d->stride == 2, "rcn_conv2d_tc: stride %d unsupported", d->stride);
+    RCN_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "rcn_conv2d_tc: stride 2 needs even H and W");
     RCN_CHECK_ARG(Cp % 64 == 0 && Cp >= d->Cin, "rcn_conv2d_tc: Cp must be a multiple of 64 >= Cin");
     RCN_CHECK_ARG(d->epi == RCN_EPI_NONE || d->aux, "rcn_conv2d_tc: epilogue needs aux");
     RCN_CHECK_ARG(get_encode() != nullptr, "rcn_conv2d_tc: cuTensorMapEncodeTiled is not available from the driver");
@@ -462,14 +579,16 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     RCN_CHECK_ARG(!ps || (d->Cout % 4 == 0), "rcn_conv2d_tc: pixel shuffle needs Cout %% 4 == 0");
     TcParams P;
     P.d = *d;
+    P.s2 = (d->stride == 2);
+    if (P.s2) { P.d.H = d->H / 2; P.d.W = d->W / 2; }   // the kernel works in output geometry (== polyphase plane geometry)
     P.Cp = Cp;
     P.passes = passes;
     int nt = d->Cout >= 128 ? 128 : ((d->Cout + 15) & ~15);
     P.Ntile = nt;
-    P.tiles_x = (d->W + TILE_W - 1) / TILE_W;
-    P.tiles_y = (d->H + TILE_H - 1) / TILE_H;
+    P.tiles_x = (P.d.W + TILE_W - 1) / TILE_W;
+    P.tiles_y = (P.d.H + TILE_H - 1) / TILE_H;
     const int stage_bytes = (passes == 3 ? 2 : 1) * (A_BYTES + nt * BLOCK_K * 2);
-    int stages = (200 * 1024) / stage_bytes;
+    int stages = (226 * 1024 - STG_BYTES - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     P.stages = stages;
@@ -479,11 +598,12 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         const char* st = getenv("RCN_TC_STAGES");
         if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
     }
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 256;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const long long Ktot = (long long)d->k * d->k * Cp;
-    bool ok = make_act_map(&ma_hi, x_hi, d->N, d->H, d->W, Cp) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt);
-    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, d->N, d->H, d->W, Cp) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt);
+    const int planes = P.s2 ? 4 * d->N : d->N;
+    bool ok = make_act_map(&ma_hi, x_hi, planes, P.d.H, P.d.W, Cp) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt);
+    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt);
     else { ma_lo = ma_hi; mw_lo = mw_hi; }
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
     static bool attr_set = false;
@@ -491,9 +611,16 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
     }
-    const long long gx = (long long)P.tiles_x * P.tiles_y * d->N;
-    RCN_CHECK_ARG(gx < 2147483647LL, "rcn_conv2d_tc: too many tiles");
-    dim3 grid((unsigned)gx, (d->Cout + nt - 1) / nt);
+    P.tiles_n = (d->Cout + nt - 1) / nt;
+    P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
+    static int num_sms = 0;
+    if (!num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const unsigned grid = (unsigned)(P.total_tiles < num_sms ? P.total_tiles : num_sms);  // persistent: one CTA per SM
     conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_conv2d_tc");

@@ -136,9 +136,11 @@ class ResidualBlockWithStride(_Block):
         self.skip = conv1x1(in_ch, out_ch, stride=stride) if (stride != 1 or in_ch != out_ch) else None
 
     def _f(self, x, out=None):
-        t = self.conv1._f(x, act=ACT_LRELU, slope=0.01)
+        # conv1 and the 1x1 skip read the same tensor with the same stride: one bf16 split serves both
+        sp = ops.shared_split(x, [ops.pack(self.conv1), ops.pack(self.skip)], self.conv1.stride[0]) if self.skip is not None else None
+        t = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=sp)
         t = self.conv2._f(t)
-        identity = x if self.skip is None else self.skip._f(x)
+        identity = x if self.skip is None else self.skip._f(x, presplit=sp)
         return self.gdn._f(t, res=identity, out=out)
 
 
@@ -152,10 +154,11 @@ class ResidualBlockUpsample(_Block):
         self.upsample = subpel_conv3x3(in_ch, out_ch, upsample)
 
     def _f(self, x, out=None):
-        t = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01)
+        sp = ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
+        t = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp)
         t = self.conv._f(t)
         t = self.igdn._f(t)
-        return self.upsample._f(x, res=t, out=out)
+        return self.upsample._f(x, res=t, out=out, presplit=sp)
 
 
 class ResidualBlock(_Block):

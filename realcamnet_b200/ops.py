@@ -134,8 +134,45 @@ def pack(module) -> PackedConv:
 
 
 # ----------------------------------------------------------------------------- conv / linear
+class SplitOperand:
+    """bf16 hi/lo planes of one activation tensor for the tcgen05 engine (shareable between the convs that read it)."""
+    __slots__ = ("hi", "lo", "key")
+
+    def __init__(self, hi, lo, key):
+        self.hi, self.lo, self.key = hi, lo, key
+
+
+def split_operand(x, cp, stride=1, in_square=False, passes=None) -> SplitOperand:
+    """fp32 NHWC -> zero-padded bf16 planes; stride 2 -> the four polyphase planes stacked on the batch axis."""
+    N, H, W, C, ldx = geom(x, "split_operand.x")
+    if passes is None:
+        passes = 3 if _ENGINE == "bf16x3" else 1
+    if stride == 2:
+        hi = torch.empty((4 * N, H // 2, W // 2, cp), device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if passes == 3 else None
+        if in_square:
+            raise ValueError("in_square is not used with stride 2")
+        _C.check(_C.lib().rcn_split_bf16_s2(_ptr(x), ldx, N, H, W, C, cp, _ptr(hi), _ptr(lo), _stream()), "rcn_split_bf16_s2")
+    else:
+        hi = torch.empty((N, H, W, cp), device=x.device, dtype=torch.bfloat16)
+        lo = torch.empty_like(hi) if passes == 3 else None
+        _C.check(_C.lib().rcn_split_bf16(_ptr(x), ldx, N * H * W, C, cp, int(in_square), _ptr(hi), _ptr(lo), _stream()),
+                 "rcn_split_bf16")
+    return SplitOperand(hi, lo, (x.data_ptr(), N, H, W, C, ldx, cp, stride, bool(in_square)))
+
+
+def shared_split(x, pcs, stride=1):
+    """One split for several convs reading the same tensor with the same stride (None when the engine is fp32
+    or a layer is not tcgen05-eligible)."""
+    if _ENGINE == "fp32" or any(pc.w_hi is None for pc in pcs) or len({pc.cp for pc in pcs}) != 1:
+        return None
+    if stride == 2 and (x.shape[1] % 2 or x.shape[2] % 2):
+        return None
+    return split_operand(x, pcs[0].cp, stride)
+
+
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
-           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None):
+           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None):
     N, H, W, Cin, ldx = geom(x, "conv2d.x")
     if Cin != pc.cin:
         raise ValueError(f"conv2d: input has {Cin} channels, weight expects {pc.cin}")
@@ -180,14 +217,13 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
         d.res, d.ldres, d.res_pre = res.data_ptr(), ldr, int(res_pre)
     d.act, d.slope, d.res_scale = act, float(slope), float(res_scale)
     eng = engine or _ENGINE
-    if eng != "fp32" and stride == 1 and pc.w_hi is not None:
+    if eng != "fp32" and pc.w_hi is not None and (stride == 1 or (H % 2 == 0 and W % 2 == 0)):
         # tcgen05 path: split the fp32 activations into bf16 hi/lo planes (x*x for the GDN pool), TMA + UMMA conv
         passes = 3 if eng == "bf16x3" else 1
-        hi = torch.empty((N, H, W, pc.cp), device=x.device, dtype=torch.bfloat16)
-        lo = torch.empty_like(hi) if passes == 3 else None
-        _C.check(_C.lib().rcn_split_bf16(_ptr(x), ldx, N * H * W, Cin, pc.cp, int(in_square), _ptr(hi), _ptr(lo), _stream()),
-                 "rcn_split_bf16")
-        _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(hi), _ptr(lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
+        sp = presplit if presplit is not None else split_operand(x, pc.cp, stride, in_square, passes)
+        if sp.key != (x.data_ptr(), N, H, W, Cin, ldx, pc.cp, stride, bool(in_square)) or (passes == 3 and sp.lo is None):
+            raise ValueError("conv2d: presplit operand does not belong to this input / layer geometry")
+        _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
                                         _stream()), "rcn_conv2d_tc")
         return out
     _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")

@@ -79,9 +79,10 @@ class SpatialFeatureTransform(nn.Module):
         """x*scale + shift + x (+ extra); both element-wise steps are conv epilogues."""
         if not self.residual:
             raise NotImplementedError("residual=False is never used by the reference")
-        s = self.cond_scale[0]._f(cond, act=ACT_RELU)
+        sp = ops.shared_split(cond, [ops.pack(self.cond_scale[0]), ops.pack(self.cond_shift[0])])
+        s = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp)
         t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra)      # (scale + 1) * x (+ extra)
-        h = self.cond_shift[0]._f(cond, act=ACT_RELU)
+        h = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp)
         return self.cond_shift[2]._f(h, res=t, out=out)                        # shift + ...
 
     def forward(self, x, cond):
@@ -224,8 +225,9 @@ class RBU(nn.Module):
         self.upsample = subpel_conv3x3(in_ch, out_ch, upsample)
 
     def _f(self, x, out=None):
-        t = self.conv._f(self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01))
-        return self.upsample._f(x, res=t, out=out)
+        sp = ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
+        t = self.conv._f(self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp))
+        return self.upsample._f(x, res=t, out=out, presplit=sp)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
@@ -432,19 +434,54 @@ class raw_compression_tcm_final(CompressionModel):
                                      symbols=sym[i] if emit_strings else None, indexes=idx[i] if emit_strings else None,
                                      scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound)
             self._finish_slice(i, lrp_sup, cin, ms, ss)
+        # symbols are final here: start their D2H copy on a side stream so the host range coder runs WHILE the
+        # synthesis transform g_s (half of the FLOPs) executes on the main stream
+        pending = self._begin_host_copy(sym, idx, z_sym) if emit_strings else None
         x_hat = self._g_s(ms[..., 320:])
         y_nchw = ops.to_nchw(y)
         out = {"x_hat": x_hat, "y": y_nchw, "lft": ops.to_nchw(local[2]), "lsc": ops.to_nchw(lsc_fea),
                "likelihoods": {"y": ops.to_nchw(y_lik), "z": ops.to_nchw(z_lik)},
                "para": {"means": ops.to_nchw(means), "scales": ops.to_nchw(scales), "y": y_nchw}}
         if emit_strings:
-            out["strings"] = [[self._encode_y(sym, idx)], self.entropy_bottleneck.compress_symbols(z_sym)]
+            h_sym, h_idx, h_z = self._end_host_copy(pending)
+            out["strings"] = [[self._encode_y(h_sym, h_idx)], self.entropy_bottleneck.compress_symbols(h_z)]
             out["shape"] = torch.Size(z.shape[1:3])
         return out
 
+    def _begin_host_copy(self, *tensors):
+        """Async device->pinned-host copies on a side stream, ordered after the work already queued."""
+        dev = tensors[0].device
+        if getattr(self, "_side", None) is None or self._side.device != dev:
+            self._side = torch.cuda.Stream(device=dev)
+            self._pinned = {}
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        self._side.wait_event(ev)
+        host = []
+        with torch.cuda.stream(self._side):
+            for j, t in enumerate(tensors):
+                key = (j, tuple(t.shape), t.dtype)
+                h = self._pinned.get(key)
+                if h is None:
+                    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                    self._pinned[key] = h
+                h.copy_(t, non_blocking=True)
+                host.append(h)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        return done, host, tensors  # the device tensors stay referenced until the copy has completed
+
+    @staticmethod
+    def _end_host_copy(pending):
+        done, host, _keep = pending
+        done.synchronize()
+        return host
+
     def _encode_y(self, sym, idx):
         cdf, length, offset = self.gaussian_conditional.host_tables()
-        return rans_encode(sym.cpu().numpy().reshape(-1), idx.cpu().numpy().reshape(-1), cdf, length, offset)
+        s = sym.cpu().numpy() if sym.is_cuda else sym.numpy()
+        i = idx.cpu().numpy() if idx.is_cuda else idx.numpy()
+        return rans_encode(s.reshape(-1), i.reshape(-1), cdf, length, offset)
 
     @torch.no_grad()
     def compress(self, x):
