@@ -106,6 +106,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 struct TcParams {
     rcn_conv_desc d;
     int Cp;       // padded input channels (multiple of 64) of the bf16 planes / packed weights
@@ -118,6 +125,9 @@ struct TcParams {
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
 };
 
+constexpr int EPI_WARPS = 16;            // 4 warps per TMEM lane quarter: one warp per scheduler cannot hide any latency
+constexpr int EPI_THREADS = EPI_WARPS * 32;
+constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int STG_COLS = 32;             // accumulator columns staged per epilogue round
 constexpr int STG_PITCH = STG_COLS + 4;  // floats; (pitch/4) odd -> conflict-free float4 rows
 constexpr int STG_BYTES = 128 * STG_PITCH * 4;
@@ -148,50 +158,79 @@ __device__ __forceinline__ void epilogue_slab(const rcn_conv_desc& p, int dbg, c
                                               int c_base, int x0, int y0, int et, bool vec) {
     const int Ho = p.H, Wo = p.W;
     if (vec) {
-        const int groups = cols >> 2;
+        // Loads-first, fully unrolled: every thread issues ALL of its global loads for the slab (residual / aux,
+        // 16 B each) before the first dependent instruction, so ~8 requests per thread are in flight instead of 1-2
+        // (the epilogue was latency-bound on HBM round trips).  Items are float4s of the STORED tensor:
+        //   NHWC store : item = (row, 4 consecutive channels)
+        //   PS2 store  : item = (row, sub-pixel (i,j), 4 consecutive shuffled channels) -- conv channels cc*4 + sub,
+        //                gathered with stride 4 from the slab, so the shuffled tensor is also written 16 B at a time.
+        const bool ps = (p.store == RCN_STORE_PS2);
+        const int groups = cols >> 2;           // float4 items per row (both layouts)
         const int total = 128 * groups;
-#pragma unroll 2
-        for (int e = et; e < total; e += 128) {
-            const int row = e / groups, g4 = (e - row * groups) * 4;
-            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
-            if (ho >= Ho || wo >= Wo) continue;
-            const int c = c_base + g4;
-            const long long pix = ((long long)n * Ho + ho) * Wo + wo;
-            const float4 a4 = *reinterpret_cast<const float4*>(stg + row * STG_PITCH + g4);
-            float val[4] = {a4.x, a4.y, a4.z, a4.w};
-            if (p.bias) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                val[0] += b4.x; val[1] += b4.y; val[2] += b4.z; val[3] += b4.w;
-            }
-            if (p.cscale) {
+        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo;
+        constexpr int IT = (128 * 8) / EPI_THREADS;  // 128 rows * 8 groups over the epilogue threads
+        float4 accv[IT], resv[IT], auxv[IT], biasv[IT];
+        long long opix[IT];
+        int och[IT];
+        bool ok[IT];
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c + j)) + __ldg(p.cshift + n * p.Cout + c + j);
+        for (int u = 0; u < IT; ++u) {
+            const int e = et + EPI_THREADS * u;
+            const int row = e / groups, g = e - row * groups;
+            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
+            ok[u] = (e < total) && (ho < Ho) && (wo < Wo);
+            resv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            auxv[u] = resv[u];
+            accv[u] = resv[u];
+            biasv[u] = resv[u];
+            opix[u] = 0;
+            och[u] = 0;
+            if (!ok[u]) continue;
+            const float* srow = stg + row * STG_PITCH;
+            if (!ps) {
+                och[u] = c_base + 4 * g;
+                opix[u] = ((long long)n * Ho + ho) * Wo + wo;
+                accv[u] = *reinterpret_cast<const float4*>(srow + 4 * g);
+                if (EPI != 0) auxv[u] = *reinterpret_cast<const float4*>(p.aux + opix[u] * p.ldaux + och[u]);
+                if (p.bias) biasv[u] = __ldg(reinterpret_cast<const float4*>(p.bias + och[u]));
+            } else {
+                const int sub = g & 3, ccg = g >> 2;          // groups = 4 sub-pixels x (cols/16) channel groups
+                const int cc0 = (c_base >> 2) + 4 * ccg;      // first shuffled channel of the item
+                och[u] = cc0;
+                opix[u] = ((long long)n * Hs + 2 * ho + (sub >> 1)) * Ws + 2 * wo + (sub & 1);
+                const float* sp = srow + 16 * ccg + sub;      // conv channel (cc0 + q)*4 + sub  ->  slab column 16*ccg + 4*q + sub
+                accv[u] = make_float4(sp[0], sp[4], sp[8], sp[12]);
+                if (p.bias) {
+                    const float* bp = p.bias + (cc0 << 2) + sub;   // conv channel of element q: (cc0 + q)*4 + sub
+                    biasv[u] = make_float4(__ldg(bp), __ldg(bp + 4), __ldg(bp + 8), __ldg(bp + 12));
+                }
             }
-            if (EPI != 0) {
-                const float4 x4 = *reinterpret_cast<const float4*>(p.aux + pix * p.ldaux + c);
-                val[0] = epi_ct<EPI>(val[0], x4.x, p.epi); val[1] = epi_ct<EPI>(val[1], x4.y, p.epi);
-                val[2] = epi_ct<EPI>(val[2], x4.z, p.epi); val[3] = epi_ct<EPI>(val[3], x4.w, p.epi);
-            }
-            float rv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.res) {
-                const float4 r4 = *reinterpret_cast<const float4*>(p.res + pix * p.ldres + c);
-                rv[0] = p.res_scale * r4.x; rv[1] = p.res_scale * r4.y; rv[2] = p.res_scale * r4.z; rv[3] = p.res_scale * r4.w;
-            }
+            if (p.res) resv[u] = *reinterpret_cast<const float4*>(p.res + opix[u] * p.ldres + och[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < IT; ++u) {
+            if (!ok[u]) continue;
+            float val[4] = {accv[u].x + biasv[u].x, accv[u].y + biasv[u].y, accv[u].z + biasv[u].z, accv[u].w + biasv[u].w};
+            const float ax[4] = {auxv[u].x, auxv[u].y, auxv[u].z, auxv[u].w};
+            const float rv[4] = {p.res_scale * resv[u].x, p.res_scale * resv[u].y, p.res_scale * resv[u].z, p.res_scale * resv[u].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
+                // conv channel of element j (bias / per-channel affine are indexed by it)
+                const int c = ps ? ((och[u] + j) << 2) + (int)((opix[u] / Ws) & 1) * 2 + (int)(opix[u] % Ws & 1) : och[u] + j;
+                if (p.cscale) val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
+                if (EPI != 0) val[j] = epi_ct<EPI>(val[j], ax[j], p.epi);
                 if (p.res && p.res_pre) val[j] += rv[j];
                 val[j] = act_ct<ACT>(val[j], p.act, p.slope);
                 if (p.res && !p.res_pre) val[j] += rv[j];
             }
-            if (!(dbg & 1)) *reinterpret_cast<float4*>(p.y + pix * p.ldy + c) = make_float4(val[0], val[1], val[2], val[3]);
+            if (!(dbg & 1)) *reinterpret_cast<float4*>(p.y + opix[u] * p.ldy + och[u]) = make_float4(val[0], val[1], val[2], val[3]);
         }
     } else {
         const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
         const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? p.Cout / 4 : p.Cout;
         const int total = 128 * cols;
-#pragma unroll 1
-        for (int e = et; e < total; e += 128) {
+#pragma unroll 2
+        for (int e = et; e < total; e += EPI_THREADS) {
             const int row = e / cols, col = e - row * cols;
             const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
             if (ho >= Ho || wo >= Wo) continue;
@@ -249,7 +288,7 @@ __device__ __forceinline__ void epilogue_dispatch(const rcn_conv_desc& p, int db
 
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; tile t -> (m-tile, n-tile).
 // TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -366,10 +405,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         __syncwarp();
     } else {
         // ================= epilogue: TMEM -> smem slab -> fused element-wise -> coalesced global =================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp_id % 4)
+        const int jsub = (warp - 2) >> 2;  // which 8-column block of the 32-column slab this warp drains (0..3)
         const int m = q * 32 + lane;
         const int et = threadIdx.x - 64;
-        const bool vec = !(P.dbg & 8) && (p.store == RCN_STORE_NHWC) && ((p.Cout & 3) == 0) && ((p.ldy & 3) == 0) &&
+        const bool vec = !(P.dbg & 8) && ((p.store == RCN_STORE_NHWC && (p.Cout & 3) == 0) ||
+                                          (p.store == RCN_STORE_PS2 && (p.Cout & 15) == 0 && p.epi == RCN_EPI_NONE)) &&
+                         ((p.ldy & 3) == 0) &&
                          ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
                          (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
@@ -388,23 +430,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             mbar_wait(&tmem_full[ab], (local >> 1) & 1);
             tc_fence_after();
             for (int c0 = 0; c0 < ncols; c0 += STG_COLS) {
-                uint32_t v[32];
+                uint32_t v[8];
                 __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
-                tmem_ld32(tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-                if (c0 + STG_COLS >= ncols) {
-                    // last TMEM read of this tile by this warp: once all four warps are here the accumulator is free
-                    tc_fence_before();
-                }
-                asm volatile("bar.sync 1, 128;" ::: "memory");  // previous slab fully consumed (and, on the last slab, TMEM drained)
+                tmem_ld8(tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 8 * jsub), v);
+                if (c0 + STG_COLS >= ncols) tc_fence_before();  // last TMEM read of this tile by this warp
+                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // previous slab consumed (+ TMEM drained on the last slab)
                 if (c0 + STG_COLS >= ncols && et == 0) {
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
                 }
-                float4* dst = reinterpret_cast<float4*>(stg + m * STG_PITCH);
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    dst[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-                                         __uint_as_float(v[4 * i + 3]));
-                asm volatile("bar.sync 2, 128;" ::: "memory");  // slab visible to the four epilogue warps
+                float4* dst = reinterpret_cast<float4*>(stg + m * STG_PITCH + 8 * jsub);
+                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
+                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
+                asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");  // slab visible to all epilogue warps
                 int cols = ncols - c0;
                 if (cols > STG_COLS) cols = STG_COLS;
                 if (!(P.dbg & 8)) epilogue_dispatch(p, P.dbg, stg, cols, n, n0 + c0, x0, y0, et, vec);
@@ -621,7 +658,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         if (num_sms <= 0) num_sms = 148;
     }
     const unsigned grid = (unsigned)(P.total_tiles < num_sms ? P.total_tiles : num_sms);  // persistent: one CTA per SM
-    conv_tc_kernel<<<grid, 192, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
+    conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_conv2d_tc");
     return RCN_OK;

@@ -77,12 +77,17 @@ __global__ void eb_dequant_kernel(const int* __restrict__ symbols /*NCHW*/, long
     }
 }
 
+struct RansPrep {
+    const int* cdf; int cdf_stride; const int* cdf_len; const int* cdf_off;
+    unsigned* packed; int* esc_count; long long* esc_pos; unsigned* esc_raw; int esc_cap; long long pos_base;
+};
+
 // Gaussian conditional on one slice: y, mu, scale are NHWC channel slices (npix, C).
 __global__ void gaussian_kernel(const float* __restrict__ y, int ldy, const float* __restrict__ mu, int ldm,
                                 const float* __restrict__ scale, int lds, long long npix, int C, long long HW,
                                 const float* __restrict__ table, int ntable, float scale_bound, float lik_bound,
                                 float* __restrict__ y_hat, int ldyh, float* __restrict__ lik, int ldl,
-                                int* __restrict__ symbols, int* __restrict__ indexes) {
+                                int* __restrict__ symbols, int* __restrict__ indexes, RansPrep rp) {
     __shared__ float tab[64];
     for (int i = threadIdx.x; i < ntable && i < 64; i += blockDim.x) tab[i] = table[i];
     __syncthreads();
@@ -110,6 +115,24 @@ __global__ void gaussian_kernel(const float* __restrict__ y, int ldy, const floa
             int idx = ntable - 1;
             for (int t = 0; t < ntable - 1; ++t) idx -= (s <= tab[t]) ? 1 : 0;
             indexes[o] = idx;
+            if (rp.packed) {
+                // range-coder front end (the per-symbol CDF lookup of BufferedRansEncoder.encode_with_indexes,
+                // raw2bit.py:1956): (start << 16) | (freq - 1); out-of-range values take the sentinel bin and are
+                // appended to the escape list (position, bypass payload) for the host state chain.
+                const int sentinel = rp.cdf_len[idx] - 2;
+                int v = (int)q - rp.cdf_off[idx];
+                unsigned raw = 0u;
+                bool escaped = false;
+                if (v < 0) { raw = (unsigned)(-2 * (long long)v - 1); v = sentinel; escaped = true; }
+                else if (v >= sentinel) { raw = (unsigned)(2 * ((long long)v - sentinel)); v = sentinel; escaped = true; }
+                const int* row = rp.cdf + (long long)idx * rp.cdf_stride;
+                const unsigned st = (unsigned)row[v], fr = (unsigned)(row[v + 1] - row[v]);
+                rp.packed[o] = (st << 16) | ((fr - 1u) & 0xFFFFu);
+                if (escaped) {
+                    const int k = atomicAdd(rp.esc_count, 1);
+                    if (k < rp.esc_cap) { rp.esc_pos[k] = rp.pos_base + o; rp.esc_raw[k] = raw; }
+                }
+            }
         }
     }
 }
@@ -183,9 +206,29 @@ extern "C" int rcn_gaussian_conditional(const float* y, int ldy, const float* mu
     RCN_CHECK_ARG((symbols == nullptr) == (indexes == nullptr), "rcn_gaussian_conditional: symbols and indexes come together");
     const long long npix = (long long)N * HW;
     gaussian_kernel<<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(y, ldy, mu, ldm, scale, lds, npix, C, HW, table, ntable,
-                                                                           scale_bound, lik_bound, y_hat, ldyh, lik, ldl, symbols, indexes);
+                                                                           scale_bound, lik_bound, y_hat, ldyh, lik, ldl, symbols, indexes,
+                                                                           RansPrep{});
     count_launch();
     RCN_CHECK_LAUNCH("rcn_gaussian_conditional");
+    return RCN_OK;
+}
+
+extern "C" int rcn_gaussian_conditional_coded(const float* y, int ldy, const float* mu, int ldm, const float* scale, int lds, int N,
+                                              long long HW, int C, const float* table, int ntable, float scale_bound,
+                                              float lik_bound, float* y_hat, int ldyh, float* lik, int ldl, int* symbols,
+                                              int* indexes, const int* cdf, int cdf_stride, const int* cdf_len, const int* cdf_off,
+                                              unsigned* packed, int* esc_count, long long* esc_pos, unsigned* esc_raw, int esc_cap,
+                                              long long pos_base, void* stream) {
+    RCN_CHECK_ARG(y && mu && scale && table && symbols && indexes, "rcn_gaussian_conditional_coded: null pointer");
+    RCN_CHECK_ARG(cdf && cdf_len && cdf_off && packed && esc_count && esc_pos && esc_raw && esc_cap > 0,
+                  "rcn_gaussian_conditional_coded: coder tables / outputs missing");
+    RCN_CHECK_ARG(ntable >= 2 && ntable <= 64, "rcn_gaussian_conditional_coded: scale table must have 2..64 entries");
+    const long long npix = (long long)N * HW;
+    RansPrep rp{cdf, cdf_stride, cdf_len, cdf_off, packed, esc_count, esc_pos, esc_raw, esc_cap, pos_base};
+    gaussian_kernel<<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(y, ldy, mu, ldm, scale, lds, npix, C, HW, table, ntable,
+                                                                           scale_bound, lik_bound, y_hat, ldyh, lik, ldl, symbols, indexes, rp);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_gaussian_conditional_coded");
     return RCN_OK;
 }
 

