@@ -164,16 +164,14 @@ int rcn_gaussian_conditional(const float* y, int ldy, const float* mu, int ldm, 
                              float* y_hat, int ldyh, float* lik, int ldl, int* symbols, int* indexes, void* stream);
 /* Same kernel, plus the range coder's per-symbol front end executed on the GPU: for every symbol the CDF row
  * `indexes[o]` of the (device-resident) integer tables is looked up and packed[o] = (start << 16) | (freq - 1) is
- * written in coding order; symbols outside the row's range take the sentinel bin and are appended (atomically,
- * unordered) to the escape list as (pos_base + o, bypass payload).  This is the work
- * BufferedRansEncoder.encode_with_indexes does per symbol on the host (models/raw2bit.py:1956); only the serial
- * state chain (rcn_rans_encode_packed) is left for the CPU.  esc_count must be zeroed by the caller. */
+ * written in coding order; symbols outside the row's range take the sentinel bin, get flags[o] = 1 and leave their
+ * bypass payload in raw[o].  This is the work BufferedRansEncoder.encode_with_indexes does per symbol on the host
+ * (models/raw2bit.py:1956); only the serial state chain (rcn_rans_encode_packed) is left for the CPU. */
 int rcn_gaussian_conditional_coded(const float* y, int ldy, const float* mu, int ldm, const float* scale, int lds, int N,
                                    long long HW, int C, const float* table, int ntable, float scale_bound,
                                    float lik_bound, float* y_hat, int ldyh, float* lik, int ldl, int* symbols,
                                    int* indexes, const int* cdf, int cdf_stride, const int* cdf_len, const int* cdf_off,
-                                   unsigned* packed, int* esc_count, long long* esc_pos, unsigned* esc_raw, int esc_cap,
-                                   long long pos_base, void* stream);
+                                   unsigned* packed, unsigned* raw, unsigned char* flags, void* stream);
 /* decoder side: indexes only (models/raw2bit.py:2011) and y_hat = symbol + mu (models/raw2bit.py:2014-2015) */
 int rcn_build_indexes(const float* scale, int lds, int N, long long HW, int C, const float* table, int ntable,
                       float scale_bound, int* indexes, void* stream);
@@ -187,9 +185,9 @@ long long rcn_rans_encode(const int32_t* symbols, const int32_t* indexes, long l
                           int cdf_stride, const int32_t* cdf_sizes, const int32_t* offsets, uint8_t* out,
                           long long out_cap);
 /* Back end of the same coder for symbols pre-digested by rcn_gaussian_conditional_coded: HOST arrays packed[n],
- * esc_pos/esc_raw[nesc] (any order).  Produces the identical byte stream as rcn_rans_encode on (symbols, indexes). */
-long long rcn_rans_encode_packed(const uint32_t* packed, long long n, const long long* esc_pos, const uint32_t* esc_raw,
-                                 long long nesc, uint8_t* out, long long out_cap);
+ * raw[n], flags[n].  Produces the identical byte stream as rcn_rans_encode on (symbols, indexes). */
+long long rcn_rans_encode_packed(const uint32_t* packed, const uint32_t* raw, const uint8_t* flags, long long n,
+                                 uint8_t* out, long long out_cap);
 /* RansDecoder.set_stream / decode_stream (models/raw2bit.py:1996-1997,2013): state persists across calls */
 typedef struct rcn_rans_decoder rcn_rans_decoder;
 rcn_rans_decoder* rcn_rans_decoder_create(const uint8_t* stream, long long nbytes);

@@ -56,13 +56,13 @@ PROTOTYPES = {
     "rcn_eb_dequantize": (_I, [_P, _I, _L, _I, _P, _P, _I, _P]),
     "rcn_gaussian_conditional": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P, _I, _F, _F, _P, _I, _P, _I, _P, _P, _P]),
     "rcn_gaussian_conditional_coded": (_I, [_P, _I, _P, _I, _P, _I, _I, _L, _I, _P, _I, _F, _F, _P, _I, _P, _I, _P, _P,
-                                             _P, _I, _P, _P, _P, _P, _P, _P, _I, _L, _P]),
+                                             _P, _I, _P, _P, _P, _P, _P, _P]),
     "rcn_build_indexes": (_I, [_P, _I, _I, _L, _I, _P, _I, _F, _P, _P]),
     "rcn_gaussian_dequantize": (_I, [_P, _P, _I, _I, _L, _I, _P, _I, _P]),
     "rcn_groupmix_workspace_floats": (_L, [_I, _L, _I, _I]),
     "rcn_groupmix_attention": (_I, [_P, _I, _P, _I, _P, _I, _P, _I, _I, _L, _I, _I, _F, _P, _I, _P, _P, _L, _P]),
     "rcn_rans_encode": (_L, [_P, _P, _L, _P, _I, _P, _P, _P, _L]),
-    "rcn_rans_encode_packed": (_L, [_P, _L, _P, _P, _L, _P, _L]),
+    "rcn_rans_encode_packed": (_L, [_P, _P, _P, _L, _P, _L]),
     "rcn_rans_decoder_create": (_P, [_P, _L]),
     "rcn_rans_decode": (_I, [_P, _P, _L, _P, _I, _P, _P, _P]),
     "rcn_rans_decoder_destroy": (None, [_P]),

@@ -79,7 +79,7 @@ __global__ void eb_dequant_kernel(const int* __restrict__ symbols /*NCHW*/, long
 
 struct RansPrep {
     const int* cdf; int cdf_stride; const int* cdf_len; const int* cdf_off;
-    unsigned* packed; int* esc_count; long long* esc_pos; unsigned* esc_raw; int esc_cap; long long pos_base;
+    unsigned* packed; unsigned* raw; unsigned char* flags;   // per symbol, coding order; raw valid where flags != 0
 };
 
 // Gaussian conditional on one slice: y, mu, scale are NHWC channel slices (npix, C).
@@ -117,8 +117,8 @@ __global__ void gaussian_kernel(const float* __restrict__ y, int ldy, const floa
             indexes[o] = idx;
             if (rp.packed) {
                 // range-coder front end (the per-symbol CDF lookup of BufferedRansEncoder.encode_with_indexes,
-                // raw2bit.py:1956): (start << 16) | (freq - 1); out-of-range values take the sentinel bin and are
-                // appended to the escape list (position, bypass payload) for the host state chain.
+                // raw2bit.py:1956): (start << 16) | (freq - 1); out-of-range values take the sentinel bin, set their
+                // flag byte and leave the bypass payload in raw[] for the host state chain.
                 const int sentinel = rp.cdf_len[idx] - 2;
                 int v = (int)q - rp.cdf_off[idx];
                 unsigned raw = 0u;
@@ -128,10 +128,8 @@ __global__ void gaussian_kernel(const float* __restrict__ y, int ldy, const floa
                 const int* row = rp.cdf + (long long)idx * rp.cdf_stride;
                 const unsigned st = (unsigned)row[v], fr = (unsigned)(row[v + 1] - row[v]);
                 rp.packed[o] = (st << 16) | ((fr - 1u) & 0xFFFFu);
-                if (escaped) {
-                    const int k = atomicAdd(rp.esc_count, 1);
-                    if (k < rp.esc_cap) { rp.esc_pos[k] = rp.pos_base + o; rp.esc_raw[k] = raw; }
-                }
+                rp.flags[o] = escaped ? 1 : 0;
+                if (escaped) rp.raw[o] = raw;
             }
         }
     }
@@ -217,14 +215,12 @@ extern "C" int rcn_gaussian_conditional_coded(const float* y, int ldy, const flo
                                               long long HW, int C, const float* table, int ntable, float scale_bound,
                                               float lik_bound, float* y_hat, int ldyh, float* lik, int ldl, int* symbols,
                                               int* indexes, const int* cdf, int cdf_stride, const int* cdf_len, const int* cdf_off,
-                                              unsigned* packed, int* esc_count, long long* esc_pos, unsigned* esc_raw, int esc_cap,
-                                              long long pos_base, void* stream) {
+                                              unsigned* packed, unsigned* raw, unsigned char* flags, void* stream) {
     RCN_CHECK_ARG(y && mu && scale && table && symbols && indexes, "rcn_gaussian_conditional_coded: null pointer");
-    RCN_CHECK_ARG(cdf && cdf_len && cdf_off && packed && esc_count && esc_pos && esc_raw && esc_cap > 0,
-                  "rcn_gaussian_conditional_coded: coder tables / outputs missing");
+    RCN_CHECK_ARG(cdf && cdf_len && cdf_off && packed && raw && flags, "rcn_gaussian_conditional_coded: coder tables / outputs missing");
     RCN_CHECK_ARG(ntable >= 2 && ntable <= 64, "rcn_gaussian_conditional_coded: scale table must have 2..64 entries");
     const long long npix = (long long)N * HW;
-    RansPrep rp{cdf, cdf_stride, cdf_len, cdf_off, packed, esc_count, esc_pos, esc_raw, esc_cap, pos_base};
+    RansPrep rp{cdf, cdf_stride, cdf_len, cdf_off, packed, raw, flags};
     gaussian_kernel<<<ew_blocks(npix * C), 256, 0, (cudaStream_t)stream>>>(y, ldy, mu, ldm, scale, lds, npix, C, HW, table, ntable,
                                                                            scale_bound, lik_bound, y_hat, ldyh, lik, ldl, symbols, indexes, rp);
     count_launch();

@@ -197,22 +197,17 @@ extern "C" long long rcn_rans_encode(const int32_t* symbols, const int32_t* inde
 }
 
 // Back end only: the per-symbol CDF lookups were done on the GPU (rcn_gaussian_conditional_coded); the host runs the
-// serial state chain over packed = (start << 16) | (freq - 1) plus the (position, payload) list of escaped symbols.
-extern "C" long long rcn_rans_encode_packed(const uint32_t* packed, long long n, const long long* esc_pos, const uint32_t* esc_raw,
-                                            long long nesc, uint8_t* out, long long out_cap) {
-    if ((n > 0 && !packed) || n < 0 || nesc < 0 || (nesc > 0 && (!esc_pos || !esc_raw)) || !out) {
+// serial state chain over packed = (start << 16) | (freq - 1), with flags[i] != 0 marking escaped symbols whose bypass
+// payload is raw[i].
+extern "C" long long rcn_rans_encode_packed(const uint32_t* packed, const uint32_t* raw, const uint8_t* flags, long long n,
+                                            uint8_t* out, long long out_cap) {
+    if ((n > 0 && (!packed || !raw || !flags)) || n < 0 || !out) {
         rcn::set_error("rcn_rans_encode_packed: bad arguments");
         return RCN_ERR_INVALID;
     }
-    std::vector<Escape> escapes((size_t)nesc);
-    for (long long i = 0; i < nesc; ++i) {
-        if (esc_pos[i] < 0 || esc_pos[i] >= n) {
-            rcn::set_error("rcn_rans_encode_packed: escape position out of range");
-            return RCN_ERR_INVALID;
-        }
-        escapes[(size_t)i] = {esc_pos[i], esc_raw[i]};
-    }
-    std::sort(escapes.begin(), escapes.end(), [](const Escape& a, const Escape& b) { return a.pos < b.pos; });
+    std::vector<Escape> escapes;
+    for (long long i = 0; i < n; ++i)
+        if (flags[i]) escapes.push_back({i, raw[i]});
     return state_chain(packed, n, escapes, out, out_cap);
 }
 

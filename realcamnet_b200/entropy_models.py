@@ -63,15 +63,18 @@ def rans_encode(symbols, indexes, cdf, cdf_length, offset) -> bytes:
 _C_ERR_NOMEM = -3
 
 
-def rans_encode_packed(packed, esc_pos, esc_raw) -> bytes:
+def rans_encode_packed(packed, raw, flags) -> bytes:
     """State chain only: `packed` = (start << 16) | (freq - 1) per symbol from the GPU front end
-    (rcn_gaussian_conditional_coded) plus the list of escaped symbols.  Same bytes as rans_encode()."""
+    (rcn_gaussian_conditional_coded); flags[i] != 0 marks an escaped symbol with bypass payload raw[i].
+    Same bytes as rans_encode()."""
     packed = np.ascontiguousarray(packed).reshape(-1).view(np.uint32)
-    esc_pos = np.ascontiguousarray(esc_pos, dtype=np.int64).reshape(-1)
-    esc_raw = np.ascontiguousarray(esc_raw).reshape(-1).view(np.uint32)
-    cap = 4 * packed.size + 48 * esc_pos.size + 64
+    raw = np.ascontiguousarray(raw).reshape(-1).view(np.uint32)
+    flags = np.ascontiguousarray(flags, dtype=np.uint8).reshape(-1)
+    if not (packed.size == raw.size == flags.size):
+        raise ValueError("packed, raw and flags must have the same length")
+    cap = 4 * packed.size + 48 * int(np.count_nonzero(flags)) + 64
     out = np.empty(cap, dtype=np.uint8)
-    n = _C.lib().rcn_rans_encode_packed(_ip(packed), packed.size, _ip(esc_pos), _ip(esc_raw), esc_pos.size, _ip(out), cap)
+    n = _C.lib().rcn_rans_encode_packed(_ip(packed), _ip(raw), _ip(flags), packed.size, _ip(out), cap)
     _C.check(n, "rcn_rans_encode_packed")
     return out[:n].tobytes()
 

@@ -382,15 +382,13 @@ def eb_dequantize(symbols, medians):
 class CoderPrep:
     """Device-side buffers for the GPU front end of the range coder (rcn_gaussian_conditional_coded)."""
 
-    def __init__(self, nsym, cdf, cdf_len, cdf_off, esc_cap=1 << 16):
+    def __init__(self, nsym, cdf, cdf_len, cdf_off):
         dev = cdf.device
         self.cdf, self.cdf_len, self.cdf_off = cdf.contiguous(), cdf_len.contiguous(), cdf_off.contiguous()
         assert self.cdf.dtype == torch.int32 and self.cdf_len.dtype == torch.int32 and self.cdf_off.dtype == torch.int32
         self.packed = torch.empty((nsym,), device=dev, dtype=torch.int32)   # bit pattern (start << 16) | (freq - 1)
-        self.esc_count = torch.zeros((1,), device=dev, dtype=torch.int32)
-        self.esc_pos = torch.empty((esc_cap,), device=dev, dtype=torch.int64)
-        self.esc_raw = torch.empty((esc_cap,), device=dev, dtype=torch.int32)
-        self.esc_cap = esc_cap
+        self.raw = torch.empty((nsym,), device=dev, dtype=torch.int32)      # bypass payload where flags != 0
+        self.flags = torch.empty((nsym,), device=dev, dtype=torch.uint8)
 
 
 def gaussian_conditional(y, mu, scale, table, y_hat=None, lik=None, symbols=None, indexes=None, scale_bound=0.11,
@@ -401,12 +399,12 @@ def gaussian_conditional(y, mu, scale, table, y_hat=None, lik=None, symbols=None
     ldl = geom(lik)[4] if lik is not None else 0
     if coder is not None:
         n = N * C * H * W
-        packed = coder.packed[pos_base:pos_base + n]
+        sl_ = slice(pos_base, pos_base + n)
         _C.check(_C.lib().rcn_gaussian_conditional_coded(
             _ptr(y), ldy, _ptr(mu), ldm, _ptr(scale), lds, N, H * W, C, _ptr(table), table.numel(), scale_bound, lik_bound,
             _ptr(y_hat), ldyh, _ptr(lik), ldl, _ptr(symbols), _ptr(indexes), _ptr(coder.cdf), coder.cdf.shape[1],
-            _ptr(coder.cdf_len), _ptr(coder.cdf_off), _ptr(packed), _ptr(coder.esc_count), _ptr(coder.esc_pos),
-            _ptr(coder.esc_raw), coder.esc_cap, pos_base, _stream()), "rcn_gaussian_conditional_coded")
+            _ptr(coder.cdf_len), _ptr(coder.cdf_off), _ptr(coder.packed[sl_]), _ptr(coder.raw[sl_]), _ptr(coder.flags[sl_]),
+            _stream()), "rcn_gaussian_conditional_coded")
         return
     _C.check(_C.lib().rcn_gaussian_conditional(
         _ptr(y), ldy, _ptr(mu), ldm, _ptr(scale), lds, N, H * W, C, _ptr(table), table.numel(), scale_bound, lik_bound,

@@ -439,14 +439,14 @@ class raw_compression_tcm_final(CompressionModel):
             self._finish_slice(i, lrp_sup, cin, ms, ss)
         # the coder front end (CDF lookups) ran inside the Gaussian kernel; start the D2H copy of its packed output on a
         # side stream so the host state chain runs WHILE the synthesis transform g_s (half of the FLOPs) executes
-        pending = self._begin_host_copy(coder.packed, coder.esc_count, coder.esc_pos, coder.esc_raw, z_sym) if emit_strings else None
+        pending = self._begin_host_copy(coder.packed, coder.raw, coder.flags, z_sym) if emit_strings else None
         x_hat = self._g_s(ms[..., 320:])
         y_nchw = ops.to_nchw(y)
         out = {"x_hat": x_hat, "y": y_nchw, "lft": ops.to_nchw(local[2]), "lsc": ops.to_nchw(lsc_fea),
                "likelihoods": {"y": ops.to_nchw(y_lik), "z": ops.to_nchw(z_lik)},
                "para": {"means": ops.to_nchw(means), "scales": ops.to_nchw(scales), "y": y_nchw}}
         if emit_strings:
-            out["strings"] = [[self._finish_y_string(pending, sym, idx)], self.entropy_bottleneck.compress_symbols(pending[1][4])]
+            out["strings"] = [[self._finish_y_string(pending, sym, idx)], self.entropy_bottleneck.compress_symbols(pending[1][3])]
             out["shape"] = torch.Size(z.shape[1:3])
         return out
 
@@ -456,15 +456,12 @@ class raw_compression_tcm_final(CompressionModel):
             raise RuntimeError("call update() before producing bitstreams (models/raw2bit.py:1759-1764)")
         return ops.CoderPrep(nsym, gc._quantized_cdf, gc._cdf_length, gc._offset)
 
-    def _finish_y_string(self, pending, sym, idx):
-        """Host state chain over the GPU-prepared symbols (falls back to the full host coder if the escape list overflowed)."""
+    def _finish_y_string(self, pending, sym=None, idx=None):
+        """Host state chain over the GPU-prepared symbols."""
         from .entropy_models import rans_encode_packed
 
-        h_packed, h_cnt, h_pos, h_raw = self._end_host_copy(pending)[:4]
-        nesc = int(h_cnt[0])
-        if nesc > h_pos.numel():
-            return self._encode_y(sym, idx)
-        return rans_encode_packed(h_packed.numpy(), h_pos.numpy()[:nesc], h_raw.numpy()[:nesc])
+        h_packed, h_raw, h_flags = self._end_host_copy(pending)[:3]
+        return rans_encode_packed(h_packed.numpy(), h_raw.numpy(), h_flags.numpy())
 
     def _begin_host_copy(self, *tensors):
         """Async device->pinned-host copies on a side stream, ordered after the work already queued."""
@@ -525,7 +522,7 @@ class raw_compression_tcm_final(CompressionModel):
                                      symbols=sym[i], indexes=idx[i], scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound,
                                      coder=coder, pos_base=i * nslice)
             self._finish_slice(i, lrp_sup, cin, ms, ss)
-        pending = self._begin_host_copy(coder.packed, coder.esc_count, coder.esc_pos, coder.esc_raw)
+        pending = self._begin_host_copy(coder.packed, coder.raw, coder.flags)
         return {"strings": [[self._finish_y_string(pending, sym, idx)], z_strings], "shape": torch.Size(z.shape[1:3])}
 
     @torch.no_grad()
