@@ -262,11 +262,16 @@ def main():
     torch.cuda.synchronize()
     kms = e0.elapsed_time(e1) / reps
     ach = work / (kms / 1e3) / 1e12
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the one `ncu --set full` capture of THIS launch at
+    # T=2048 (profiles/r1_conv_tcgen05_ncu_full.md: 2.156 + 2.107 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
+    # other tile sizes were not captured.
+    traffic = {("bf16x3", 2048): 4.263066e9, ("fp32", 2048): 4.257296e9}.get((args.engine, T))
     roofline = {"kernel": kname + " -- 3x3 128->128 @ full res (g_s tail)", "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kms, "peak_source": peaks["_src"] + ", " + peak_note,
                 "algorithmic_tflop_per_launch": kflop / 1e12, "tensor_tflop_per_launch": work / 1e12,
                 "algorithmic_tflops": kflop / (kms / 1e3) / 1e12,
+                "traffic_unit": "bytes/launch (ncu dram read+write); algorithmic bytes = 4.29e9 (bf16 hi+lo planes in, fp32 map out)",
                 "step_tflops": world * FLOP_PER_PACKED_POS * T * T * args.steps / (ms / 1e3) / 1e12}
     del a, o
 
