@@ -89,6 +89,10 @@ typedef struct rcn_conv_desc {
     const float* res; int ldres; int res_pre;  /* res has the geometry of the stored output */
     int act; float slope;
     float res_scale;     /* multiplies res (2.0 for `conv_block(x) + x` of ConvTransBlock, models/tcm.py:262) */
+    /* optional (tcgen05 engine, RCN_STORE_NHWC / RCN_STORE_PS2 with Cp_out % 64 == 0 stored channels): also write the result
+     * as the NEXT layer's bf16 hi/lo operand planes (pixel stride Cp_out), so that layer needs no rcn_split_bf16 pass.
+     * y may then be NULL (planes only: the fp32 tensor of a conv->conv chain is never materialised). */
+    void* y_hi; void* y_lo; int Cp_out;
 } rcn_conv_desc;
 
 int rcn_conv2d(const rcn_conv_desc* d, void* stream);

@@ -76,9 +76,10 @@ class Lens_Shading_Correction(nn.Module):
             Conv2d(nf, out_c, 1, 1))
 
     def _f(self, x):
-        for i in (0, 2, 4):
-            x = self.model[i]._f(x, act=ACT_LRELU, slope=0.1)
-        return self.model[6]._f(x)
+        sp = None
+        for i in (0, 2, 4):   # per-pixel MLP: the hidden maps only exist as the next layer's bf16 planes
+            x, sp = self.model[i]._f(x, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
+        return self.model[6]._f(x, presplit=sp)
 
     def forward(self, img_input):
         return ops.to_nchw(self._f(ops.to_nhwc(img_input)))
@@ -103,8 +104,9 @@ class Res_GFM(nn.Module):
         """x NHWC, vec (N,1,1,cond_c)"""
         scale = self.GFM_scale_conv1._f(self.GFM_scale_conv0._f(vec, act=ACT_LRELU, slope=0.1))
         shift = self.GFM_shift_conv1._f(self.GFM_shift_conv0._f(vec, act=ACT_LRELU, slope=0.1))
-        fea = self.conv0._f(x, cscale=scale.reshape(-1), cshift=shift.reshape(-1), act=ACT_LRELU, slope=0.01)
-        return self.conv1._f(fea, res=x)
+        fea, sp = self.conv0._f(x, cscale=scale.reshape(-1), cshift=shift.reshape(-1), act=ACT_LRELU, slope=0.01,
+                                emit_split=True, keep_fp32=False)
+        return self.conv1._f(fea, res=x, presplit=sp)
 
     def forward(self, x):
         fea = self._f(ops.to_nhwc(x[0]), x[1].reshape(x[1].shape[0], 1, 1, -1).contiguous())

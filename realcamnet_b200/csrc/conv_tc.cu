@@ -223,7 +223,21 @@ __device__ __forceinline__ void epilogue_slab(const rcn_conv_desc& p, int dbg, c
                 val[j] = act_ct<ACT>(val[j], p.act, p.slope);
                 if (p.res && !p.res_pre) val[j] += rv[j];
             }
-            if (!(dbg & 1)) *reinterpret_cast<float4*>(p.y + opix[u] * p.ldy + och[u]) = make_float4(val[0], val[1], val[2], val[3]);
+            if (!(dbg & 1)) {
+                if (p.y) *reinterpret_cast<float4*>(p.y + opix[u] * p.ldy + och[u]) = make_float4(val[0], val[1], val[2], val[3]);
+                if (p.y_hi) {
+                    // the consumer's tcgen05 operand planes: x = hi + lo in bf16 (same rounding as rcn_split_bf16)
+                    __nv_bfloat16 hh[4], ll[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        hh[j] = __float2bfloat16_rn(val[j]);
+                        ll[j] = __float2bfloat16_rn(val[j] - __bfloat162float(hh[j]));
+                    }
+                    const long long po = opix[u] * p.Cp_out + och[u];
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_hi) + po) = *reinterpret_cast<uint2*>(hh);
+                    if (p.y_lo) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_lo) + po) = *reinterpret_cast<uint2*>(ll);
+                }
+            }
         }
     } else {
         const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
@@ -412,7 +426,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const bool vec = !(P.dbg & 8) && ((p.store == RCN_STORE_NHWC && (p.Cout & 3) == 0) ||
                                           (p.store == RCN_STORE_PS2 && (p.Cout & 15) == 0 && p.epi == RCN_EPI_NONE)) &&
                          ((p.ldy & 3) == 0) &&
-                         ((reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
+                         (!p.y || (reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
                          (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
                          (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
@@ -604,7 +618,18 @@ extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, i
 
 extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, int Cp,
                              int passes, void* stream) {
-    RCN_CHECK_ARG(d && d->y && x_hi && w_hi, "rcn_conv2d_tc: null pointer");
+    RCN_CHECK_ARG(d && (d->y || d->y_hi) && x_hi && w_hi, "rcn_conv2d_tc: null pointer");
+    if (d->y_hi) {
+        const bool ps2 = d->store == RCN_STORE_PS2;
+        const int cs = ps2 ? d->Cout / 4 : d->Cout;
+        RCN_CHECK_ARG((d->store == RCN_STORE_NHWC || ps2) && d->Cp_out == cs && (cs % 64) == 0 && (!ps2 || d->epi == RCN_EPI_NONE) &&
+                          (!d->y || ((d->ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0)) &&
+                          (!d->res || ((d->ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0)) &&
+                          (d->epi == RCN_EPI_NONE || ((d->ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)) &&
+                          (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0),
+                      "rcn_conv2d_tc: operand-plane emission needs an NHWC / pixel-shuffle store with a multiple of 64 stored "
+                      "channels and 16-byte aligned tensors");
+    }
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
     RCN_CHECK_ARG(d->stride == 1 || d->stride == 2, "rcn_conv2d_tc: stride %d unsupported", d->stride);

@@ -57,7 +57,8 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def _f(self, x, res=None, out=None):
-        return self.fc2._f(self.fc1._f(x, act=ACT_GELU), res=res, out=out)
+        h, sp = self.fc1._f(x, act=ACT_GELU, emit_split=True, keep_fp32=False)
+        return self.fc2._f(h, res=res, out=out, presplit=sp)
 
     def forward(self, x):
         shp = x.shape

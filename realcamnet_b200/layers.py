@@ -138,8 +138,8 @@ class ResidualBlockWithStride(_Block):
     def _f(self, x, out=None):
         # conv1 and the 1x1 skip read the same tensor with the same stride: one bf16 split serves both
         sp = ops.shared_split(x, [ops.pack(self.conv1), ops.pack(self.skip)], self.conv1.stride[0]) if self.skip is not None else None
-        t = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=sp)
-        t = self.conv2._f(t)
+        t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
+        t = self.conv2._f(t, presplit=tsp)
         identity = x if self.skip is None else self.skip._f(x, presplit=sp)
         return self.gdn._f(t, res=identity, out=out)
 
@@ -155,8 +155,8 @@ class ResidualBlockUpsample(_Block):
 
     def _f(self, x, out=None):
         sp = ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
-        t = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp)
-        t = self.conv._f(t)
+        t, tsp = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
+        t = self.conv._f(t, presplit=tsp)
         t = self.igdn._f(t)
         return self.upsample._f(x, res=t, out=out, presplit=sp)
 
@@ -171,11 +171,12 @@ class ResidualBlock(_Block):
 
     def _f(self, x, out=None, extra_identity=False):
         """extra_identity: also add x once more (ConvTransBlock's ``conv_block(x) + x``)."""
-        t = self.conv1._f(x, act=ACT_LRELU, slope=0.01)
+        t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, emit_split=True, keep_fp32=False)
         identity = x if self.skip is None else self.skip._f(x)
         if extra_identity and self.skip is not None:
             raise ValueError("extra_identity needs in_ch == out_ch")
-        return self.conv2._f(t, act=ACT_LRELU, slope=0.01, res=identity, res_scale=2.0 if extra_identity else 1.0, out=out)
+        return self.conv2._f(t, act=ACT_LRELU, slope=0.01, res=identity, res_scale=2.0 if extra_identity else 1.0, out=out,
+                             presplit=tsp)
 
 
 class AttentionBlock(_Block):
@@ -192,9 +193,9 @@ class AttentionBlock(_Block):
                 self.relu = nn.ReLU(inplace=True)
 
             def _f(self, x):
-                t = self.conv[0]._f(x, act=ACT_RELU)
-                t = self.conv[2]._f(t, act=ACT_RELU)
-                return self.conv[4]._f(t, res=x, res_pre=True, act=ACT_RELU)
+                t, sp = self.conv[0]._f(x, act=ACT_RELU, emit_split=True, keep_fp32=False)
+                t, sp = self.conv[2]._f(t, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+                return self.conv[4]._f(t, res=x, res_pre=True, act=ACT_RELU, presplit=sp)
 
         self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
         self.conv_b = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit(), conv1x1(N, N))

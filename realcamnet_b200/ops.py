@@ -172,8 +172,21 @@ def shared_split(x, pcs, stride=1):
 
 
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
-           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None):
-    N, H, W, Cin, ldx = geom(x, "conv2d.x")
+           cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None,
+           emit_split=False, keep_fp32=True):
+    """One conv / linear layer with its fused epilogue.
+
+    x may be None when `presplit` carries operand planes that a previous tcgen05 conv emitted (conv->conv chains never
+    materialise the fp32 intermediate).  emit_split=True returns (out, SplitOperand | None): the epilogue additionally
+    writes the NEXT layer's bf16 hi/lo planes; with keep_fp32=False `out` is None when that was possible."""
+    eng = engine or _ENGINE
+    if x is None:
+        if presplit is None or presplit.key[7] != 1:
+            raise ValueError("conv2d: x=None needs stride-1 operand planes from a previous layer")
+        N, H, W = presplit.hi.shape[0], presplit.hi.shape[1], presplit.hi.shape[2]
+        Cin, ldx = presplit.key[4], 0
+    else:
+        N, H, W, Cin, ldx = geom(x, "conv2d.x")
     if Cin != pc.cin:
         raise ValueError(f"conv2d: input has {Cin} channels, weight expects {pc.cin}")
     pad = pc.k // 2
@@ -181,26 +194,35 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     Wo = (W + 2 * pad - pc.k) // stride + 1
     ps = store in (STORE_PS2, STORE_PS2_NCHW)
     Hs, Ws, Cs = (2 * Ho, 2 * Wo, pc.cout // 4) if ps else (Ho, Wo, pc.cout)
-    if out is None:
+    use_tc = eng != "fp32" and pc.w_hi is not None and (stride == 1 or (H % 2 == 0 and W % 2 == 0))
+    if x is None and not use_tc:
+        raise ValueError("conv2d: operand planes can only feed the tcgen05 engine")
+    dev = x.device if x is not None else presplit.hi.device
+    can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and Cs % 64 == 0 and
+                (store != STORE_PS2 or epi == EPI_NONE) and pc.cout % 16 == 0)
+    want_out = keep_fp32 or not can_emit or out is not None
+    if want_out and out is None:
         if store in (STORE_NCHW, STORE_PS2_NCHW):
-            out = torch.empty((N, Cs, Hs, Ws), device=x.device, dtype=torch.float32)
+            out = torch.empty((N, Cs, Hs, Ws), device=dev, dtype=torch.float32)
         else:
-            out = torch.empty((N, Hs, Ws, Cs), device=x.device, dtype=torch.float32)
-    if store in (STORE_NCHW, STORE_PS2_NCHW):
-        if tuple(out.shape) != (N, Cs, Hs, Ws) or not out.is_contiguous():
-            raise ValueError("conv2d: NCHW output must be contiguous with the right shape")
-        ldy = 0
-    else:
-        oN, oH, oW, oC, ldy = geom(out, "conv2d.out")
-        if (oN, oH, oW, oC) != (N, Hs, Ws, Cs):
-            raise ValueError(f"conv2d: output shape {tuple(out.shape)} != {(N, Hs, Ws, Cs)}")
+            out = torch.empty((N, Hs, Ws, Cs), device=dev, dtype=torch.float32)
+    ldy = 0
+    if out is not None:
+        if store in (STORE_NCHW, STORE_PS2_NCHW):
+            if tuple(out.shape) != (N, Cs, Hs, Ws) or not out.is_contiguous():
+                raise ValueError("conv2d: NCHW output must be contiguous with the right shape")
+        else:
+            oN, oH, oW, oC, ldy = geom(out, "conv2d.out")
+            if (oN, oH, oW, oC) != (N, Hs, Ws, Cs):
+                raise ValueError(f"conv2d: output shape {tuple(out.shape)} != {(N, Hs, Ws, Cs)}")
     d = _C.ConvDesc()
-    d.x, d.N, d.H, d.W, d.Cin, d.ldx = x.data_ptr(), N, H, W, Cin, ldx
+    d.x, d.N, d.H, d.W, d.Cin, d.ldx = (x.data_ptr() if x is not None else None), N, H, W, Cin, ldx
     d.w = pc.w.data_ptr()
     d.bias = pc.bias.data_ptr() if (bias and pc.bias is not None) else None
     d.k, d.stride, d.Cout, d.in_square = pc.k, stride, pc.cout, int(in_square)
-    d.y, d.ldy, d.store = out.data_ptr(), ldy, store
+    d.y, d.ldy, d.store = (out.data_ptr() if out is not None else None), ldy, store
     d.epi = epi
+    lda = ldr = 0
     if epi != EPI_NONE:
         aN, aH, aW, aC, lda = geom(aux, "conv2d.aux")
         if (aN, aH, aW, aC) != (N, Ho, Wo, pc.cout):
@@ -216,18 +238,32 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
             raise ValueError(f"conv2d: residual shape {tuple(res.shape)} != {(N, Hs, Ws, Cs)}")
         d.res, d.ldres, d.res_pre = res.data_ptr(), ldr, int(res_pre)
     d.act, d.slope, d.res_scale = act, float(slope), float(res_scale)
-    eng = engine or _ENGINE
-    if eng != "fp32" and pc.w_hi is not None and (stride == 1 or (H % 2 == 0 and W % 2 == 0)):
-        # tcgen05 path: split the fp32 activations into bf16 hi/lo planes (x*x for the GDN pool), TMA + UMMA conv
+    sp_out = None
+    if can_emit:   # alignment requirements of the 16-byte epilogue path
+        ok = (ldy % 4 == 0 and (out is None or out.data_ptr() % 16 == 0) and lda % 4 == 0 and ldr % 4 == 0 and
+              (aux is None or aux.data_ptr() % 16 == 0) and (res is None or res.data_ptr() % 16 == 0))
+        if ok:
+            passes_out = 3 if _ENGINE == "bf16x3" else 1
+            y_hi = torch.empty((N, Hs, Ws, Cs), device=dev, dtype=torch.bfloat16)
+            y_lo = torch.empty_like(y_hi) if passes_out == 3 else None
+            d.y_hi, d.y_lo, d.Cp_out = y_hi.data_ptr(), (y_lo.data_ptr() if y_lo is not None else None), Cs
+            sp_out = SplitOperand(y_hi, y_lo, (None, N, Hs, Ws, Cs, None, Cs, 1, False))
+        elif out is None:
+            raise ValueError("conv2d: cannot drop the fp32 output of a layer whose epilogue is not 16-byte aligned")
+    if use_tc:
+        # tcgen05 path: bf16 hi/lo operand planes (from the producer's epilogue, a shared split, or a split pass here)
         passes = 3 if eng == "bf16x3" else 1
         sp = presplit if presplit is not None else split_operand(x, pc.cp, stride, in_square, passes)
-        if sp.key != (x.data_ptr(), N, H, W, Cin, ldx, pc.cp, stride, bool(in_square)) or (passes == 3 and sp.lo is None):
+        k0 = sp.key
+        same = (k0[1:5] == (N, H, W, Cin) and k0[6:] == (pc.cp, stride, bool(in_square)) and
+                (k0[0] is None or (x is not None and k0[0] == x.data_ptr() and k0[5] == ldx)))
+        if not same or (passes == 3 and sp.lo is None):
             raise ValueError("conv2d: presplit operand does not belong to this input / layer geometry")
         _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
                                         _stream()), "rcn_conv2d_tc")
-        return out
-    _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")
-    return out
+    else:
+        _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")
+    return (out, sp_out) if emit_split else out
 
 
 def layernorm(x, weight, bias, eps=1e-5, out=None, act=ACT_NONE):

@@ -80,10 +80,10 @@ class SpatialFeatureTransform(nn.Module):
         if not self.residual:
             raise NotImplementedError("residual=False is never used by the reference")
         sp = ops.shared_split(cond, [ops.pack(self.cond_scale[0]), ops.pack(self.cond_shift[0])])
-        s = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp)
-        t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra)      # (scale + 1) * x (+ extra)
-        h = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp)
-        return self.cond_shift[2]._f(h, res=t, out=out)                        # shift + ...
+        s, ssp = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+        t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra, presplit=ssp)      # (scale + 1) * x (+ extra)
+        h, hsp = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+        return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp)                        # shift + ...
 
     def forward(self, x, cond):
         return ops.to_nchw(self._f(ops.to_nhwc(x), ops.to_nhwc(cond)))
@@ -147,7 +147,8 @@ class HyCondModEncBlock(nn.Module):
         self.conv = HyCondModConvBlock(out_channels, out_channels)
 
     def _f(self, x, out=None):
-        return self.conv._f(self.down._f(x), out=out)
+        t, sp = self.down.conv._f(x, act=self.down._act[0], slope=self.down._act[1], emit_split=True, keep_fp32=False)
+        return self.conv.conv._f(t, act=self.conv._act[0], slope=self.conv._act[1], out=out, presplit=sp)
 
 
 class HyCondModDecBlock(nn.Module):
@@ -226,7 +227,8 @@ class RBU(nn.Module):
 
     def _f(self, x, out=None):
         sp = ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
-        t = self.conv._f(self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp))
+        t, tsp = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
+        t = self.conv._f(t, presplit=tsp)
         return self.upsample._f(x, res=t, out=out, presplit=sp)
 
     def forward(self, x):
@@ -239,9 +241,9 @@ def _cc_transform(in_ch, out_ch):
 
 
 def _run_cc(seq, x, **last):
-    h = seq[0]._f(x, act=ACT_GELU)
-    h = seq[2]._f(h, act=ACT_GELU)
-    return seq[4]._f(h, **last)
+    h, sp = seq[0]._f(x, act=ACT_GELU, emit_split=True, keep_fp32=False)
+    h, sp = seq[2]._f(h, act=ACT_GELU, presplit=sp, emit_split=True, keep_fp32=False)
+    return seq[4]._f(h, presplit=sp, **last)
 
 
 class raw_compression_tcm_final(CompressionModel):

@@ -80,8 +80,8 @@ class Block(nn.Module):
         t = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps)
         x1 = self.msa._f(t, res=x)
         t = ops.layernorm(x1, self.ln2.weight, self.ln2.bias, self.ln2.eps)
-        h = self.mlp[0]._f(t, act=ACT_GELU)
-        return self.mlp[2]._f(h, res=x1, out=out)
+        h, hsp = self.mlp[0]._f(t, act=ACT_GELU, emit_split=True, keep_fp32=False)   # 4C-wide hidden: planes only
+        return self.mlp[2]._f(h, res=x1, out=out, presplit=hsp)
 
     def forward(self, x):
         return self._f(x.contiguous())
