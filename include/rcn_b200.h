@@ -229,6 +229,10 @@ int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int C
 /* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand) */
 int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream);
 
+/* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
+ * tiles seen, 0.  reset != 0 clears the counters. */
+int rcn_tc_prof(unsigned long long* out4, int reset);
+
 #ifdef __cplusplus
 }
 #endif

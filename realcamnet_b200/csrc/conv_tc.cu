@@ -12,9 +12,10 @@
 // weights are split as x = hi + lo (two bf16 planes) and hi*hi + lo*hi + hi*lo is accumulated in
 // fp32 -- ~16 mantissa bits, which keeps the 1e-3 parity bar through the ~100-layer path.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (TMEM lane quarter = warp_id % 4).  mbarrier ring: full[s] (TMA -> MMA),
-// empty[s] (tcgen05.commit -> TMA), tmem_full (last commit -> epilogue).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, one 64-column half of the accumulator per warp).
+// mbarrier ring: full[s] (TMA -> MMA), empty[s] (tcgen05.commit -> TMA), tmem_full[2] (last commit of a tile ->
+// epilogue), tmem_empty[2] (8 epilogue warps -> MMA issuer): the accumulator is double-buffered in TMEM.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -94,25 +95,6 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
 struct TcParams {
     rcn_conv_desc d;
     int Cp;       // padded input channels (multiple of 64) of the bf16 planes / packed weights
@@ -125,22 +107,22 @@ struct TcParams {
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
 };
 
-constexpr int EPI_WARPS = 16;            // 4 warps per TMEM lane quarter: one warp per scheduler cannot hide any latency
+constexpr int EPI_WARPS = 8;             // 2 warps per TMEM lane quarter (warp_id % 4), each draining 64 accumulator columns
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
-constexpr int STG_COLS = 32;             // accumulator columns staged per epilogue round
-constexpr int STG_PITCH = STG_COLS + 4;  // floats; (pitch/4) odd -> conflict-free float4 rows
-constexpr int STG_BYTES = 128 * STG_PITCH * 4;
+constexpr int SLAB_FLOATS = 32 * 16;     // warp-private transposition slab: 32 pixel rows x 16 floats, 16-byte chunks XOR-swizzled
+constexpr int STG_BYTES = EPI_WARPS * SLAB_FLOATS * 4;   // 16 KB
+// The bias vector is staged in shared memory once per CTA: with ~220 KB of the SM's 228 KB carved out as shared memory there
+// is practically no L1 left, and per-item bias loads from every SM hammer the same few L2 lines (measured: ~7 us per
+// 128x128 tile, the whole epilogue cost of the 1x1 layers).
+constexpr int BIAS_MAX = 2048;
+constexpr int BIAS_BYTES = BIAS_MAX * 4;
 
-template <int ACT>
-__device__ __forceinline__ float act_ct(float v, int act, float slope) {
-    if constexpr (ACT < 0) return act_apply(v, act, slope);
-    else return act_apply(v, ACT, slope);  // constant-folds to the single selected branch
-}
-template <int EPI>
-__device__ __forceinline__ float epi_ct(float v, float a, int epi) {
-    const int e = (EPI < 0) ? epi : EPI;
-    switch (e) {
+// The generic (runtime-selected) variants are real function calls: inlining the full activation switch (erff, tanhf, expf)
+// into the unrolled per-element code multiplies the kernel size and the register pressure for combinations that are rare.
+__device__ __noinline__ float act_generic(float v, int act, float slope) { return act_apply(v, act, slope); }
+__device__ __noinline__ float epi_generic(float v, float a, int epi) {
+    switch (epi) {
         case RCN_EPI_GDN: return a * rsqrtf(v);
         case RCN_EPI_IGDN: return a * sqrtf(v);
         case RCN_EPI_MUL_AUXP1: return v * (a + 1.f);
@@ -149,134 +131,320 @@ __device__ __forceinline__ float epi_ct(float v, float a, int epi) {
         default: return v;
     }
 }
+template <int ACT>
+__device__ __forceinline__ float act_ct(float v, int act, float slope) {
+    if constexpr (ACT < 0) return act_generic(v, act, slope);
+    else return act_apply(v, ACT, slope);  // constant-folds to the single selected branch
+}
+template <int EPI>
+__device__ __forceinline__ float epi_ct(float v, float a, int epi) {
+    if constexpr (EPI < 0) return epi_generic(v, a, epi);
+    else if constexpr (EPI == RCN_EPI_GDN) return a * rsqrtf(v);
+    else if constexpr (EPI == RCN_EPI_IGDN) return a * sqrtf(v);
+    else if constexpr (EPI == RCN_EPI_MUL_AUXP1) return v * (a + 1.f);
+    else if constexpr (EPI == RCN_EPI_MULP1_AUX) return (v + 1.f) * a;
+    else if constexpr (EPI == RCN_EPI_SIGMOID_GATE) return a * (1.f / (1.f + expf(-v)));
+    else return v;
+}
 
-// One staged slab (128 pixels x up to 32 channels starting at channel n0 + c0) -> fused element-wise -> global.
-// ACT / EPI are compile-time so the loop body only holds the math of the selected variant (a runtime switch
-// inside the loop gets if-converted into ALL branches executing predicated: ~1000 instructions per 4 elements).
+// perf triage (RCN_TC_DEBUG & 128): cycles one epilogue warp of CTA 0 spends waiting for accumulators / working, tiles
+__device__ unsigned long long g_tcprof[16];
+__device__ __forceinline__ float4 ldg4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+// Explicit shared-space accesses: the dynamic smem base is re-aligned through an integer cast, after which the compiler only
+// sees generic pointers and emits generic LD/ST for the staging slab.
+__device__ __forceinline__ void sts4(uint32_t addr, float4 t) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+}
+__device__ __forceinline__ float4 lds4(uint32_t addr) {
+    float4 t;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(addr) : "memory");
+    return t;
+}
+__device__ __forceinline__ float lds1(uint32_t addr) {
+    float t;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(addr));
+    return t;
+}
+
+// tcgen05.ld of 16 / 32 accumulator columns for this warp's 32 TMEM lanes.  The load is asynchronous until
+// tcgen05.wait::ld; the wait takes the destination registers as in/out operands so that the compiler cannot read (or move)
+// them before the data has landed.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t* v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+                   "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld16(uint32_t* v) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+__device__ __forceinline__ void epi_release(uint64_t* empty_bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty_bar)) : "memory");
+}
+
+// Launch-invariant epilogue parameters held in REGISTERS.  Reading them from the kernel-parameter constant bank inside the
+// per-element code costs a uniform load + compare + branch chain (~40 cycles each, a dozen per float4: measured ~2000 cycles
+// per 16-column quarter, i.e. the whole cost of the 1x1 layers); the empty asm statements make the values opaque so the
+// compiler cannot rematerialise them from the constant bank.
+struct EpiRegs {
+    float* y; const float* res; const float* aux; const float* cscale; const float* cshift;
+    __nv_bfloat16* y_hi; __nv_bfloat16* y_lo;
+    int H, W, Cout, ldy, ldres, ldaux, cpo;
+    float slope, rpre, rpost;   // residual weights: v = act(v + rpre*res) + rpost*res  (0 when absent)
+    uint32_t flags;
+};
+enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256 };
+template <typename T>
+__device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
+__device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
+__device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg) {
+    EpiRegs r;
+    r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
+    r.y_hi = reinterpret_cast<__nv_bfloat16*>(p.y_hi); r.y_lo = reinterpret_cast<__nv_bfloat16*>(p.y_lo);
+    r.H = p.H; r.W = p.W; r.Cout = p.Cout; r.ldy = p.ldy; r.ldres = p.ldres; r.ldaux = p.ldaux; r.cpo = p.Cp_out;
+    r.slope = p.slope;
+    r.rpre = (p.res && p.res_pre) ? p.res_scale : 0.f;
+    r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
+    r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
+              (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
+              ((dbg & 128) ? EF_PROF : 0);
+    opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
+    opaque(r.H); opaque(r.W); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
+    opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
+    return r;
+}
+
+// Vector epilogue of one tile for one warp (NHWC and pixel-shuffle stores, 16-byte aligned tensors).
+// The warp owns pixel rows [32q, 32q+32) of the 8x16 tile (image rows y0+2q, y0+2q+1) and accumulator columns
+// [cb, cb + wcols), wcols <= 64, processed 16 columns ("quarter" hh) at a time.  Accumulators arrive one pixel row per lane
+// (TMEM lane = pixel) and are transposed through a warp-private swizzled slab -- no block-wide barrier -- so that 4 lanes hold
+// the 4 float4s of one pixel's 16 columns and every global access of the warp covers 8 pixels x 64 contiguous bytes:
+//   item `it` of a lane = pixel (y0 + 2q + (it >> 1), x0 + (lane >> 2) + 8 (it & 1)), float4 `lane & 3` of the slab row.
+//   NHWC store : slab row = 16 consecutive channels; float4 c = channels cb + 16hh + 4c ..+3 of that pixel.
+//   pixel shuffle: slab row = [sub-pixel 0: 4 shuffled channels | sub 1 | sub 2 | sub 3]; float4 c = shuffled channels
+//                (cb + 16hh)/4 ..+3 of OUTPUT pixel (2y + (c >> 1), 2x + (c & 1)).
+// The residual (or aux) operand of all 16 items is requested BEFORE the wait on the accumulator barrier, so its HBM latency
+// hides behind the MMAs of this tile; the TMEM load of quarter hh+1 is in flight while quarter hh is finished.
 template <int ACT, int EPI>
-__device__ __forceinline__ void epilogue_slab(const rcn_conv_desc& p, int dbg, const float* __restrict__ stg, int cols, int n,
-                                              int c_base, int x0, int y0, int et, bool vec) {
-    const int Ho = p.H, Wo = p.W;
-    if (vec) {
-        // Loads-first, fully unrolled: every thread issues ALL of its global loads for the slab (residual / aux,
-        // 16 B each) before the first dependent instruction, so ~8 requests per thread are in flight instead of 1-2
-        // (the epilogue was latency-bound on HBM round trips).  Items are float4s of the STORED tensor:
-        //   NHWC store : item = (row, 4 consecutive channels)
-        //   PS2 store  : item = (row, sub-pixel (i,j), 4 consecutive shuffled channels) -- conv channels cc*4 + sub,
-        //                gathered with stride 4 from the slab, so the shuffled tensor is also written 16 B at a time.
-        const bool ps = (p.store == RCN_STORE_PS2);
-        const int groups = cols >> 2;           // float4 items per row (both layouts)
-        const int total = 128 * groups;
-        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo;
-        constexpr int IT = (128 * 8) / EPI_THREADS;  // 128 rows * 8 groups over the epilogue threads
-        float4 accv[IT], resv[IT], auxv[IT], biasv[IT];
-        long long opix[IT];
-        int och[IT];
-        bool ok[IT];
+__device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int epi, uint32_t slab, uint32_t sbias, uint32_t taddr,
+                                                  uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0,
+                                                  int cb, int wcols, int q, int lane) {
+    const bool ps = (r.flags & EF_PS) != 0;
+    const int chunk = lane & 3, r0 = lane >> 2;
+    const int hy = y0 + 2 * q, wx = x0 + r0;
+    bool okp[4];
 #pragma unroll
-        for (int u = 0; u < IT; ++u) {
-            const int e = et + EPI_THREADS * u;
-            const int row = e / groups, g = e - row * groups;
-            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
-            ok[u] = (e < total) && (ho < Ho) && (wo < Wo);
-            resv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            auxv[u] = resv[u];
-            accv[u] = resv[u];
-            biasv[u] = resv[u];
-            opix[u] = 0;
-            och[u] = 0;
-            if (!ok[u]) continue;
-            const float* srow = stg + row * STG_PITCH;
-            if (!ps) {
-                och[u] = c_base + 4 * g;
-                opix[u] = ((long long)n * Ho + ho) * Wo + wo;
-                accv[u] = *reinterpret_cast<const float4*>(srow + 4 * g);
-                if (EPI != 0) auxv[u] = *reinterpret_cast<const float4*>(p.aux + opix[u] * p.ldaux + och[u]);
-                if (p.bias) biasv[u] = __ldg(reinterpret_cast<const float4*>(p.bias + och[u]));
-            } else {
-                const int sub = g & 3, ccg = g >> 2;          // groups = 4 sub-pixels x (cols/16) channel groups
-                const int cc0 = (c_base >> 2) + 4 * ccg;      // first shuffled channel of the item
-                och[u] = cc0;
-                opix[u] = ((long long)n * Hs + 2 * ho + (sub >> 1)) * Ws + 2 * wo + (sub & 1);
-                const float* sp = srow + 16 * ccg + sub;      // conv channel (cc0 + q)*4 + sub  ->  slab column 16*ccg + 4*q + sub
-                accv[u] = make_float4(sp[0], sp[4], sp[8], sp[12]);
-                if (p.bias) {
-                    const float* bp = p.bias + (cc0 << 2) + sub;   // conv channel of element q: (cc0 + q)*4 + sub
-                    biasv[u] = make_float4(__ldg(bp), __ldg(bp + 4), __ldg(bp + 8), __ldg(bp + 12));
-                }
-            }
-            if (p.res) resv[u] = *reinterpret_cast<const float4*>(p.res + opix[u] * p.ldres + och[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < IT; ++u) {
-            if (!ok[u]) continue;
-            float val[4] = {accv[u].x + biasv[u].x, accv[u].y + biasv[u].y, accv[u].z + biasv[u].z, accv[u].w + biasv[u].w};
-            const float ax[4] = {auxv[u].x, auxv[u].y, auxv[u].z, auxv[u].w};
-            const float rv[4] = {p.res_scale * resv[u].x, p.res_scale * resv[u].y, p.res_scale * resv[u].z, p.res_scale * resv[u].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                // conv channel of element j (bias / per-channel affine are indexed by it)
-                const int c = ps ? ((och[u] + j) << 2) + (int)((opix[u] / Ws) & 1) * 2 + (int)(opix[u] % Ws & 1) : och[u] + j;
-                if (p.cscale) val[j] = val[j] * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
-                if (EPI != 0) val[j] = epi_ct<EPI>(val[j], ax[j], p.epi);
-                if (p.res && p.res_pre) val[j] += rv[j];
-                val[j] = act_ct<ACT>(val[j], p.act, p.slope);
-                if (p.res && !p.res_pre) val[j] += rv[j];
-            }
-            if (!(dbg & 1)) {
-                if (p.y) *reinterpret_cast<float4*>(p.y + opix[u] * p.ldy + och[u]) = make_float4(val[0], val[1], val[2], val[3]);
-                if (p.y_hi) {
-                    // the consumer's tcgen05 operand planes: x = hi + lo in bf16 (same rounding as rcn_split_bf16)
-                    __nv_bfloat16 hh[4], ll[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        hh[j] = __float2bfloat16_rn(val[j]);
-                        ll[j] = __float2bfloat16_rn(val[j] - __bfloat162float(hh[j]));
-                    }
-                    const long long po = opix[u] * p.Cp_out + och[u];
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_hi) + po) = *reinterpret_cast<uint2*>(hh);
-                    if (p.y_lo) *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.y_lo) + po) = *reinterpret_cast<uint2*>(ll);
-                }
-            }
-        }
+    for (int it = 0; it < 4; ++it) okp[it] = (hy + (it >> 1) < r.H) && (wx + 8 * (it & 1) < r.W);
+    // stored-tensor geometry of the lane's items
+    long long pix0;
+    int sx, sy, chb, chs;      // pixel steps for x + 8 / y + 1; first stored channel of quarter 0 and its step per quarter
+    if (!ps) {
+        pix0 = ((long long)n * r.H + hy) * r.W + wx;
+        sx = 8; sy = r.W; chb = cb + 4 * chunk; chs = 16;
     } else {
-        const bool ps = (p.store == RCN_STORE_PS2 || p.store == RCN_STORE_PS2_NCHW);
-        const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? p.Cout / 4 : p.Cout;
-        const int total = 128 * cols;
-#pragma unroll 2
-        for (int e = et; e < total; e += EPI_THREADS) {
-            const int row = e / cols, col = e - row * cols;
-            const int ho = y0 + row / TILE_W, wo = x0 + (row % TILE_W);
-            if (ho >= Ho || wo >= Wo) continue;
-            const int c = c_base + col;
-            const long long mpix = ((long long)n * Ho + ho) * Wo + wo;
-            float val = stg[row * STG_PITCH + col];
-            if (p.bias) val += __ldg(p.bias + c);
-            if (p.cscale) val = val * (1.f + __ldg(p.cscale + n * p.Cout + c)) + __ldg(p.cshift + n * p.Cout + c);
-            if (EPI != 0) val = epi_ct<EPI>(val, p.aux[mpix * p.ldaux + c], p.epi);
-            int hh = ho, ww = wo, cc = c;
-            if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
-            const long long pix = ((long long)n * Hs + hh) * Ws + ww;
-            float rv = 0.f;
-            if (p.res) rv = p.res_scale * p.res[pix * p.ldres + cc];
-            if (p.res && p.res_pre) val += rv;
-            val = act_ct<ACT>(val, p.act, p.slope);
-            if (p.res && !p.res_pre) val += rv;
-            if (!(dbg & 1)) {
-                if (p.store == RCN_STORE_NCHW || p.store == RCN_STORE_PS2_NCHW)
-                    p.y[(((long long)n * Cs + cc) * Hs + hh) * Ws + ww] = val;
-                else
-                    p.y[pix * p.ldy + cc] = val;
+        const int Ws = 2 * r.W;
+        pix0 = ((long long)n * 2 * r.H + 2 * hy + (chunk >> 1)) * Ws + 2 * wx + (chunk & 1);
+        sx = 16; sy = 2 * Ws; chb = cb >> 2; chs = 4;
+    }
+    const int lane_cols = ps ? 0 : 4 * chunk;   // columns of a quarter that must exist for this lane's float4 to be valid
+    long long ip[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) ip[it] = pix0 + (it & 1) * sx + (long long)(it >> 1) * sy;
+    const bool has_res = (r.flags & EF_RES) != 0;
+    constexpr bool has_aux = (EPI != 0);
+    // operand prefetched ahead of the accumulator: the residual when there is one, else aux
+    const float* pre_ptr = has_res ? r.res : (has_aux ? r.aux : nullptr);
+    const int pre_ld = has_res ? r.ldres : r.ldaux;
+    float4 pre[4][4];
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            pre[hh][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pre_ptr && (16 * hh + lane_cols < wcols) && okp[it]) pre[hh][it] = ldg4(pre_ptr + ip[it] * pre_ld + chb + chs * hh);
+        }
+    }
+    const bool prof = (r.flags & EF_PROF) && blockIdx.x == 0 && threadIdx.x == 64;
+    long long tp0 = 0, tp1 = 0;
+    if (prof) tp0 = clock64();
+    mbar_wait(full_bar, parity);
+    tc_fence_after();
+    if (prof) { tp1 = clock64(); atomicAdd(&g_tcprof[0], (unsigned long long)(tp1 - tp0)); atomicAdd(&g_tcprof[2], 1ull); }
+    if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
+    uint32_t v[16];
+    tmem_ld16_async(taddr, v);
+    const int wsw = (lane >> 1) & 3;   // write-side swizzle of row `lane`
+    const int rsw = (r0 >> 1) & 3;     // read-side swizzle of rows r0 + 8*it
+#pragma unroll
+    for (int hh = 0; hh < 4; ++hh) {
+        if (16 * hh >= wcols) break;   // warp-uniform
+        const bool ah = 16 * hh + lane_cols < wcols;
+        const int ch = chb + chs * hh;
+        // per-channel parameters of this lane's 4 elements (conv channel index of element e: c0 + ce * e)
+        const int c0 = ps ? (cb + 16 * hh + chunk) : ch, ce = ps ? 4 : 1;
+        float bi[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f}, csh[4] = {0.f, 0.f, 0.f, 0.f};
+        if (ah) {
+            if (sbias) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) bi[e] = lds1(sbias + 4u * (uint32_t)(c0 + ce * e));
+            }
+            if (r.flags & EF_CS) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    cs[e] = 1.f + __ldg(r.cscale + n * r.Cout + c0 + ce * e);
+                    csh[e] = __ldg(r.cshift + n * r.Cout + c0 + ce * e);
+                }
+            }
+        }
+        // second operand (aux when a residual is also present)
+        float4 sec[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            sec[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (has_aux && has_res && ah && okp[it]) sec[it] = ldg4(r.aux + ip[it] * r.ldaux + ch);
+        }
+        // ---- transpose: row `lane` <- the 16 accumulator columns of this quarter
+        tmem_wait_ld16(v);
+        const uint32_t wrow = slab + (uint32_t)lane * 64u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float4 t;
+            if (!ps) t = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
+            else t = make_float4(__uint_as_float(v[k]), __uint_as_float(v[4 + k]), __uint_as_float(v[8 + k]), __uint_as_float(v[12 + k]));
+            sts4(wrow + 16u * (uint32_t)(k ^ wsw), t);
+        }
+        if (16 * (hh + 1) < wcols) tmem_ld16_async(taddr + 16 * (hh + 1), v);   // next quarter in flight
+        else epi_release(empty_bar, lane);                                      // last TMEM read of this tile by this warp
+        __syncwarp();
+        float4 acc[4];
+#pragma unroll
+        for (int it = 0; it < 4; ++it) acc[it] = lds4(slab + (uint32_t)(r0 + 8 * it) * 64u + 16u * (uint32_t)(chunk ^ rsw));
+        __syncwarp();
+        if (!ah) continue;
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            if (!okp[it]) continue;
+            float val[4] = {acc[it].x + bi[0], acc[it].y + bi[1], acc[it].z + bi[2], acc[it].w + bi[3]};
+            const float4 rr = has_res ? pre[hh][it] : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 aa = has_res ? sec[it] : pre[hh][it];
+            const float ax[4] = {aa.x, aa.y, aa.z, aa.w};
+            const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                val[e] = fmaf(val[e], cs[e], csh[e]);                       // Res_GFM modulation (identity when absent)
+                if (EPI != 0) val[e] = epi_ct<EPI>(val[e], ax[e], epi);
+                val[e] = fmaf(r.rpre, rv[e], val[e]);                       // residual before / after the activation
+                val[e] = act_ct<ACT>(val[e], act, r.slope);
+                val[e] = fmaf(r.rpost, rv[e], val[e]);
+            }
+            if (r.flags & EF_NOSTORE) continue;
+            if (r.flags & EF_Y) *reinterpret_cast<float4*>(r.y + ip[it] * r.ldy + ch) = make_float4(val[0], val[1], val[2], val[3]);
+            if (r.flags & EF_HI) {
+                // the consumer's tcgen05 operand planes: x = hi + lo in bf16 (same rounding as rcn_split_bf16)
+                __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hb[e] = __float2bfloat16_rn(val[e]);
+                    lb[e] = __float2bfloat16_rn(val[e] - __bfloat162float(hb[e]));
+                }
+                const long long po = ip[it] * r.cpo + ch;
+                *reinterpret_cast<uint2*>(r.y_hi + po) = *reinterpret_cast<uint2*>(hb);
+                if (r.flags & EF_LO) *reinterpret_cast<uint2*>(r.y_lo + po) = *reinterpret_cast<uint2*>(lb);
             }
         }
     }
+    if (prof) atomicAdd(&g_tcprof[1], (unsigned long long)(clock64() - tp1));
 }
 
-__device__ __forceinline__ void epilogue_dispatch(const rcn_conv_desc& p, int dbg, const float* stg, int cols, int n, int c_base,
-                                                  int x0, int y0, int et, bool vec) {
-#define RCN_EP(A, E) epilogue_slab<A, E>(p, dbg, stg, cols, n, c_base, x0, y0, et, vec)
-    if (p.epi == RCN_EPI_NONE) {
-        switch (p.act) {
+// Generic epilogue straight from the accumulator registers (one pixel row per lane): NCHW / pixel-shuffle-to-NCHW stores
+// (lanes = consecutive pixels of an image row, i.e. the coalesced direction of an NCHW tensor) and odd / unaligned shapes.
+template <int ACT, int EPI>
+__device__ __forceinline__ void rows_block(const EpiRegs& r, int act, int epi, int store, uint32_t sbias, const uint32_t* v, int n, int ho,
+                                           int wo, int cb, int wc) {
+    const int Ho = r.H, Wo = r.W;
+    const bool ps = (store == RCN_STORE_PS2 || store == RCN_STORE_PS2_NCHW);
+    const bool nchw = (store == RCN_STORE_NCHW || store == RCN_STORE_PS2_NCHW);
+    const int Hs = ps ? 2 * Ho : Ho, Ws = ps ? 2 * Wo : Wo, Cs = ps ? r.Cout / 4 : r.Cout;
+    const long long mpix = ((long long)n * Ho + ho) * Wo + wo;
+    const bool has_res = (r.flags & EF_RES) != 0, has_cs = (r.flags & EF_CS) != 0;
+    const bool has_aux = EPI > 0 || (EPI < 0 && epi != RCN_EPI_NONE);
+    float outv[16];
+#pragma unroll
+    for (int col = 0; col < 16; ++col) {
+        outv[col] = 0.f;
+        if (col >= wc) continue;
+        const int c = cb + col;
+        float val = __uint_as_float(v[col]);
+        if (sbias) val += lds1(sbias + 4u * (uint32_t)c);
+        if (has_cs) val = val * (1.f + __ldg(r.cscale + n * r.Cout + c)) + __ldg(r.cshift + n * r.Cout + c);
+        if (has_aux) val = epi_ct<EPI>(val, r.aux[mpix * r.ldaux + c], epi);
+        int hh = ho, ww = wo, cc = c;
+        if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
+        float rv = 0.f;
+        if (has_res) rv = r.res[(((long long)n * Hs + hh) * Ws + ww) * r.ldres + cc];
+        val = fmaf(r.rpre, rv, val);
+        val = act_ct<ACT>(val, act, r.slope);
+        val = fmaf(r.rpost, rv, val);
+        outv[col] = val;
+    }
+    if (r.flags & EF_NOSTORE) return;
+    if (store == RCN_STORE_PS2_NCHW) {
+        // columns (4cc + 2i + j): the pair j = 0,1 is two adjacent output pixels -> one 8-byte store, 128 B per image row per warp
+#pragma unroll
+        for (int col = 0; col < 16; col += 2) {
+            if (col >= wc) continue;
+            const int c = cb + col, cc = c >> 2, i = (c >> 1) & 1;
+            float* dst = r.y + (((long long)n * Cs + cc) * Hs + 2 * ho + i) * Ws + 2 * wo;
+            if (col + 1 < wc) *reinterpret_cast<float2*>(dst) = make_float2(outv[col], outv[col + 1]);
+            else dst[0] = outv[col];
+        }
+    } else {
+#pragma unroll
+        for (int col = 0; col < 16; ++col) {
+            if (col >= wc) continue;
+            const int c = cb + col;
+            int hh = ho, ww = wo, cc = c;
+            if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
+            if (nchw) r.y[(((long long)n * Cs + cc) * Hs + hh) * Ws + ww] = outv[col];
+            else r.y[(((long long)n * Hs + hh) * Ws + ww) * r.ldy + cc] = outv[col];
+        }
+    }
+}
+template <int ACT, int EPI>
+__device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, int epi, int store, uint32_t sbias, uint32_t taddr,
+                                                   uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0, int cb,
+                                                   int wcols, int q, int lane) {
+    mbar_wait(full_bar, parity);
+    tc_fence_after();
+    if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
+    const int m = q * 32 + lane;
+    const int ho = y0 + m / TILE_W, wo = x0 + (m % TILE_W);
+    const bool ok = ho < r.H && wo < r.W;
+#pragma unroll 1
+    for (int c0 = 0; c0 < wcols; c0 += 16) {
+        uint32_t v[16];
+        __syncwarp();
+        tmem_ld16_async(taddr + c0, v);
+        tmem_wait_ld16(v);
+        if (c0 + 16 >= wcols) epi_release(empty_bar, lane);
+        if (ok) rows_block<ACT, EPI>(r, act, epi, store, sbias, v, n, ho, wo, cb + c0, wcols - c0 > 16 ? 16 : wcols - c0);
+    }
+}
+
+#define RCN_EPI_ARGS_DECL const rcn_conv_desc &p, const EpiRegs &r, int dbg, uint32_t slab, uint32_t sbias, uint32_t taddr, uint64_t *full_bar, uint32_t parity, \
+                          uint64_t *empty_bar, int n, int x0, int y0, int cb, int wcols, int q, int lane
+__device__ __forceinline__ void epilogue_dispatch_vec(RCN_EPI_ARGS_DECL, int act, int epi) {
+#define RCN_EP(A, E) epilogue_tile_vec<A, E>(r, act, epi, slab, sbias, taddr, full_bar, parity, empty_bar, n, x0, y0, cb, wcols, q, lane)
+    if (epi == RCN_EPI_NONE) {
+        switch (act) {
             case RCN_ACT_NONE: RCN_EP(RCN_ACT_NONE, 0); break;
             case RCN_ACT_RELU: RCN_EP(RCN_ACT_RELU, 0); break;
             case RCN_ACT_LRELU: RCN_EP(RCN_ACT_LRELU, 0); break;
@@ -286,8 +454,8 @@ __device__ __forceinline__ void epilogue_dispatch(const rcn_conv_desc& p, int db
             case RCN_ACT_HSWISH: RCN_EP(RCN_ACT_HSWISH, 0); break;
             default: RCN_EP(-1, 0); break;
         }
-    } else if (p.act == RCN_ACT_NONE) {
-        switch (p.epi) {
+    } else if (act == RCN_ACT_NONE) {
+        switch (epi) {
             case RCN_EPI_GDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_GDN); break;
             case RCN_EPI_IGDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_IGDN); break;
             case RCN_EPI_MUL_AUXP1: RCN_EP(RCN_ACT_NONE, RCN_EPI_MUL_AUXP1); break;
@@ -297,6 +465,13 @@ __device__ __forceinline__ void epilogue_dispatch(const rcn_conv_desc& p, int db
     } else {
         RCN_EP(-1, -1);
     }
+#undef RCN_EP
+}
+__device__ __forceinline__ void epilogue_dispatch_rows(RCN_EPI_ARGS_DECL, int act, int epi, int store) {
+#define RCN_EP(A, E) epilogue_tile_rows<A, E>(r, act, epi, store, sbias, taddr, full_bar, parity, empty_bar, n, x0, y0, cb, wcols, q, lane)
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) RCN_EP(RCN_ACT_NONE, 0);
+    else if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) RCN_EP(RCN_ACT_CLAMP01, 0);
+    else RCN_EP(-1, -1);
 #undef RCN_EP
 }
 
@@ -312,7 +487,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int B_BYTES = P.Ntile * BLOCK_K * 2;
     const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);  // multiple of 1024 (Ntile % 16 == 0)
     float* stg = reinterpret_cast<float*>(smem + (size_t)P.stages * stage_bytes);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES);
+    float* sbias_mem = reinterpret_cast<float*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES + BIAS_BYTES);
     uint64_t* empty_bar = full_bar + P.stages;
     uint64_t* tmem_full = empty_bar + P.stages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;          // [2]
@@ -324,9 +500,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (p.bias) {
+        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) sbias_mem[i] = __ldg(p.bias + i);
+    }
+    const uint32_t sbias = p.bias ? smem_u32(sbias_mem) : 0u;   // shared-space address (0 = no bias)
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -343,12 +523,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t tx_bytes = loadA ? (uint32_t)stage_bytes : (uint32_t)((P.passes == 3 ? 2 : 1) * B_BYTES);
             int stage = 0;
             uint32_t phase = 0;
-            for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x) {
-                const int nt = (int)(t % P.tiles_n);
-                long long mt = t / P.tiles_n;
-                const int tx = (int)(mt % P.tiles_x); mt /= P.tiles_x;
-                const int ty = (int)(mt % P.tiles_y);
-                const int n = (int)(mt / P.tiles_y);
+            const uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+            for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x) {
+                const int nt = (int)(t % tiles_n);
+                uint32_t mt = t / tiles_n;
+                const int tx = (int)(mt % tiles_x); mt /= tiles_x;
+                const int ty = (int)(mt % tiles_y);
+                const int n = (int)(mt / tiles_y);
                 const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * P.Ntile;
                 for (int it = 0; it < kiters; ++it) {
                     const int tap = it / chunks, ch = it - tap * chunks;
@@ -382,8 +563,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             int stage = 0;
             uint32_t phase = 0;
             uint32_t local = 0;
-            for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++local) {
-                const int n0 = (int)(t % P.tiles_n) * P.Ntile;
+            for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
+                const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
                 int nact = p.Cout - n0;
                 if (nact > P.Ntile) nact = P.Ntile;
                 nact = (nact + 15) & ~15;
@@ -418,48 +599,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ================= epilogue: TMEM -> smem slab -> fused element-wise -> coalesced global =================
-        const int q = warp & 3;          // TMEM lane quarter this warp may access (hardware: warp_id % 4)
-        const int jsub = (warp - 2) >> 2;  // which 8-column block of the 32-column slab this warp drains (0..3)
-        const int m = q * 32 + lane;
-        const int et = threadIdx.x - 64;
-        const bool vec = !(P.dbg & 8) && ((p.store == RCN_STORE_NHWC && (p.Cout & 3) == 0) ||
-                                          (p.store == RCN_STORE_PS2 && (p.Cout & 15) == 0 && p.epi == RCN_EPI_NONE)) &&
+        // ================= epilogue: TMEM -> registers -> (warp-private transposition slab) -> fused element-wise -> global
+        const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp_id % 4)
+        const int jsub = (warp - 2) >> 2;  // which 64-column half of the accumulator this warp drains (0..1)
+        const uint32_t slab = smem_u32(stg + (warp - 2) * SLAB_FLOATS);
+        const bool vec = ((p.store == RCN_STORE_NHWC && (p.Cout & 3) == 0) ||
+                          (p.store == RCN_STORE_PS2 && (p.Cout & 15) == 0 && p.epi == RCN_EPI_NONE)) &&
                          ((p.ldy & 3) == 0) &&
                          (!p.y || (reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
                          (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
-                         (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0))) &&
-                         (!p.bias || ((reinterpret_cast<uintptr_t>(p.bias) & 15) == 0));
+                         (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
+        const EpiRegs er = make_epi_regs(p, P.dbg);
+        int act = p.act, epi = p.epi, store = p.store;
+        opaque(act); opaque(epi); opaque(store);
+        uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+        opaque(tiles_n); opaque(tiles_x); opaque(tiles_y);
+        int Ntile = P.Ntile;
+        opaque(Ntile);
         uint32_t local = 0;
-        for (long long t = blockIdx.x; t < P.total_tiles; t += gridDim.x, ++local) {
-            const int nt = (int)(t % P.tiles_n);
-            long long mt = t / P.tiles_n;
-            const int tx = (int)(mt % P.tiles_x); mt /= P.tiles_x;
-            const int ty = (int)(mt % P.tiles_y);
-            const int n = (int)(mt / P.tiles_y);
-            const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * P.Ntile;
-            int ncols = p.Cout - n0;
-            if (ncols > P.Ntile) ncols = P.Ntile;
+        for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {   // total_tiles < 2^31 (host-checked)
+            const int nt = (int)(t % tiles_n);
+            uint32_t mt = t / tiles_n;
+            const int tx = (int)(mt % tiles_x); mt /= tiles_x;
+            const int ty = (int)(mt % tiles_y);
+            const int n = (int)(mt / tiles_y);
+            const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * Ntile;
+            int ncols = er.Cout - n0;
+            if (ncols > Ntile) ncols = Ntile;
+            int wcols = ncols - 64 * jsub;
+            if (wcols > 64) wcols = 64;
             const uint32_t ab = local & 1;
-            mbar_wait(&tmem_full[ab], (local >> 1) & 1);
-            tc_fence_after();
-            for (int c0 = 0; c0 < ncols; c0 += STG_COLS) {
-                uint32_t v[8];
-                __syncwarp();  // tcgen05.ld is warp-collective (.sync.aligned)
-                tmem_ld8(tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(c0 + 8 * jsub), v);
-                if (c0 + STG_COLS >= ncols) tc_fence_before();  // last TMEM read of this tile by this warp
-                asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");  // previous slab consumed (+ TMEM drained on the last slab)
-                if (c0 + STG_COLS >= ncols && et == 0) {
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty[ab])) : "memory");
-                }
-                float4* dst = reinterpret_cast<float4*>(stg + m * STG_PITCH + 8 * jsub);
-                dst[0] = make_float4(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3]));
-                dst[1] = make_float4(__uint_as_float(v[4]), __uint_as_float(v[5]), __uint_as_float(v[6]), __uint_as_float(v[7]));
-                asm volatile("bar.sync 2, %0;" ::"n"(EPI_THREADS) : "memory");  // slab visible to all epilogue warps
-                int cols = ncols - c0;
-                if (cols > STG_COLS) cols = STG_COLS;
-                if (!(P.dbg & 8)) epilogue_dispatch(p, P.dbg, stg, cols, n, n0 + c0, x0, y0, et, vec);
-            }
+            const uint32_t taddr = tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * jsub);
+            if (vec) epilogue_dispatch_vec(p, er, P.dbg, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0, n0 + 64 * jsub, wcols, q, lane, act, epi);
+            else epilogue_dispatch_rows(p, er, P.dbg, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0, n0 + 64 * jsub, wcols, q, lane, act, epi, store);
         }
     }
     tc_fence_before();
@@ -581,6 +753,12 @@ bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int 
 
 using namespace rcn;
 
+extern "C" int rcn_tc_prof(unsigned long long* out16, int reset) {
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_tcprof, z, sizeof(z)); return RCN_OK; }
+    cudaDeviceSynchronize();
+    return cudaMemcpyFromSymbol(out16, g_tcprof, 16 * sizeof(unsigned long long)) == cudaSuccess ? RCN_OK : RCN_ERR_CUDA;
+}
+
 extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream) {
     RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && Cp % 64 == 0, "rcn_split_bf16: bad arguments");
     const long long total = npix * (Cp / 4);
@@ -632,6 +810,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     }
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
+    RCN_CHECK_ARG(d->Cout <= BIAS_MAX, "rcn_conv2d_tc: Cout %d > %d unsupported", d->Cout, BIAS_MAX);
     RCN_CHECK_ARG(d->stride == 1 || d->stride == 2, "rcn_conv2d_tc: stride %d unsupported", d->stride);
     RCN_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "rcn_conv2d_tc: stride 2 needs even H and W");
     RCN_CHECK_ARG(Cp % 64 == 0 && Cp >= d->Cin, "rcn_conv2d_tc: Cp must be a multiple of 64 >= Cin");
@@ -650,7 +829,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.tiles_x = (P.d.W + TILE_W - 1) / TILE_W;
     P.tiles_y = (P.d.H + TILE_H - 1) / TILE_H;
     const int stage_bytes = (passes == 3 ? 2 : 1) * (A_BYTES + nt * BLOCK_K * 2);
-    int stages = (226 * 1024 - STG_BYTES - 1024 - 256) / stage_bytes;
+    int stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 256) / stage_bytes;
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     P.stages = stages;
@@ -660,7 +839,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         const char* st = getenv("RCN_TC_STAGES");
         if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
     }
-    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 256;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const long long Ktot = (long long)d->k * d->k * Cp;
     const int planes = P.s2 ? 4 * d->N : d->N;
@@ -675,6 +854,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     }
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
+    RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");
     static int num_sms = 0;
     if (!num_sms) {
         int dev = 0;
