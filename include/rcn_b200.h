@@ -231,7 +231,7 @@ int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int C
 
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */
-int rcn_tc_prof(unsigned long long* out4, int reset);
+int rcn_tc_prof(unsigned long long* out16, int reset);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,7 @@ PROTOTYPES = {
     "rcn_split_bf16": (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
     "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P]),
     "rcn_wmsa": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
