@@ -107,7 +107,12 @@ struct TcParams {
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
 };
 
-constexpr int EPI_WARPS = 8;             // 2 warps per TMEM lane quarter (warp_id % 4), each draining 64 accumulator columns
+#ifndef RCN_TC_EPI_WARPS
+#define RCN_TC_EPI_WARPS 8
+#endif
+constexpr int EPI_WARPS = RCN_TC_EPI_WARPS;   // EPI_WARPS / 4 warps per TMEM lane quarter (warp_id % 4), each draining WCOLS accumulator columns
+constexpr int WCOLS = 128 / (EPI_WARPS / 4);  // 64 (8 warps) or 32 (16 warps)
+constexpr int QN = WCOLS / 16;                // 16-column quarters per warp and tile
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int TC_THREADS = 64 + EPI_THREADS;
 constexpr int SLAB_FLOATS = 32 * 16;     // warp-private transposition slab: 32 pixel rows x 16 floats, 16-byte chunks XOR-swizzled
@@ -263,9 +268,9 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
     // operand prefetched ahead of the accumulator: the residual when there is one, else aux
     const float* pre_ptr = has_res ? r.res : (has_aux ? r.aux : nullptr);
     const int pre_ld = has_res ? r.ldres : r.ldaux;
-    float4 pre[4][4];
+    float4 pre[QN][4];
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
+    for (int hh = 0; hh < QN; ++hh) {
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             pre[hh][it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -284,7 +289,7 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
     const int wsw = (lane >> 1) & 3;   // write-side swizzle of row `lane`
     const int rsw = (r0 >> 1) & 3;     // read-side swizzle of rows r0 + 8*it
 #pragma unroll
-    for (int hh = 0; hh < 4; ++hh) {
+    for (int hh = 0; hh < QN; ++hh) {
         if (16 * hh >= wcols) break;   // warp-uniform
         const bool ah = 16 * hh + lane_cols < wcols;
         const int ch = chb + chs * hh;
@@ -439,45 +444,18 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, in
     }
 }
 
-#define RCN_EPI_ARGS_DECL const rcn_conv_desc &p, const EpiRegs &r, int dbg, uint32_t slab, uint32_t sbias, uint32_t taddr, uint64_t *full_bar, uint32_t parity, \
-                          uint64_t *empty_bar, int n, int x0, int y0, int cb, int wcols, int q, int lane
-__device__ __forceinline__ void epilogue_dispatch_vec(RCN_EPI_ARGS_DECL, int act, int epi) {
-#define RCN_EP(A, E) epilogue_tile_vec<A, E>(r, act, epi, slab, sbias, taddr, full_bar, parity, empty_bar, n, x0, y0, cb, wcols, q, lane)
-    if (epi == RCN_EPI_NONE) {
-        switch (act) {
-            case RCN_ACT_NONE: RCN_EP(RCN_ACT_NONE, 0); break;
-            case RCN_ACT_RELU: RCN_EP(RCN_ACT_RELU, 0); break;
-            case RCN_ACT_LRELU: RCN_EP(RCN_ACT_LRELU, 0); break;
-            case RCN_ACT_GELU: RCN_EP(RCN_ACT_GELU, 0); break;
-            case RCN_ACT_SIGMOID: RCN_EP(RCN_ACT_SIGMOID, 0); break;
-            case RCN_ACT_HALF_TANH: RCN_EP(RCN_ACT_HALF_TANH, 0); break;
-            case RCN_ACT_HSWISH: RCN_EP(RCN_ACT_HSWISH, 0); break;
-            default: RCN_EP(-1, 0); break;
-        }
-    } else if (act == RCN_ACT_NONE) {
-        switch (epi) {
-            case RCN_EPI_GDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_GDN); break;
-            case RCN_EPI_IGDN: RCN_EP(RCN_ACT_NONE, RCN_EPI_IGDN); break;
-            case RCN_EPI_MUL_AUXP1: RCN_EP(RCN_ACT_NONE, RCN_EPI_MUL_AUXP1); break;
-            case RCN_EPI_MULP1_AUX: RCN_EP(RCN_ACT_NONE, RCN_EPI_MULP1_AUX); break;
-            default: RCN_EP(RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE); break;
-        }
-    } else {
-        RCN_EP(-1, -1);
-    }
-#undef RCN_EP
-}
-__device__ __forceinline__ void epilogue_dispatch_rows(RCN_EPI_ARGS_DECL, int act, int epi, int store) {
-#define RCN_EP(A, E) epilogue_tile_rows<A, E>(r, act, epi, store, sbias, taddr, full_bar, parity, empty_bar, n, x0, y0, cb, wcols, q, lane)
-    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) RCN_EP(RCN_ACT_NONE, 0);
-    else if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) RCN_EP(RCN_ACT_CLAMP01, 0);
-    else RCN_EP(-1, -1);
-#undef RCN_EP
-}
-
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; tile t -> (m-tile, n-tile).
 // TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// One instantiation per (activation, combinator, store path): the epilogue of a single variant is ~3k SASS instructions; with all
+// variants inlined behind a runtime switch the kernel was 50k instructions and a quarter of the epilogue warps' stall samples were
+// instruction-cache misses (ncu: stall_no_inst).
+#if RCN_TC_EPI_WARPS == 16
+#define RCN_TC_BOUNDS __maxnreg__(RCN_TC_MAXNREG)
+#else
+#define RCN_TC_BOUNDS __launch_bounds__(TC_THREADS, 1)
+#endif
+template <int ACT, int EPI, bool VEC>
+__global__ void RCN_TC_BOUNDS
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
     extern __shared__ uint8_t smem_raw[];
@@ -601,14 +579,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else {
         // ================= epilogue: TMEM -> registers -> (warp-private transposition slab) -> fused element-wise -> global
         const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp_id % 4)
-        const int jsub = (warp - 2) >> 2;  // which 64-column half of the accumulator this warp drains (0..1)
+        const int jsub = (warp - 2) >> 2;  // which WCOLS-column slice of the accumulator this warp drains
         const uint32_t slab = smem_u32(stg + (warp - 2) * SLAB_FLOATS);
-        const bool vec = ((p.store == RCN_STORE_NHWC && (p.Cout & 3) == 0) ||
-                          (p.store == RCN_STORE_PS2 && (p.Cout & 15) == 0 && p.epi == RCN_EPI_NONE)) &&
-                         ((p.ldy & 3) == 0) &&
-                         (!p.y || (reinterpret_cast<uintptr_t>(p.y) & 15) == 0) &&
-                         (!p.res || (((p.ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.res) & 15) == 0))) &&
-                         (p.epi == RCN_EPI_NONE || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0)));
         const EpiRegs er = make_epi_regs(p, P.dbg);
         int act = p.act, epi = p.epi, store = p.store;
         opaque(act); opaque(epi); opaque(store);
@@ -626,12 +598,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * Ntile;
             int ncols = er.Cout - n0;
             if (ncols > Ntile) ncols = Ntile;
-            int wcols = ncols - 64 * jsub;
-            if (wcols > 64) wcols = 64;
+            int wcols = ncols - WCOLS * jsub;
+            if (wcols > WCOLS) wcols = WCOLS;
             const uint32_t ab = local & 1;
-            const uint32_t taddr = tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * jsub);
-            if (vec) epilogue_dispatch_vec(p, er, P.dbg, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0, n0 + 64 * jsub, wcols, q, lane, act, epi);
-            else epilogue_dispatch_rows(p, er, P.dbg, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0, n0 + 64 * jsub, wcols, q, lane, act, epi, store);
+            const uint32_t taddr = tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(WCOLS * jsub);
+            if constexpr (VEC)
+                epilogue_tile_vec<ACT, EPI>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                                            n0 + WCOLS * jsub, wcols, q, lane);
+            else
+                epilogue_tile_rows<ACT, EPI>(er, act, epi, store, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                                             n0 + WCOLS * jsub, wcols, q, lane);
         }
     }
     tc_fence_before();
@@ -748,6 +724,52 @@ bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
+
+template <int ACT, int EPI, bool VEC>
+TcKernel tc_variant() {
+    static bool attr_set = false;   // once per instantiation
+    TcKernel k = conv_tc_kernel<ACT, EPI, VEC>;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set = true;
+    }
+    return k;
+}
+
+// (act, epi, 16-byte path?) -> instantiation; combinations the path never uses share the generic (-1, -1) variant
+TcKernel select_kernel(int act, int epi, bool vec) {
+    if (vec) {
+        if (epi == RCN_EPI_NONE) {
+            switch (act) {
+                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true>();
+                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true>();
+                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true>();
+                case RCN_ACT_GELU: return tc_variant<RCN_ACT_GELU, 0, true>();
+                case RCN_ACT_SIGMOID: return tc_variant<RCN_ACT_SIGMOID, 0, true>();
+                case RCN_ACT_HALF_TANH: return tc_variant<RCN_ACT_HALF_TANH, 0, true>();
+                case RCN_ACT_HSWISH: return tc_variant<RCN_ACT_HSWISH, 0, true>();
+                default: return tc_variant<-1, -1, true>();
+            }
+        }
+        if (act == RCN_ACT_NONE) {
+            switch (epi) {
+                case RCN_EPI_GDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_GDN, true>();
+                case RCN_EPI_IGDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_IGDN, true>();
+                case RCN_EPI_MUL_AUXP1: return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true>();
+                case RCN_EPI_MULP1_AUX: return tc_variant<RCN_ACT_NONE, RCN_EPI_MULP1_AUX, true>();
+                case RCN_EPI_SIGMOID_GATE: return tc_variant<RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE, true>();
+                default: break;
+            }
+        }
+        return tc_variant<-1, -1, true>();
+    }
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) return tc_variant<RCN_ACT_NONE, 0, false>();
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) return tc_variant<RCN_ACT_CLAMP01, 0, false>();
+    return tc_variant<-1, -1, false>();
+}
+
 }  // namespace
 }  // namespace rcn
 
@@ -847,11 +869,13 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt);
     else { ma_lo = ma_hi; mw_lo = mw_hi; }
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
-    }
+    // epilogue variant (mirrors the alignment rules of the 16-byte path)
+    const bool vec = ((d->store == RCN_STORE_NHWC && (d->Cout & 3) == 0) ||
+                      (d->store == RCN_STORE_PS2 && (d->Cout & 15) == 0 && d->epi == RCN_EPI_NONE)) &&
+                     ((d->ldy & 3) == 0) && (!d->y || (reinterpret_cast<uintptr_t>(d->y) & 15) == 0) &&
+                     (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
+                     (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
+    const TcKernel kern = select_kernel(d->act, d->epi, vec);
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
     RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");
@@ -863,7 +887,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         if (num_sms <= 0) num_sms = 148;
     }
     const unsigned grid = (unsigned)(P.total_tiles < num_sms ? P.total_tiles : num_sms);  // persistent: one CTA per SM
-    conv_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
+    kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_conv2d_tc");
     return RCN_OK;
