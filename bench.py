@@ -44,7 +44,27 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.rows, self._halt = index, [], threading.Event()
 
+    def _nvml(self):
+        """In-process NVML sampling (no fork of a process that maps tens of GB of device memory)."""
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self._halt.is_set():
+            sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+            self.rows.append([str(sm), str(mx)] + ["Active" if r & bits[n] else "Not Active"
+                                                   for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")])
+            self._halt.wait(0.05)
+
     def run(self):
+        try:
+            return self._nvml()
+        except Exception:
+            pass
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
@@ -129,6 +149,7 @@ def main():
     ap.add_argument("--tile", type=int, default=2048, help="packed tile side T (BASELINE config[1]: 2048)")
     ap.add_argument("--cpu-tile", type=int, default=256, help="tile side of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--engine", default=os.environ.get("RCN_CONV_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
                     help="conv engine: fp32 = CUDA-core exact; bf16x3 = tcgen05 with hi/lo split operands (parity grade); "
                          "bf16 = tcgen05 single pass (fast mode, outside the 1e-3 parity bar)")
@@ -171,6 +192,7 @@ def main():
     weights.fill_(model, seed=0)
     model = model.to(dev).eval()
     model.update()
+    model.enable_cuda_graphs(not args.no_graphs)
     x_host = [t.pin_memory() for t in inputs.make_inputs(T, seed=1234 + rank)]
     x_dev = [t.to(dev) for t in x_host]
     mp_tile = 4.0 * T * T / 1e6
@@ -261,7 +283,8 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     kms = e0.elapsed_time(e1) / reps
-    ach = work / (kms / 1e3) / 1e12
+    ach = kflop / (kms / 1e3) / 1e12        # ALGORITHMIC FLOPs of the convolution (2*k*k*Cin*Cout per output pixel) / time
+    issued = work / (kms / 1e3) / 1e12      # what the tensor pipe executed (3 bf16 MMAs per product in the bf16x3 engine)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the one `ncu --set full` capture of THIS launch at
     # T=2048 (profiles/r1_conv_tcgen05_ncu_full.md: 2.156 + 2.107 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
     # other tile sizes were not captured.
@@ -269,8 +292,8 @@ def main():
     roofline = {"kernel": kname + " -- 3x3 128->128 @ full res (g_s tail)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kms, "peak_source": peaks["_src"] + ", " + peak_note,
-                "algorithmic_tflop_per_launch": kflop / 1e12, "tensor_tflop_per_launch": work / 1e12,
-                "algorithmic_tflops": kflop / (kms / 1e3) / 1e12,
+                "algorithmic_tflop_per_launch": kflop / 1e12, "issued_tflop_per_launch": work / 1e12,
+                "issued_tflops": issued, "tensor_pipe_frac": issued / peak,
                 "traffic_unit": "bytes/launch (ncu dram read+write); algorithmic bytes = 4.29e9 (bf16 hi+lo planes in, fp32 map out)",
                 "step_tflops": world * FLOP_PER_PACKED_POS * T * T * args.steps / (ms / 1e3) / 1e12}
     del a, o
@@ -287,7 +310,7 @@ def main():
                 "dtype": {"fp32": "f32", "bf16x3": "bf16x3 (tcgen05, fp32 accumulate)", "bf16": "bf16"}[args.engine], "data": "synthetic",
                 "config": {"workload": f"raw_compression_tcm_final.forward + range coder on one 4x{T}x{T} packed-Bayer tile per GPU "
                                        "(BASELINE config[1]), random-init weights (name-keyed, seed 0)",
-                           "tile": T, "tiles_per_gpu": 1, "conv_engine": args.engine, "parallelism": f"tile-sharded x{world}",
+                           "tile": T, "tiles_per_gpu": 1, "conv_engine": args.engine, "cuda_graphs": not args.no_graphs, "parallelism": f"tile-sharded x{world}",
                            "l2_policy": "inputs and activations (>2 GB per layer) exceed the 126 MB L2; no explicit flush",
                            "bitstream_bytes": nbytes, "symbols": nsym},
                 "clocks": clocks, "gpu_launches": int(launches),

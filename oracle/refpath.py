@@ -332,10 +332,9 @@ def lrp(sd, i, mean_support, y_hat_slice):
     return 0.5 * torch.tanh(_cc(sd, f"lrp_transforms.{i}", torch.cat([mean_support, y_hat_slice], dim=1)))
 
 
-@torch.no_grad()
-def final_forward(sd, x, num_slices=5, trace=None):
-    """raw_compression_tcm_final.forward, raw2bit.py:1766-1855 (eval mode)."""
-    y, lsc, local, vec = analysis(sd, x)
+def _forward_core(sd, y, num_slices=5, trace=None):
+    """Hyper-prior + slice loop shared by TCM.forward (tcm.py:437-481) and raw_compression_tcm_final.forward
+    (raw2bit.py:1798-1846); returns (y_hat, y_likelihoods, z_likelihoods, means, scales)."""
     z = hyper_analysis(sd, y)
     eb, gc = _eb(sd), _gc()
     _, z_lik = eb(z)
@@ -352,19 +351,13 @@ def final_forward(sd, x, num_slices=5, trace=None):
         y_hat_slices.append(y_hat)
         liks.append(lik), mus.append(mu), scales.append(scale)
     y_hat = torch.cat(y_hat_slices, dim=1)
-    x_hat = synthesis(sd, y_hat)
     if trace is not None:
-        trace.update(z=z, z_hat=z_hat, latent_means=latent_means, latent_scales=latent_scales,
-                     y_hat=y_hat, gfm_vector=vec, local=local)
-    return {"x_hat": x_hat, "y": y, "lft": local[2], "lsc": lsc,
-            "likelihoods": {"y": torch.cat(liks, dim=1), "z": z_lik},
-            "para": {"means": torch.cat(mus, dim=1), "scales": torch.cat(scales, dim=1), "y": y}}
+        trace.update(z=z, z_hat=z_hat, latent_means=latent_means, latent_scales=latent_scales, y_hat=y_hat)
+    return y_hat, torch.cat(liks, dim=1), z_lik, torch.cat(mus, dim=1), torch.cat(scales, dim=1)
 
 
-@torch.no_grad()
-def final_compress(sd, x, num_slices=5, trace=None):
-    """raw_compression_tcm_final.compress, raw2bit.py:1876-1960."""
-    y, _, _, _ = analysis(sd, x)
+def _compress_core(sd, y, num_slices=5, trace=None):
+    """tcm.py:515-570 / raw2bit.py:1903-1960."""
     z = hyper_analysis(sd, y)
     eb, gc = _eb(sd), _gc()
     eb.update(force=True)
@@ -390,9 +383,8 @@ def final_compress(sd, x, num_slices=5, trace=None):
     return {"strings": [[y_string], z_strings], "shape": z.size()[-2:]}
 
 
-@torch.no_grad()
-def final_decompress(sd, strings, shape, num_slices=5):
-    """raw_compression_tcm_final.decompress, raw2bit.py:1982-2027."""
+def _decompress_core(sd, strings, shape, num_slices=5):
+    """tcm.py:592-634 / raw2bit.py:1982-2024; returns y_hat."""
     eb, gc = _eb(sd), _gc()
     eb.update(force=True)
     z_hat = eb.decompress(strings[1], shape)
@@ -409,7 +401,79 @@ def final_decompress(sd, strings, shape, num_slices=5):
         y_hat = rv + mu
         y_hat = y_hat + lrp(sd, i, mean_support, y_hat)
         y_hat_slices.append(y_hat)
-    return {"x_hat": synthesis(sd, torch.cat(y_hat_slices, dim=1)).clamp_(0, 1)}
+    return torch.cat(y_hat_slices, dim=1)
+
+
+@torch.no_grad()
+def final_forward(sd, x, num_slices=5, trace=None):
+    """raw_compression_tcm_final.forward, raw2bit.py:1766-1855 (eval mode)."""
+    y, lsc, local, vec = analysis(sd, x)
+    y_hat, y_lik, z_lik, means, scales = _forward_core(sd, y, num_slices, trace)
+    x_hat = synthesis(sd, y_hat)
+    if trace is not None:
+        trace.update(gfm_vector=vec, local=local)
+    return {"x_hat": x_hat, "y": y, "lft": local[2], "lsc": lsc, "likelihoods": {"y": y_lik, "z": z_lik},
+            "para": {"means": means, "scales": scales, "y": y}}
+
+
+@torch.no_grad()
+def final_compress(sd, x, num_slices=5, trace=None):
+    """raw_compression_tcm_final.compress, raw2bit.py:1876-1960."""
+    return _compress_core(sd, analysis(sd, x)[0], num_slices, trace)
+
+
+@torch.no_grad()
+def final_decompress(sd, strings, shape, num_slices=5):
+    """raw_compression_tcm_final.decompress, raw2bit.py:1982-2027."""
+    return {"x_hat": synthesis(sd, _decompress_core(sd, strings, shape, num_slices)).clamp_(0, 1)}
+
+
+# ----------------------------------------------------------------------------- TCM (RGB baseline, tcm.py:320-637)
+def tcm_analysis(sd, x):
+    """g_a, tcm.py:335-347,360: RBWS(3,128) + 3 x (2 ConvTransBlock + down)."""
+    h = rb_with_stride(sd, "g_a.0", x)
+    idx = 1
+    for lvl in range(3):
+        for i in range(2):
+            h = conv_trans_block(sd, f"g_a.{idx}", h, HEAD_DIM[lvl], 8, i % 2 == 1)
+            idx += 1
+        h = rb_with_stride(sd, f"g_a.{idx}", h) if lvl < 2 else conv(sd, f"g_a.{idx}", h, 2)
+        idx += 1
+    return h
+
+
+def tcm_synthesis(sd, y_hat):
+    """g_s, tcm.py:349-363: RBU(320,128) + 3 x (2 ConvTransBlock + up), last up = subpel_conv3x3(128, 3, 2)."""
+    h = rb_upsample(sd, "g_s.0", y_hat)
+    idx = 1
+    for lvl in range(3):
+        for i in range(2):
+            h = conv_trans_block(sd, f"g_s.{idx}", h, HEAD_DIM[3 + lvl], 8, i % 2 == 1)
+            idx += 1
+        h = rb_upsample(sd, f"g_s.{idx}", h) if lvl < 2 else subpel(sd, f"g_s.{idx}", h)
+        idx += 1
+    return h
+
+
+@torch.no_grad()
+def tcm_forward(sd, x, num_slices=5):
+    """TCM.forward, tcm.py:437-490."""
+    y = tcm_analysis(sd, x)
+    y_hat, y_lik, z_lik, means, scales = _forward_core(sd, y, num_slices)
+    return {"x_hat": tcm_synthesis(sd, y_hat), "likelihoods": {"y": y_lik, "z": z_lik},
+            "para": {"means": means, "scales": scales, "y": y}}
+
+
+@torch.no_grad()
+def tcm_compress(sd, x, num_slices=5, trace=None):
+    """TCM.compress, tcm.py:511-570."""
+    return _compress_core(sd, tcm_analysis(sd, x), num_slices, trace)
+
+
+@torch.no_grad()
+def tcm_decompress(sd, strings, shape, num_slices=5):
+    """TCM.decompress, tcm.py:592-637."""
+    return {"x_hat": tcm_synthesis(sd, _decompress_core(sd, strings, shape, num_slices)).clamp_(0, 1)}
 
 
 # ----------------------------------------------------------------------------- fast coder (plain C) wrappers
@@ -608,6 +672,58 @@ def gma_block(sd, x, size, num_heads=8, p=""):
     x = x + efficient_att(sd, pre + "att", cur, size, num_heads)
     cur = layernorm(sd, pre + "norm2", x)
     return x + linear(sd, pre + "mlp.fc2", F.gelu(linear(sd, pre + "mlp.fc1", cur)))
+
+
+def _tokens(x):
+    B, C, H, W = x.shape
+    return x.flatten(2).transpose(1, 2), (H, W)
+
+
+def _untokens(t, size):
+    B, N, C = t.shape
+    return t.transpose(1, 2).reshape(B, C, size[0], size[1])
+
+
+@torch.no_grad()
+def gma_pair(sd, p, x, num_heads):
+    """GMABlock.forward, raw2bit.py:168-184 (NCHW in/out, two GMA_Blocks)."""
+    pre = (p + ".") if p else ""
+    t, size = _tokens(x)
+    t = gma_block(sd, t, size, num_heads, pre + "block_1")
+    t = gma_block(sd, t, size, num_heads, pre + "block_2")
+    return _untokens(t, size)
+
+
+@torch.no_grad()
+def gma_atten(sd, p, x, num_heads):
+    """GMAAtten.forward, raw2bit.py:225-234 (compressai AttentionBlock gate around a GMABlock)."""
+    pre = (p + ".") if p else ""
+    x = conv(sd, pre + "in_conv", x)
+    z = gma_pair(sd, pre + "non_local_block", x, num_heads)
+
+    def unit(pp, v):
+        h = F.relu(conv(sd, pp + ".conv.0", v))
+        h = F.relu(conv(sd, pp + ".conv.2", h))
+        return F.relu(conv(sd, pp + ".conv.4", h) + v)
+
+    a, b = x, z
+    for i in range(3):
+        a = unit(f"{pre}conv_a.{i}", a)
+        b = unit(f"{pre}conv_b.{i}", b)
+    b = conv(sd, pre + "conv_b.3", b)
+    return conv(sd, pre + "out_conv", a * torch.sigmoid(b) + x)
+
+
+@torch.no_grad()
+def conv_gma_block(sd, p, x, conv_dim, num_heads):
+    """ConvGMABlock.forward, raw2bit.py:346-355."""
+    pre = (p + ".") if p else ""
+    both = conv(sd, pre + "conv1_1", x)
+    cx, tx = both[:, :conv_dim], both[:, conv_dim:]
+    cx = residual_block(sd, pre + "conv_block", cx) + cx
+    t, size = _tokens(tx)
+    tx = _untokens(gma_block(sd, t, size, num_heads, pre + "trans_block"), size)
+    return x + conv(sd, pre + "conv1_2", torch.cat((cx, tx), dim=1))
 
 
 def psnr(a, b, peak=None):

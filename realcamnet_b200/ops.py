@@ -61,8 +61,17 @@ def empty(N, H, W, C, like=None, device=None):
     return torch.empty((N, H, W, C), device=dev, dtype=torch.float32)
 
 
+_replayed = 0
+
+
 def launch_count() -> int:
-    return int(_C.lib().rcn_launch_count())
+    """Kernels launched by the library in this process, plus the launches replayed through CUDA graphs."""
+    return int(_C.lib().rcn_launch_count()) + _replayed
+
+
+def count_replayed(n: int):
+    global _replayed
+    _replayed += int(n)
 
 
 # ----------------------------------------------------------------------------- conv engine selection

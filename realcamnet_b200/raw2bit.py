@@ -22,7 +22,8 @@ from .layers import (AttentionBlock, Conv2d, Linear, ResidualBlock, ResidualBloc
 from .LiteISP import Color_Condition_GFM, Lens_Shading_Correction, Res_GFM
 from .ops import (ACT_CLAMP01, ACT_GELU, ACT_HALF_TANH, ACT_LRELU, ACT_NONE, ACT_RELU, ACT_SIGMOID, EPI_MUL_AUXP1,
                   EPI_MULP1_AUX, STORE_NCHW, STORE_PS2_NCHW)
-from .tcm import Block, ConvTransBlock, SWAtten, SwinBlock, get_scale_table  # noqa: F401
+from .tcm import (Block, ConvTransBlock, SliceCodecModel, StageRunner, SWAtten, SwinBlock, _cc_transform,  # noqa: F401
+                  _run_cc, get_scale_table)
 
 
 class CALayer(nn.Module):
@@ -235,18 +236,7 @@ class RBU(nn.Module):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
 
 
-def _cc_transform(in_ch, out_ch):
-    return nn.Sequential(conv(in_ch, 224, stride=1, kernel_size=3), nn.GELU(), conv(224, 128, stride=1, kernel_size=3),
-                         nn.GELU(), conv(128, out_ch, stride=1, kernel_size=3))
-
-
-def _run_cc(seq, x, **last):
-    h, sp = seq[0]._f(x, act=ACT_GELU, emit_split=True, keep_fp32=False)
-    h, sp = seq[2]._f(h, act=ACT_GELU, presplit=sp, emit_split=True, keep_fp32=False)
-    return seq[4]._f(h, presplit=sp, **last)
-
-
-class raw_compression_tcm_final(CompressionModel):
+class raw_compression_tcm_final(SliceCodecModel):
     """The paper model (models/raw2bit.py:1614-2027).
 
     forward(x=[raw(B,4,H,W), cond(B,4,h',w'), coord(B,2,H,W)]) -> dict(x_hat, y, lft, lsc, likelihoods{y,z},
@@ -310,37 +300,6 @@ class raw_compression_tcm_final(CompressionModel):
         self.entropy_bottleneck = EntropyBottleneck(192)
         self.gaussian_conditional = GaussianConditional(None)
 
-    # ------------------------------------------------------------------------------ host logic
-    def update(self, scale_table=None, force=False):
-        if scale_table is None:
-            scale_table = get_scale_table()
-        updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
-        updated |= super().update(force=force)
-        return updated
-
-    def load_state_dict(self, state_dict, strict=True):
-        """models/raw2bit.py:1857-1864: size the CDF buffers from the checkpoint first."""
-        gc = self.gaussian_conditional
-        for name in ("_quantized_cdf", "_offset", "_cdf_length", "scale_table"):
-            key = f"gaussian_conditional.{name}"
-            if key not in state_dict:
-                continue
-            buf = getattr(gc, name)
-            if buf.numel() == 0:
-                buf.resize_(state_dict[key].size())
-        eb = self.entropy_bottleneck
-        for name in ("_quantized_cdf", "_offset", "_cdf_length"):
-            key = f"entropy_bottleneck.{name}"
-            if key in state_dict and getattr(eb, name).numel() == 0:
-                getattr(eb, name).resize_(state_dict[key].size())
-        return super().load_state_dict(state_dict, strict=strict)
-
-    def _scale_table_dev(self):
-        gc = self.gaussian_conditional
-        if gc.scale_table.numel() == 0:  # forward() before update(): likelihoods do not need the table
-            gc.scale_table = get_scale_table().to(gc.scale_bound.device)
-        return gc.scale_table
-
     # ------------------------------------------------------------------------------ transforms (NHWC)
     def _analysis(self, x):
         """models/raw2bit.py:1771-1796 (and 1877-1901 in compress)."""
@@ -360,18 +319,6 @@ class raw_compression_tcm_final(CompressionModel):
             fea = down._f(fea)
         return fea, lsc_fea, local
 
-    def _h_a(self, y):
-        z = self.h_a[0]._f(y)
-        for blk in list(self.h_a)[1:-1]:
-            z = blk._f(z)
-        return self.h_a[-1]._f(z)
-
-    def _h_s(self, net, z_hat, out):
-        h = net[0]._f(z_hat)
-        for blk in list(net)[1:-1]:
-            h = blk._f(h)
-        return net[-1]._f(h, out=out)
-
     def _g_s(self, y_hat, clamp=False):
         h = y_hat
         mods = list(self.g_s)
@@ -379,175 +326,114 @@ class raw_compression_tcm_final(CompressionModel):
             h = m._f(h)
         return mods[-1]._f(h, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
 
-    def _alloc_supports(self, z_hat):
-        N, hz, wz, _ = z_hat.shape
-        h, w = hz * 4, wz * 4
-        tot = 320 + (320 // self.num_slices) * self.num_slices
-        ms = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_means] + y_hat_slices)
-        ss = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_scales] + y_hat_slices)
-        self._h_s(self.h_scale_s, z_hat, ss[..., :320])
-        self._h_s(self.h_mean_s, z_hat, ms[..., :320])
-        return ms, ss, h, w
-
-    def _slice_params(self, i, ms, ss):
-        """raw2bit.py:1818-1828: returns (lrp_support buffer, mu, scale)."""
-        sl = 320 // self.num_slices
-        cin = 320 + sl * min(i, self.max_support_slices if self.max_support_slices >= 0 else i)
-        N, h, w, _ = ms.shape
-        lrp_sup = ops.empty(N, h, w, cin + sl, like=ms)                 # cat([mean_support, y_hat_slice])
-        mean_support = self.atten_mean[i][0]._f(ms[..., :cin], out=lrp_sup[..., :cin])
-        mu = _run_cc(self.cc_mean_transforms[i], mean_support)
-        scale_support = self.atten_scale[i][0]._f(ss[..., :cin])
-        scale = _run_cc(self.cc_scale_transforms[i], scale_support)
-        return lrp_sup, cin, mu, scale
-
-    def _finish_slice(self, i, lrp_sup, cin, ms, ss):
-        """y_hat_slice += 0.5*tanh(lrp(...)) written into both support buffers (raw2bit.py:1835-1840)."""
-        sl = 320 // self.num_slices
-        dst = ms[..., 320 + sl * i: 320 + sl * (i + 1)]
-        _run_cc(self.lrp_transforms[i], lrp_sup, act=ACT_HALF_TANH, res=lrp_sup[..., cin:], out=dst)
-        ops.copy_channels(dst, ss[..., 320 + sl * i: 320 + sl * (i + 1)])
-
     # ------------------------------------------------------------------------------ public API
     @torch.no_grad()
     def forward(self, x, emit_strings=False):
         if self.training:
             raise NotImplementedError("inference path only: call .eval() (train mode adds quantisation noise)")
-        y, lsc_fea, local = self._analysis(x)
-        z = self._h_a(y)
-        z_hat, z_lik, z_sym = self.entropy_bottleneck._f(z, want_symbols=emit_strings)
-        ms, ss, h, w = self._alloc_supports(z_hat)
-        N = y.shape[0]
-        sl = 320 // self.num_slices
-        table = self._scale_table_dev()
-        gc = self.gaussian_conditional
-        means = ops.empty(N, h, w, 320, like=y)
-        scales = ops.empty(N, h, w, 320, like=y)
-        y_lik = ops.empty(N, h, w, 320, like=y)
-        nslice = N * sl * h * w
+
+        def stage_a(xs):
+            y, lsc_fea, local = self._analysis(xs)
+            E = self._entropy_stage(y, emit_strings)
+            E.y, E.lsc_fea, E.lft = y, lsc_fea, local[2]
+            return E
+
+        def stage_b(E):
+            # the coder front end (CDF lookups) ran inside the Gaussian kernel of stage a; its D2H copy is started between the
+            # stages so the host state chain runs WHILE the synthesis transform g_s (half of the FLOPs) executes
+            y_nchw = ops.to_nchw(E.y)
+            return {"x_hat": self._g_s(E.ms[..., 320:]), "y": y_nchw, "lft": ops.to_nchw(E.lft), "lsc": ops.to_nchw(E.lsc_fea),
+                    "likelihoods": {"y": ops.to_nchw(E.y_lik), "z": ops.to_nchw(E.z_lik)},
+                    "para": {"means": ops.to_nchw(E.means), "scales": ops.to_nchw(E.scales), "y": y_nchw}}
+
+        run = StageRunner(self, ("forward", emit_strings), list(x), stage_a, stage_b)
+        E = run.a()
+        pending = self._begin_host_copy(E.coder.packed, E.coder.raw, E.coder.flags, E.z_sym) if emit_strings else None
+        out = dict(run.b())
         if emit_strings:
-            sym = torch.empty((self.num_slices, nslice), device=y.device, dtype=torch.int32)
-            idx = torch.empty_like(sym)
-            coder = self._coder_prep(self.num_slices * nslice)
-        for i in range(self.num_slices):
-            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
-            ops.copy_channels(mu, means[..., sl * i: sl * (i + 1)])
-            ops.copy_channels(scale, scales[..., sl * i: sl * (i + 1)])
-            ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
-                                     lik=y_lik[..., sl * i: sl * (i + 1)],
-                                     symbols=sym[i] if emit_strings else None, indexes=idx[i] if emit_strings else None,
-                                     scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound,
-                                     coder=coder if emit_strings else None, pos_base=i * nslice)
-            self._finish_slice(i, lrp_sup, cin, ms, ss)
-        # the coder front end (CDF lookups) ran inside the Gaussian kernel; start the D2H copy of its packed output on a
-        # side stream so the host state chain runs WHILE the synthesis transform g_s (half of the FLOPs) executes
-        pending = self._begin_host_copy(coder.packed, coder.raw, coder.flags, z_sym) if emit_strings else None
-        x_hat = self._g_s(ms[..., 320:])
-        y_nchw = ops.to_nchw(y)
-        out = {"x_hat": x_hat, "y": y_nchw, "lft": ops.to_nchw(local[2]), "lsc": ops.to_nchw(lsc_fea),
-               "likelihoods": {"y": ops.to_nchw(y_lik), "z": ops.to_nchw(z_lik)},
-               "para": {"means": ops.to_nchw(means), "scales": ops.to_nchw(scales), "y": y_nchw}}
-        if emit_strings:
-            out["strings"] = [[self._finish_y_string(pending, sym, idx)], self.entropy_bottleneck.compress_symbols(pending[1][3])]
-            out["shape"] = torch.Size(z.shape[1:3])
+            out["strings"] = self._strings(E, pending)
+            out["shape"] = torch.Size(E.z.shape[1:3])
         return out
-
-    def _coder_prep(self, nsym):
-        gc = self.gaussian_conditional
-        if gc._offset.numel() == 0:
-            raise RuntimeError("call update() before producing bitstreams (models/raw2bit.py:1759-1764)")
-        return ops.CoderPrep(nsym, gc._quantized_cdf, gc._cdf_length, gc._offset)
-
-    def _finish_y_string(self, pending, sym=None, idx=None):
-        """Host state chain over the GPU-prepared symbols."""
-        from .entropy_models import rans_encode_packed
-
-        h_packed, h_raw, h_flags = self._end_host_copy(pending)[:3]
-        return rans_encode_packed(h_packed.numpy(), h_raw.numpy(), h_flags.numpy())
-
-    def _begin_host_copy(self, *tensors):
-        """Async device->pinned-host copies on a side stream, ordered after the work already queued."""
-        dev = tensors[0].device
-        if getattr(self, "_side", None) is None or self._side.device != dev:
-            self._side = torch.cuda.Stream(device=dev)
-            self._pinned = {}
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
-        self._side.wait_event(ev)
-        host = []
-        with torch.cuda.stream(self._side):
-            for j, t in enumerate(tensors):
-                key = (j, tuple(t.shape), t.dtype)
-                h = self._pinned.get(key)
-                if h is None:
-                    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                    self._pinned[key] = h
-                h.copy_(t, non_blocking=True)
-                host.append(h)
-            done = torch.cuda.Event()
-            done.record(self._side)
-        return done, host, tensors  # the device tensors stay referenced until the copy has completed
-
-    @staticmethod
-    def _end_host_copy(pending):
-        done, host, _keep = pending
-        done.synchronize()
-        return host
-
-    def _encode_y(self, sym, idx):
-        cdf, length, offset = self.gaussian_conditional.host_tables()
-        s = sym.cpu().numpy() if sym.is_cuda else sym.numpy()
-        i = idx.cpu().numpy() if idx.is_cuda else idx.numpy()
-        return rans_encode(s.reshape(-1), i.reshape(-1), cdf, length, offset)
 
     @torch.no_grad()
     def compress(self, x):
         """models/raw2bit.py:1876-1960."""
         if self.gaussian_conditional._offset.numel() == 0:
             raise RuntimeError("call update() before compress()")
-        y, _, _ = self._analysis(x)
-        z = self._h_a(y)
-        z_hat, _, z_sym = self.entropy_bottleneck._f(z, want_symbols=True, want_lik=False)
-        z_strings = self.entropy_bottleneck.compress_symbols(z_sym)
-        ms, ss, h, w = self._alloc_supports(z_hat)
-        N = y.shape[0]
-        sl = 320 // self.num_slices
-        gc = self.gaussian_conditional
-        table = self._scale_table_dev()
-        nslice = N * sl * h * w
-        sym = torch.empty((self.num_slices, nslice), device=y.device, dtype=torch.int32)
-        idx = torch.empty_like(sym)
-        coder = self._coder_prep(self.num_slices * nslice)
-        for i in range(self.num_slices):
-            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
-            ops.gaussian_conditional(y[..., sl * i: sl * (i + 1)], mu, scale, table, y_hat=lrp_sup[..., cin:],
-                                     symbols=sym[i], indexes=idx[i], scale_bound=gc._scale_bound, lik_bound=gc.likelihood_bound,
-                                     coder=coder, pos_base=i * nslice)
-            self._finish_slice(i, lrp_sup, cin, ms, ss)
-        pending = self._begin_host_copy(coder.packed, coder.raw, coder.flags)
-        return {"strings": [[self._finish_y_string(pending, sym, idx)], z_strings], "shape": torch.Size(z.shape[1:3])}
+        run = StageRunner(self, ("compress",), list(x), lambda xs: self._entropy_stage(self._analysis(xs)[0], True, want_lik=False),
+                          None)
+        E = run.a()
+        pending = self._begin_host_copy(E.coder.packed, E.coder.raw, E.coder.flags, E.z_sym)
+        return {"strings": self._strings(E, pending), "shape": torch.Size(E.z.shape[1:3])}
 
     @torch.no_grad()
     def decompress(self, strings, shape):
         """models/raw2bit.py:1982-2027 (batch 1, like the reference)."""
-        if self.gaussian_conditional._offset.numel() == 0:
-            raise RuntimeError("call update() before decompress()")
-        z_hat = self.entropy_bottleneck._decompress_nhwc(strings[1], shape)
-        ms, ss, h, w = self._alloc_supports(z_hat)
-        N = z_hat.shape[0]
-        sl = 320 // self.num_slices
-        gc = self.gaussian_conditional
-        table = self._scale_table_dev()
-        cdf, length, offset = gc.host_tables()
-        dec = RansDecoder()
-        dec.set_stream(strings[0][0])
-        idx = torch.empty((N, sl, h, w), device=z_hat.device, dtype=torch.int32)
-        for i in range(self.num_slices):
-            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
-            ops.build_indexes(scale, table, idx, gc._scale_bound)
-            rv = dec.decode_stream(idx.cpu().numpy(), cdf, length, offset)
-            rv = torch.from_numpy(rv).to(z_hat.device)
-            ops.gaussian_dequantize(rv, mu, lrp_sup[..., cin:])
-            self._finish_slice(i, lrp_sup, cin, ms, ss)
-        dec.close()
-        return {"x_hat": self._g_s(ms[..., 320:], clamp=True)}
+        return {"x_hat": self._g_s(self._decode_stage(strings, shape), clamp=True)}
+
+
+# ----------------------------------------------------------------------------- GroupMix drop-ins (SURVEY 8a G5)
+class GMABlock(nn.Module):
+    """Two GMA_Blocks on an NCHW map (models/raw2bit.py:168-184): the GroupMix replacement of SwinBlock."""
+
+    def __init__(self, input_dim, head_dim, drop_path) -> None:
+        super().__init__()
+        self.input_dim = input_dim
+        self.num_head = input_dim // head_dim
+        self.block_1 = GMA_Block(input_dim, self.num_head, drop_path_rate=drop_path)
+        self.block_2 = GMA_Block(input_dim, self.num_head, drop_path_rate=drop_path)
+
+    def _f(self, x):
+        return self.block_2._f(self.block_1._f(x))
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+class GMAAtten(AttentionBlock):
+    """GroupMix-gated attention of the entropy parameter nets (models/raw2bit.py:209-234; SWAtten with GMABlock inside)."""
+
+    def __init__(self, input_dim, output_dim, head_dim, drop_path, inter_dim=192) -> None:
+        if inter_dim is None:
+            # the reference's inter_dim=None branch builds GMABlock but then calls the undefined in_conv/out_conv
+            # (models/raw2bit.py:219-234): it can never run
+            raise NotImplementedError("GMAAtten(inter_dim=None) cannot run in the reference (forward needs in_conv/out_conv)")
+        super().__init__(N=inter_dim)
+        self.num_head = inter_dim // head_dim
+        self.head_dim = head_dim
+        self.non_local_block = GMABlock(inter_dim, head_dim, drop_path=drop_path)
+        self.in_conv = conv1x1(input_dim, inter_dim)
+        self.out_conv = conv1x1(inter_dim, output_dim)
+
+    def _f(self, x, out=None):
+        x = self.in_conv._f(x)
+        z = self.non_local_block._f(x)
+        return self.out_conv._f(self._gate(x, z, x), out=out)
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+class ConvGMABlock(nn.Module):
+    """Conv || GroupMix block, shape-compatible with ConvTransBlock (models/raw2bit.py:330-355)."""
+
+    def __init__(self, conv_dim, trans_dim, head_dim, drop_path=0.):
+        super().__init__()
+        self.conv_dim, self.trans_dim, self.head_dim = conv_dim, trans_dim, head_dim
+        self.num_head = trans_dim // head_dim
+        self.drop_path = drop_path
+        self.trans_block = GMA_Block(trans_dim, self.num_head, drop_path_rate=drop_path)
+        self.conv1_1 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
+        self.conv1_2 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
+        self.conv_block = ResidualBlock(conv_dim, conv_dim)
+
+    def _f(self, x, out=None):
+        cd = self.conv_dim
+        both = self.conv1_1._f(x)
+        cat = torch.empty_like(both)
+        self.conv_block._f(both[..., :cd], out=cat[..., :cd], extra_identity=True)
+        self.trans_block._f(both[..., cd:], out=cat[..., cd:])
+        return self.conv1_2._f(cat, res=x, out=out)
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))

@@ -24,9 +24,16 @@ from oracle import inputs, ref_import, weights  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def main():
+def main(only_new=False):
     ref = ref_import.import_reference()
     torch.set_grad_enabled(False)
+    if only_new:      # fixtures added later in the round: leave the committed earlier ones untouched
+        return extra(ref)
+    base(ref)
+    extra(ref)
+
+
+def base(ref):
 
     # ---- raw_compression_tcm_final, T=256 (raw2bit.py:1614-2027)
     m = ref.raw2bit.raw_compression_tcm_final().eval()
@@ -71,8 +78,39 @@ def main():
         xx = torch.randn(2, 24 * 16, dim, generator=gen)
         o = g(xx, (24, 16))
         np.savez_compressed(os.path.join(OUT, f"gma_dim{dim}.npz"), x=xx.numpy(), out=o.numpy())
+
+
+def extra(ref):
+    # ---- GroupMix drop-in wrappers, the two instantiations of the reference's test_gma (raw2bit.py:4361-4367)
+    g = ref.raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.).eval()
+    weights.fill_(g, seed=0)
+    xx = torch.randn(1, 144, 32, 32, generator=torch.Generator().manual_seed(901))
+    np.savez_compressed(os.path.join(OUT, "conv_gma_block.npz"), x=xx.numpy(), out=g(xx).numpy())
+    g = ref.raw2bit.GMAAtten(320, 320, 25, 0., 200).eval()
+    weights.fill_(g, seed=0)
+    xx = torch.randn(1, 320, 32, 32, generator=torch.Generator().manual_seed(902))
+    np.savez_compressed(os.path.join(OUT, "gma_atten.npz"), x=xx.numpy(), out=g(xx).numpy())
+
+    # ---- TCM, the RGB baseline with the same entropy model (tcm.py:320-637), 256x256
+    m = ref.tcm.TCM().eval()
+    weights.fill_(m, seed=0)
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(1236))
+    out = m(x)
+    m.update(force=True)
+    c = m.compress(x)
+    d = m.decompress(c["strings"], c["shape"])
+    np.savez_compressed(
+        os.path.join(OUT, "tcm_T256.npz"), x_sum=np.float64(x.double().sum()),
+        weights_abs_sum=np.float64(weights.checksum(m.state_dict())["abs_sum"]),
+        y=out["para"]["y"].numpy(), means=out["para"]["means"].numpy(), scales=out["para"]["scales"].numpy(),
+        lik_y_sub=out["likelihoods"]["y"][:, ::4].numpy(), lik_z=out["likelihoods"]["z"].numpy(),
+        x_hat_sub=out["x_hat"][:, :, ::2, ::2].numpy(), x_hat_abs_sum=np.float64(out["x_hat"].double().abs().sum()),
+        dec_x_hat_sub=d["x_hat"][:, :, ::2, ::2].numpy(),
+        y_string=np.frombuffer(c["strings"][0][0], dtype=np.uint8),
+        z_string=np.frombuffer(c["strings"][1][0], dtype=np.uint8), shape=np.asarray(c["shape"]))
+    print("tcm_T256: y bytes", len(c["strings"][0][0]), "z bytes", len(c["strings"][1][0]))
     print("done")
 
 
 if __name__ == "__main__":
-    main()
+    main(only_new="--extra" in sys.argv)

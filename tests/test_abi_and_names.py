@@ -89,14 +89,22 @@ def test_update_builds_the_oracle_tables():
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference only exists in the authoring container")
-@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200"])
+@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200", "tcm", "convgma", "gmaatten", "gmablock"])
 def test_state_dict_names_match_reference(which):
     from oracle import ref_import
 
     ref = ref_import.import_reference()
-    from realcamnet_b200 import LiteISP, groupmix, raw2bit
+    from realcamnet_b200 import LiteISP, groupmix, raw2bit, tcm
 
-    if which == "final":
+    if which == "tcm":
+        a, b = ref.tcm.TCM(), tcm.TCM()
+    elif which == "convgma":
+        a, b = ref.raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.), raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.)
+    elif which == "gmaatten":
+        a, b = ref.raw2bit.GMAAtten(320, 320, 25, 0., 200), raw2bit.GMAAtten(320, 320, 25, 0., 200)
+    elif which == "gmablock":
+        a, b = ref.raw2bit.GMABlock(200, 25, 0.), raw2bit.GMABlock(200, 25, 0.)
+    elif which == "final":
         a, b = ref.raw2bit.raw_compression_tcm_final(), raw2bit.raw_compression_tcm_final()
     elif which == "liteisp":
         a, b = ref.LiteISP.LiteISPNet_GFM_LSC(), LiteISP.LiteISPNet_GFM_LSC()

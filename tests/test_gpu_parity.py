@@ -365,6 +365,82 @@ def test_final_compress_roundtrip_and_bytes(final_pair):
         assert rel(d["x_hat"][:, :, ::4, ::4], torch.from_numpy(gold["dec_x_hat_sub"])) < TOL
 
 
+def test_gma_wrappers_match_oracle_and_fixture(dev, engine, golden_dir):
+    """ConvGMABlock / GMAAtten / GMABlock in the reference's test_gma configuration."""
+    from realcamnet_b200 import raw2bit
+
+    gold = np.load(os.path.join(golden_dir, "conv_gma_block.npz"))
+    m = raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.)
+    weights.fill_(m, seed=0)
+    out = m.to(dev).eval()(torch.from_numpy(gold["x"]).to(dev))
+    assert rel(out, torch.from_numpy(gold["out"])) < 1e-4
+    gold = np.load(os.path.join(golden_dir, "gma_atten.npz"))
+    m = raw2bit.GMAAtten(320, 320, 25, 0., 200)
+    weights.fill_(m, seed=0)
+    out = m.to(dev).eval()(torch.from_numpy(gold["x"]).to(dev))
+    assert rel(out, torch.from_numpy(gold["out"])) < 1e-4
+    m = raw2bit.GMABlock(200, 25, 0.)
+    weights.fill_(m, seed=0)
+    sd = cpu_sd(m)
+    x = torch.randn(2, 200, 24, 40, generator=torch.Generator().manual_seed(5))
+    assert rel(m.to(dev).eval()(x.to(dev)), refpath.gma_pair(sd, "", x, 8)) < 1e-4
+
+
+def test_tcm_matches_oracle_fixture_and_roundtrips(dev, engine, golden_dir):
+    """TCM.forward / compress / decompress (tcm.py:437-637)."""
+    from realcamnet_b200 import tcm
+
+    gold = np.load(os.path.join(golden_dir, "tcm_T256.npz"))
+    m = tcm.TCM()
+    weights.fill_(m, seed=0)
+    m = m.to(dev).eval()
+    m.update()
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(1236)).to(dev)
+    out = m(x, emit_strings=True)
+    assert set(out.keys()) == {"x_hat", "likelihoods", "para", "strings", "shape"}
+    assert rel(out["para"]["y"], torch.from_numpy(gold["y"])) < TOL
+    sym = torch.round(out["para"]["y"] - out["para"]["means"]).cpu()
+    ref_sym = torch.round(torch.from_numpy(gold["y"]) - torch.from_numpy(gold["means"]))
+    mismatch = float((sym != ref_sym).float().mean())
+    assert mismatch < 1e-3, f"{mismatch:.2e} of the symbols differ"
+    assert refpath.psnr(out["x_hat"][:, :, ::2, ::2].cpu(), torch.from_numpy(gold["x_hat_sub"])) > 50.0
+    c = m.compress(x)
+    assert c["strings"][0][0] == out["strings"][0][0] and c["strings"][1] == out["strings"][1]
+    assert c["strings"][1][0] == gold["z_string"].tobytes()
+    d = m.decompress(c["strings"], c["shape"])
+    assert torch.equal(d["x_hat"], out["x_hat"].clamp(0, 1))
+    if mismatch == 0.0:
+        assert rel(out["para"]["means"], torch.from_numpy(gold["means"])) < TOL
+        assert rel(out["para"]["scales"], torch.from_numpy(gold["scales"])) < TOL
+        assert rel(out["x_hat"][:, :, ::2, ::2], torch.from_numpy(gold["x_hat_sub"])) < TOL
+        if c["strings"][0][0] == gold["y_string"].tobytes():
+            assert rel(d["x_hat"][:, :, ::2, ::2], torch.from_numpy(gold["dec_x_hat_sub"])) < TOL
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager(final_pair):
+    """enable_cuda_graphs(): the replayed two-stage graphs give the eager results bit for bit, also on new inputs."""
+    gold, m, sd, x, xd = final_pair
+    eager = m(xd, emit_strings=True)
+    eager = {"x_hat": eager["x_hat"].clone(), "y": eager["y"].clone(), "lik": eager["likelihoods"]["y"].clone(),
+             "strings": eager["strings"]}
+    x2 = [t.to(xd[0].device) for t in inputs.make_inputs(256, seed=4321)]
+    eager2 = m(x2, emit_strings=True)
+    e2 = (eager2["x_hat"].clone(), eager2["strings"])
+    m.enable_cuda_graphs(True)
+    try:
+        for _ in range(2):      # capture, then a pure replay
+            g = m(xd, emit_strings=True)
+            assert torch.equal(g["x_hat"], eager["x_hat"]) and torch.equal(g["y"], eager["y"])
+            assert torch.equal(g["likelihoods"]["y"], eager["lik"])
+            assert g["strings"] == eager["strings"]
+        g2 = m(x2, emit_strings=True)
+        assert torch.equal(g2["x_hat"], e2[0]) and g2["strings"] == e2[1]
+        c = m.compress(xd)
+        assert c["strings"] == eager["strings"]
+    finally:
+        m.enable_cuda_graphs(False)
+
+
 def test_batch_and_nonsquare_tiles(dev, engine):
     """Edge cases: batch 2 and a 256x384 tile give the same result as the oracle."""
     from realcamnet_b200 import raw2bit

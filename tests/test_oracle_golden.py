@@ -91,3 +91,46 @@ def test_gma_block_matches_reference_fixture(golden_dir, dim):
     sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
     o = refpath.gma_block(sd, torch.from_numpy(g["x"]), (24, 16), 8)
     np.testing.assert_allclose(o.numpy(), g["out"], rtol=0, atol=2e-6)
+
+
+# ----------------------------------------------------------------------------- fixtures added later in round 1
+def test_gma_wrappers_match_reference_fixture(golden_dir):
+    """ConvGMABlock / GMAAtten in the reference's own test_gma configuration (raw2bit.py:4361-4367)."""
+    from realcamnet_b200 import raw2bit
+
+    g = np.load(os.path.join(golden_dir, "conv_gma_block.npz"))
+    m = raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.)
+    weights.fill_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    o = refpath.conv_gma_block(sd, "", torch.from_numpy(g["x"]), 64, 8)
+    np.testing.assert_allclose(o.numpy(), g["out"], rtol=0, atol=2e-6 * float(np.abs(g["out"]).max()))
+    g = np.load(os.path.join(golden_dir, "gma_atten.npz"))
+    m = raw2bit.GMAAtten(320, 320, 25, 0., 200)
+    weights.fill_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    o = refpath.gma_atten(sd, "", torch.from_numpy(g["x"]), 8)
+    np.testing.assert_allclose(o.numpy(), g["out"], rtol=0, atol=2e-6 * float(np.abs(g["out"]).max()))
+
+
+def test_tcm_matches_reference_fixture(golden_dir):
+    """TCM (tcm.py:320-637): forward, compress bytes and decompress of the oracle == the unmodified reference's."""
+    from realcamnet_b200 import tcm
+
+    g = np.load(os.path.join(golden_dir, "tcm_T256.npz"))
+    m = tcm.TCM()
+    weights.fill_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert abs(weights.checksum(sd)["abs_sum"] - float(g["weights_abs_sum"])) < 1e-3
+    x = torch.rand(1, 3, 256, 256, generator=torch.Generator().manual_seed(1236))
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6
+    out = refpath.tcm_forward(sd, x)
+    np.testing.assert_array_equal(out["para"]["y"].numpy(), g["y"])
+    np.testing.assert_array_equal(out["para"]["means"].numpy(), g["means"])
+    np.testing.assert_array_equal(out["para"]["scales"].numpy(), g["scales"])
+    np.testing.assert_array_equal(out["likelihoods"]["y"][:, ::4].numpy(), g["lik_y_sub"])
+    np.testing.assert_array_equal(out["likelihoods"]["z"].numpy(), g["lik_z"])
+    np.testing.assert_array_equal(out["x_hat"][:, :, ::2, ::2].numpy(), g["x_hat_sub"])
+    c = refpath.tcm_compress(sd, x)
+    assert c["strings"][0][0] == g["y_string"].tobytes() and c["strings"][1][0] == g["z_string"].tobytes()
+    d = refpath.tcm_decompress(sd, c["strings"], c["shape"])
+    np.testing.assert_array_equal(d["x_hat"][:, :, ::2, ::2].numpy(), g["dec_x_hat_sub"])
