@@ -92,7 +92,9 @@ typedef struct rcn_conv_desc {
     /* optional (tcgen05 engine, RCN_STORE_NHWC / RCN_STORE_PS2 with Cp_out % 64 == 0 stored channels): also write the result
      * as the NEXT layer's bf16 hi/lo operand planes (pixel stride Cp_out), so that layer needs no rcn_split_bf16 pass.
      * y may then be NULL (planes only: the fp32 tensor of a conv->conv chain is never materialised). */
-    void* y_hi; void* y_lo; int Cp_out;
+    void* y_hi; void* y_lo; int Cp_out;   /* Cp_out = pixel stride of the emitted planes (>= stored channels: a channel slice of a
+                                           * wider plane buffer, e.g. one half of a concat the next layer reads) */
+    int ldp_in;          /* rcn_conv2d_tc: pixel stride of the INPUT planes x_hi/x_lo in elements (0 = Cp, dense planes) */
 } rcn_conv_desc;
 
 int rcn_conv2d(const rcn_conv_desc* d, void* stream);
@@ -218,7 +220,8 @@ int rcn_groupmix_attention(const float* q, int ldq, const float* k, int ldk, con
  *   x_hi/x_lo : (N,H,W,Cp) bf16 planes from rcn_split_bf16 (x = hi + lo; lo may be NULL when passes == 1)
  *   w_hi/w_lo : [Cout][k*k][Cp] bf16 from rcn_pack_conv_weight_tc
  *   passes    : 1 = bf16 (hi*hi) ; 3 = "bf16x3" (hi*hi + lo*hi + hi*lo, ~fp32-grade products)
- * stride 1: planes from rcn_split_bf16; stride 2 (even H, W): planes from rcn_split_bf16_s2.  Cp is a multiple of 64. */
+ * stride 1: planes from rcn_split_bf16; stride 2 (even H, W): planes from rcn_split_bf16_s2.
+ * Cp is 16 (Cin <= 16), 32 (Cin <= 32) or a multiple of 64: it is also the K chunk the kernel stages per pipeline step. */
 int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                   int Cp, int passes, void* stream);
 /* fp32 NHWC (pixel stride ldx) -> zero-padded bf16 hi/lo planes; square != 0 feeds x*x (GDN norm pool) */

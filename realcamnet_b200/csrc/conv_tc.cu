@@ -26,8 +26,10 @@
 namespace rcn {
 namespace {
 
-constexpr int TILE_H = 8, TILE_W = 16, BLOCK_K = 64;
-constexpr int A_BYTES = 128 * BLOCK_K * 2;  // 16 KB
+constexpr int TILE_H = 8, TILE_W = 16;
+// K chunk per pipeline stage: 64 channels (128-byte swizzled rows) in general; 32 / 16 channels (64- / 32-byte swizzled rows) for
+// layers with <= 32 / <= 16 input channels, whose operand planes are then only that wide (the packed-Bayer ingest convs and the
+// condition UNet would otherwise move 2-16x zero padding through L2 and shared memory for each of the 9 taps).
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -84,20 +86,22 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+// K-major swizzled operand tile: rows of bk*2 bytes (128 / 64 / 32), 8-row groups 8*bk*2 bytes apart
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);  // start address, 16-byte units
     d |= (uint64_t)1 << 16;                       // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;             // stride byte offset between 8-row groups
+    d |= (uint64_t)((uint32_t)(16 * bk) >> 4) << 32;   // stride byte offset between 8-row groups
     d |= (uint64_t)1 << 46;                       // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                       // SWIZZLE_128B
+    d |= (uint64_t)(bk == 64 ? 2 : (bk == 32 ? 4 : 6)) << 61;   // SWIZZLE_128B / SWIZZLE_64B / SWIZZLE_32B
     return d;
 }
 
 struct TcParams {
     rcn_conv_desc d;
-    int Cp;       // padded input channels (multiple of 64) of the bf16 planes / packed weights
+    int Cp;       // padded input channels of the bf16 planes / packed weights (multiple of bk)
+    int bk;       // K chunk per stage: 64, 32 or 16 channels
+    int a_bytes, b_bytes;   // shared-memory footprint of one A / B tile (1024-byte multiples)
     int Ntile;    // output channels per tile (multiple of 16, <= 128)
     int tiles_x, tiles_y, tiles_n;
     long long total_tiles;
@@ -462,8 +466,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const rcn_conv_desc& p = P.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int B_BYTES = P.Ntile * BLOCK_K * 2;
-    const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);  // multiple of 1024 (Ntile % 16 == 0)
+    const int BLOCK_K = P.bk, A_BYTES = P.a_bytes, B_BYTES = P.b_bytes;
+    const int stage_bytes = (P.passes == 3 ? 2 : 1) * (A_BYTES + B_BYTES);  // multiple of 1024
     float* stg = reinterpret_cast<float*>(smem + (size_t)P.stages * stage_bytes);
     float* sbias_mem = reinterpret_cast<float*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)P.stages * stage_bytes + STG_BYTES + BIAS_BYTES);
@@ -498,7 +502,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ================= TMA producer =================
         if (lane == 0) {
             const bool loadA = !(P.dbg & 4);
-            const uint32_t tx_bytes = loadA ? (uint32_t)stage_bytes : (uint32_t)((P.passes == 3 ? 2 : 1) * B_BYTES);
+            const uint32_t b_tx = (uint32_t)(P.Ntile * BLOCK_K * 2), a_tx = (uint32_t)(128 * BLOCK_K * 2);   // bytes the boxes really carry
+            const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (b_tx + (loadA ? a_tx : 0u));
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
@@ -556,9 +561,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t a_hi = make_sw128_desc(sa), b_hi = make_sw128_desc(sa + A_BYTES);
-                    const uint64_t a_lo = make_sw128_desc(sa + A_BYTES + B_BYTES), b_lo = make_sw128_desc(sa + 2 * A_BYTES + B_BYTES);
-#pragma unroll
+                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
+                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
+                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
+#pragma unroll 4
                     for (int j = 0; j < ((P.dbg & 2) ? 0 : BLOCK_K / 16); ++j) {
                         const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
                         if (P.passes == 3) {
@@ -704,23 +710,28 @@ EncodeTiledFn get_encode() {
     return fn;
 }
 
-bool make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cp) {
+CUtensorMapSwizzle swizzle_of(int bk) {
+    return bk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (bk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// planes (N,H,W,Cp) with pixel stride ldp >= Cp elements (a channel slice of a wider plane buffer when ldp > Cp)
+bool make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cp, int ldp, int bk) {
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cp * 2, (cuuint64_t)W * Cp * 2, (cuuint64_t)H * W * Cp * 2};
-    cuuint32_t box[4] = {BLOCK_K, TILE_W, TILE_H, 1};
+    cuuint64_t strides[3] = {(cuuint64_t)ldp * 2, (cuuint64_t)W * ldp * 2, (cuuint64_t)H * W * ldp * 2};
+    cuuint32_t box[4] = {(cuuint32_t)bk, TILE_W, TILE_H, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int Ntile) {
+bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int Ntile, int bk) {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {BLOCK_K, (cuuint32_t)Ntile};
+    cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)Ntile};
     cuuint32_t es[2] = {1, 1};
     return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
@@ -781,8 +792,10 @@ extern "C" int rcn_tc_prof(unsigned long long* out16, int reset) {
     return cudaMemcpyFromSymbol(out16, g_tcprof, 16 * sizeof(unsigned long long)) == cudaSuccess ? RCN_OK : RCN_ERR_CUDA;
 }
 
+static inline bool cp_ok(int Cp) { return Cp == 16 || Cp == 32 || (Cp > 0 && Cp % 64 == 0); }
+
 extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && Cp % 64 == 0, "rcn_split_bf16: bad arguments");
+    RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && cp_ok(Cp), "rcn_split_bf16: bad arguments");
     const long long total = npix * (Cp / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
@@ -794,7 +807,7 @@ extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, in
 
 // stride-2 operand: the four polyphase planes (py,px) of x, each (N, H/2, W/2, Cp), stacked on the batch axis
 extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(x && hi && N > 0 && C > 0 && Cp >= C && Cp % 64 == 0, "rcn_split_bf16_s2: bad arguments");
+    RCN_CHECK_ARG(x && hi && N > 0 && C > 0 && Cp >= C && cp_ok(Cp), "rcn_split_bf16_s2: bad arguments");
     RCN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "rcn_split_bf16_s2: H and W must be even");
     const long long total = (long long)N * H * W * (Cp / 4);
     long long blocks = (total + 255) / 256;
@@ -806,7 +819,7 @@ extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, i
 }
 
 extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && Cp % 64 == 0, "rcn_pack_conv_weight_tc: bad arguments");
+    RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && cp_ok(Cp), "rcn_pack_conv_weight_tc: bad arguments");
     const long long total = (long long)Cout * k * k * Cp;
     long long blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
@@ -822,20 +835,23 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     if (d->y_hi) {
         const bool ps2 = d->store == RCN_STORE_PS2;
         const int cs = ps2 ? d->Cout / 4 : d->Cout;
-        RCN_CHECK_ARG((d->store == RCN_STORE_NHWC || ps2) && d->Cp_out == cs && (cs % 64) == 0 && (!ps2 || d->epi == RCN_EPI_NONE) &&
+        RCN_CHECK_ARG((d->store == RCN_STORE_NHWC || ps2) && d->Cp_out >= cs && (d->Cp_out % 8) == 0 && (cs % 4) == 0 && (!ps2 || d->epi == RCN_EPI_NONE) &&
                           (!d->y || ((d->ldy & 3) == 0 && (reinterpret_cast<uintptr_t>(d->y) & 15) == 0)) &&
                           (!d->res || ((d->ldres & 3) == 0 && (reinterpret_cast<uintptr_t>(d->res) & 15) == 0)) &&
                           (d->epi == RCN_EPI_NONE || ((d->ldaux & 3) == 0 && (reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)) &&
                           (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0),
-                      "rcn_conv2d_tc: operand-plane emission needs an NHWC / pixel-shuffle store with a multiple of 64 stored "
-                      "channels and 16-byte aligned tensors");
+                      "rcn_conv2d_tc: operand-plane emission needs an NHWC / pixel-shuffle store, a plane pixel stride Cp_out >= the "
+                      "stored channels (multiple of 8) and 16-byte aligned tensors");
     }
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
     RCN_CHECK_ARG(d->Cout <= BIAS_MAX, "rcn_conv2d_tc: Cout %d > %d unsupported", d->Cout, BIAS_MAX);
     RCN_CHECK_ARG(d->stride == 1 || d->stride == 2, "rcn_conv2d_tc: stride %d unsupported", d->stride);
     RCN_CHECK_ARG(d->stride == 1 || (d->H % 2 == 0 && d->W % 2 == 0), "rcn_conv2d_tc: stride 2 needs even H and W");
-    RCN_CHECK_ARG(Cp % 64 == 0 && Cp >= d->Cin, "rcn_conv2d_tc: Cp must be a multiple of 64 >= Cin");
+    RCN_CHECK_ARG(cp_ok(Cp) && Cp >= d->Cin, "rcn_conv2d_tc: Cp must be 16, 32 or a multiple of 64, and >= Cin");
+    const int ldp = d->ldp_in > 0 ? d->ldp_in : Cp;
+    RCN_CHECK_ARG(ldp >= Cp && ldp % 8 == 0 && (reinterpret_cast<uintptr_t>(x_hi) & 15) == 0 && (!x_lo || (reinterpret_cast<uintptr_t>(x_lo) & 15) == 0),
+                  "rcn_conv2d_tc: operand planes need a pixel stride >= Cp that is a multiple of 8 and 16-byte aligned bases");
     RCN_CHECK_ARG(d->epi == RCN_EPI_NONE || d->aux, "rcn_conv2d_tc: epilogue needs aux");
     RCN_CHECK_ARG(get_encode() != nullptr, "rcn_conv2d_tc: cuTensorMapEncodeTiled is not available from the driver");
     const bool ps = d->store == RCN_STORE_PS2 || d->store == RCN_STORE_PS2_NCHW;
@@ -850,9 +866,13 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.Ntile = nt;
     P.tiles_x = (P.d.W + TILE_W - 1) / TILE_W;
     P.tiles_y = (P.d.H + TILE_H - 1) / TILE_H;
-    const int stage_bytes = (passes == 3 ? 2 : 1) * (A_BYTES + nt * BLOCK_K * 2);
-    int stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 256) / stage_bytes;
-    if (stages > 8) stages = 8;
+    const int bk = Cp >= 64 ? 64 : Cp;
+    P.bk = bk;
+    P.a_bytes = 128 * bk * 2;                          // 16 / 8 / 4 KB
+    P.b_bytes = (nt * bk * 2 + 1023) & ~1023;
+    const int stage_bytes = (passes == 3 ? 2 : 1) * (P.a_bytes + P.b_bytes);
+    int stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 512) / stage_bytes;
+    if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
     P.stages = stages;
     {
@@ -861,12 +881,12 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         const char* st = getenv("RCN_TC_STAGES");
         if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
     }
-    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 256;
+    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 512;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const long long Ktot = (long long)d->k * d->k * Cp;
     const int planes = P.s2 ? 4 * d->N : d->N;
-    bool ok = make_act_map(&ma_hi, x_hi, planes, P.d.H, P.d.W, Cp) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt);
-    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt);
+    bool ok = make_act_map(&ma_hi, x_hi, planes, P.d.H, P.d.W, Cp, ldp, bk) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt, bk);
+    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp, ldp, bk) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt, bk);
     else { ma_lo = ma_hi; mw_lo = mw_hi; }
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
     // epilogue variant (mirrors the alignment rules of the 16-byte path)

@@ -94,6 +94,11 @@ def get_engine() -> str:
 
 
 # ----------------------------------------------------------------------------- weights
+def plane_channels(c: int) -> int:
+    """Channel count of the bf16 operand planes of a c-channel tensor: 16, 32 or a multiple of 64."""
+    return 16 if c <= 16 else (32 if c <= 32 else (c + 63) // 64 * 64)
+
+
 class PackedConv:
     __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo")
 
@@ -120,8 +125,8 @@ def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
     b = bias.detach().contiguous() if bias is not None else None
     pc = PackedConv(out, b, k, cin, cout)
     if k in (1, 3) and cin >= _TC_MIN_CIN:
-        # tcgen05 operand: [Cout][k*k][Cp] bf16 hi/lo, Cp = Cin rounded up to the 64-channel K chunk
-        cp = (cin + 63) // 64 * 64
+        # tcgen05 operand: [Cout][k*k][Cp] bf16 hi/lo, Cp = Cin rounded up to the K chunk (16 / 32 for the few-channel layers)
+        cp = plane_channels(cin)
         pc.cp = cp
         pc.w_hi = torch.empty((cout, k * k * cp), device=w.device, dtype=torch.bfloat16)
         pc.w_lo = torch.empty_like(pc.w_hi)
@@ -207,7 +212,7 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     if x is None and not use_tc:
         raise ValueError("conv2d: operand planes can only feed the tcgen05 engine")
     dev = x.device if x is not None else presplit.hi.device
-    can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and Cs % 64 == 0 and
+    can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and plane_channels(Cs) == Cs and
                 (store != STORE_PS2 or epi == EPI_NONE) and pc.cout % 16 == 0)
     want_out = keep_fp32 or not can_emit or out is not None
     if want_out and out is None:

@@ -190,14 +190,14 @@ class HybridConditionModule(nn.Module):
                                       nn.LeakyReLU(0.1, True), Conv2d(oc, oc, 3, 2, 1))
         self._m = m
 
-    def _f(self, x):
+    def _f(self, x, presplit=None):
         N, H, W, _ = x.shape
         m = self._m
         # skip tensors are produced straight into the first half of the decoder concat buffers
         cat3 = ops.empty(N, H, W, 2 * m, like=x)
         cat2 = ops.empty(N, H // 2, W // 2, 4 * m, like=x)
         cat1 = ops.empty(N, H // 4, W // 4, 8 * m, like=x)
-        x1 = self.in_conv._f(x, out=cat3[..., :m])
+        x1 = self.in_conv.conv._f(x, act=self.in_conv._act[0], slope=self.in_conv._act[1], out=cat3[..., :m], presplit=presplit)
         x2 = self.enc_1._f(x1, out=cat2[..., :2 * m])
         x3 = self.enc_2._f(x2, out=cat1[..., :4 * m])
         x4 = self.enc_3._f(x3)
@@ -205,9 +205,13 @@ class HybridConditionModule(nn.Module):
         y = self.dec_2._f(y, cat2)
         y = self.dec_3._f(y, cat3)
         y = self.out_conv._f(y)
-        c1 = self.CondNet1[2]._f(self.CondNet1[0]._f(y, act=ACT_LRELU, slope=0.1))
-        c2 = self.CondNet2[2]._f(self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1))
-        c3 = self.CondNet3[0]._f(y, act=ACT_LRELU, slope=0.1)
+        # the three CondNets read y through a stride-2 3x3 conv: one polyphase split serves all of them
+        heads = [self.CondNet1[0], self.CondNet2[0], self.CondNet3[0]]
+        sp = ops.shared_split(y, [ops.pack(h) for h in heads], stride=2)
+        t, tsp = self.CondNet1[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
+        c1 = self.CondNet1[2]._f(t, presplit=tsp)
+        c2 = self.CondNet2[2]._f(self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp))
+        c3 = self.CondNet3[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp)
         c3 = self.CondNet3[2]._f(c3, act=ACT_LRELU, slope=0.1)
         c3 = self.CondNet3[4]._f(c3)
         return [c1, c2, c3]
@@ -306,8 +310,9 @@ class raw_compression_tcm_final(SliceCodecModel):
         raw, cond, coord = ops.to_nhwc(x[0]), ops.to_nhwc(x[1]), ops.to_nhwc(x[2])
         vec = self.classifier._f(cond)                                  # (B,1,1,128) gfm_vector
         lsc_fea = self.lsc._f(coord)
-        local = self.local_condition._f(raw)
-        fea = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea)   # conv_first(x) * (lsc + 1)
+        rsp = ops.shared_split(raw, [ops.pack(self.conv_first), ops.pack(self.local_condition.in_conv.conv)])   # both read raw
+        local = self.local_condition._f(raw, presplit=rsp)
+        fea = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, presplit=rsp)   # conv_first(x) * (lsc + 1)
         fea = self.conv_down._f(fea)
         for lvl, (gfm, blocks, down) in enumerate(((self.gfm1, self.m_down1, self.m_down1_down),
                                                    (self.gfm2, self.m_down2, self.m_down2_down),
@@ -322,9 +327,14 @@ class raw_compression_tcm_final(SliceCodecModel):
     def _g_s(self, y_hat, clamp=False):
         h = y_hat
         mods = list(self.g_s)
-        for m in mods[:-1]:
+        for m in mods[:-3]:
             h = m._f(h)
-        return mods[-1]._f(h, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
+        # tail at full resolution (raw2bit.py:1680-1682): subpel -> ResidualBlock -> subpel.  The 128-channel maps are 2.1 GB
+        # each: the producers write the consumers' bf16 operand planes themselves, and the ResidualBlock output (read by the
+        # last conv only) never exists in fp32.
+        h, hsp = mods[-3]._f(h, emit_split=True, keep_fp32=True)
+        h, rsp = mods[-2]._f(h, presplit=hsp, emit_split=True, keep_fp32=False)    # h is None when only the planes exist
+        return mods[-1]._f(h, presplit=rsp, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
 
     # ------------------------------------------------------------------------------ public API
     @torch.no_grad()

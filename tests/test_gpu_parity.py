@@ -48,6 +48,9 @@ CONV_CASES = [
     (2, 17, 23, 4, 20, 3, 1), (1, 16, 16, 64, 64, 3, 2), (1, 9, 11, 48, 12, 3, 1), (2, 8, 8, 128, 320, 1, 1),
     (1, 33, 31, 16, 3, 3, 1), (1, 20, 20, 2, 48, 1, 1), (1, 12, 12, 320, 128, 3, 2), (3, 7, 5, 36, 130, 1, 2),
     (1, 40, 40, 128, 128, 3, 1),
+    # K chunks of 16 / 32 channels (32- / 64-byte swizzled operand rows): Cin <= 16 and <= 32, all strides and kernel sizes
+    (1, 24, 40, 16, 64, 3, 1), (2, 18, 22, 32, 16, 3, 1), (1, 16, 32, 20, 48, 1, 1), (1, 32, 16, 16, 32, 3, 2), (1, 16, 16, 32, 32, 3, 2),
+    (1, 26, 30, 9, 16, 1, 1),
 ]
 
 
