@@ -107,7 +107,9 @@ int rcn_pack_conv_weight(const float* w_oihw, int Cout, int Cin, int k, float* o
  * Agg_0 applies Hardswish right after its LayerNorm, models/groupmix.py:47-53).
  * models/tcm.py:223,227,233-234; models/groupmix.py:279,285,291,296. */
 int rcn_layernorm(const float* x, long long npix, int C, int ldx, const float* gamma, const float* beta,
-                  float eps, float* y, int ldy, int act, void* stream);
+                  float eps, float* y, int ldy, int act, void* y_hi, void* y_lo, int ldp, void* stream);
+/* y_hi / y_lo (optional, pixel stride ldp elements): also / only write the result as the next layer's bf16 operand planes
+ * (LayerNorm feeds embedding_layer / mlp[0], models/tcm.py:233-234); y may be NULL when y_hi is given. */
 
 /* Swin window attention core of WMSA.forward (models/tcm.py:179-207): cyclic shift, window
  * partition, per-head softmax(q k^T * hd^-0.5 + relative-position bias [+ shift mask]) v,
@@ -116,7 +118,8 @@ int rcn_layernorm(const float* x, long long npix, int C, int ldx, const float* g
  * (heads, 2ws-1, 2ws-1) relative_position_params tensor (models/tcm.py:155,209-212).
  * The mask of generate_mask (models/tcm.py:160-177) is computed from indices, never stored. */
 int rcn_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int head_dim, int ws, int shifted,
-             const float* relpos, float* out, int ldo, void* stream);
+             const float* relpos, float* out, int ldo, void* out_hi, void* out_lo, int ldp, void* stream);
+/* out_hi / out_lo (optional): operand planes of the attention output for WMSA.linear (models/tcm.py:206); out may be NULL. */
 
 /* ---- layout changes at the API boundary (reference tensors are NCHW) ------------------------ */
 int rcn_nchw_to_nhwc(const float* x, int N, int C, int H, int W, float* y, int ldy, void* stream);

@@ -40,8 +40,8 @@ PROTOTYPES = {
     "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
-    "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P]),
-    "rcn_wmsa": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
+    "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),
+    "rcn_wmsa": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),
     "rcn_nchw_to_nhwc": (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_nhwc_to_nchw": (_I, [_P, _I, _I, _I, _I, _I, _P, _P]),
     "rcn_copy_channels": (_I, [_P, _I, _L, _I, _P, _I, _P]),

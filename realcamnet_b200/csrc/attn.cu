@@ -1,4 +1,6 @@
 // LayerNorm over channels and Swin window attention (W-MSA / SW-MSA), NHWC fp32.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rcn {
@@ -8,7 +10,8 @@ namespace {
 template <int NIT>
 __global__ void layernorm_kernel(const float* __restrict__ x, long long npix, int C, int ldx,
                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                 float* __restrict__ y, int ldy, int act) {
+                                 float* __restrict__ y, int ldy, int act, __nv_bfloat16* __restrict__ y_hi,
+                                 __nv_bfloat16* __restrict__ y_lo, int ldp) {
     const int lane = threadIdx.x & 31;
     const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (pix >= npix) return;
@@ -33,11 +36,18 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long npix, in
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)C + eps);
-    float* yr = y + pix * ldy;
 #pragma unroll
     for (int i = 0; i < NIT; ++i) {
         const int c = lane + 32 * i;
-        if (c < C) yr[c] = act_apply((v[i] - mean) * rstd * gamma[c] + beta[c], act, 0.f);
+        if (c < C) {
+            const float r = act_apply((v[i] - mean) * rstd * gamma[c] + beta[c], act, 0.f);
+            if (y) y[pix * ldy + c] = r;
+            if (y_hi) {   // the consumer's tcgen05 operand planes (same rounding as rcn_split_bf16)
+                const __nv_bfloat16 h = __float2bfloat16_rn(r);
+                y_hi[pix * ldp + c] = h;
+                if (y_lo) y_lo[pix * ldp + c] = __float2bfloat16_rn(r - __bfloat162float(h));
+            }
+        }
     }
 }
 
@@ -45,7 +55,8 @@ __global__ void layernorm_kernel(const float* __restrict__ x, long long npix, in
 // K and V of the head are staged in shared memory (broadcast reads), scores live in registers.
 template <int WS, int HD>
 __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, int ldq, int shifted,
-                            const float* __restrict__ relpos, float* __restrict__ out, int ldo, int nheads) {
+                            const float* __restrict__ relpos, float* __restrict__ out, int ldo, int nheads,
+                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ldp) {
     constexpr int P = WS * WS;
     extern __shared__ float sm[];  // [HPB][2][P][HD]
     const int t = threadIdx.x;     // token in window
@@ -111,14 +122,31 @@ __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, 
 #pragma unroll
         for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, vs[j * HD + d], o[d]);
     }
-    float* op = out + ((long long)(n * H + gy) * W + gx) * ldo + head * HD;
+    const long long opix = (long long)(n * H + gy) * W + gx;
+    if (out) {
+        float* op = out + opix * ldo + head * HD;
 #pragma unroll
-    for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+        for (int d = 0; d < HD; d += 4) *reinterpret_cast<float4*>(op + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+    }
+    if (out_hi) {   // the projection layer's tcgen05 operand planes
+#pragma unroll
+        for (int d = 0; d < HD; d += 4) {
+            __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                hb[e] = __float2bfloat16_rn(o[d + e]);
+                lb[e] = __float2bfloat16_rn(o[d + e] - __bfloat162float(hb[e]));
+            }
+            const long long po = opix * ldp + head * HD + d;
+            *reinterpret_cast<uint2*>(out_hi + po) = *reinterpret_cast<uint2*>(hb);
+            if (out_lo) *reinterpret_cast<uint2*>(out_lo + po) = *reinterpret_cast<uint2*>(lb);
+        }
+    }
 }
 
 template <int WS, int HD>
 int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shifted, const float* relpos,
-                float* out, int ldo, cudaStream_t s) {
+                float* out, int ldo, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldp, cudaStream_t s) {
     constexpr int P = WS * WS;
     const int nheads = C / HD;
     int hpb = 256 / P;
@@ -129,7 +157,7 @@ int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shift
     const size_t smem = (size_t)hpb * 2 * P * HD * sizeof(float);
     auto kern = wmsa_kernel<WS, HD>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, block, smem, s>>>(qkv, H, W, C, ldq, shifted, relpos, out, ldo, nheads);
+    kern<<<grid, block, smem, s>>>(qkv, H, W, C, ldq, shifted, relpos, out, ldo, nheads, out_hi, out_lo, ldp);
     return 0;
 }
 
@@ -137,38 +165,45 @@ int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shift
 }  // namespace rcn
 
 extern "C" int rcn_layernorm(const float* x, long long npix, int C, int ldx, const float* gamma, const float* beta,
-                             float eps, float* y, int ldy, int act, void* stream) {
+                             float eps, float* y, int ldy, int act, void* y_hi_, void* y_lo_, int ldp, void* stream) {
     using namespace rcn;
-    RCN_CHECK_ARG(x && y && gamma && beta && npix > 0, "rcn_layernorm: bad arguments");
+    __nv_bfloat16* y_hi = (__nv_bfloat16*)y_hi_;
+    __nv_bfloat16* y_lo = (__nv_bfloat16*)y_lo_;
+    RCN_CHECK_ARG(x && (y || y_hi) && gamma && beta && npix > 0, "rcn_layernorm: bad arguments");
+    RCN_CHECK_ARG(!y_hi || ldp >= C, "rcn_layernorm: plane pixel stride %d < C", ldp);
     RCN_CHECK_ARG(C > 0 && C <= 1024, "rcn_layernorm: C=%d unsupported (1..1024)", C);
     const int wpb = 8;
     cudaStream_t s = (cudaStream_t)stream;
     const int grid = cdiv(npix, wpb);
-    if (C <= 32) layernorm_kernel<1><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
-    else if (C <= 64) layernorm_kernel<2><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
-    else if (C <= 128) layernorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
-    else if (C <= 256) layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
-    else layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act);
+    if (C <= 32) layernorm_kernel<1><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
+    else if (C <= 64) layernorm_kernel<2><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
+    else if (C <= 128) layernorm_kernel<4><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
+    else if (C <= 256) layernorm_kernel<8><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
+    else layernorm_kernel<32><<<grid, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_layernorm");
     return RCN_OK;
 }
 
 extern "C" int rcn_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int head_dim, int ws, int shifted,
-                        const float* relpos, float* out, int ldo, void* stream) {
+                        const float* relpos, float* out, int ldo, void* out_hi_, void* out_lo_, int ldp, void* stream) {
     using namespace rcn;
-    RCN_CHECK_ARG(qkv && relpos && out, "rcn_wmsa: null pointer");
+    __nv_bfloat16* out_hi = (__nv_bfloat16*)out_hi_;
+    __nv_bfloat16* out_lo = (__nv_bfloat16*)out_lo_;
+    RCN_CHECK_ARG(qkv && relpos && (out || out_hi), "rcn_wmsa: null pointer");
+    RCN_CHECK_ARG(!out_hi || (ldp >= C && ldp % 4 == 0 && ((uintptr_t)out_hi & 7) == 0 && ((uintptr_t)out_lo & 7) == 0),
+                  "rcn_wmsa: operand planes need a pixel stride >= C (multiple of 4) and 8-byte aligned bases");
     RCN_CHECK_ARG(H % ws == 0 && W % ws == 0, "rcn_wmsa: map %dx%d not divisible by window %d", H, W, ws);
     RCN_CHECK_ARG(C % head_dim == 0 && ldq % 4 == 0 && ldo % 4 == 0, "rcn_wmsa: bad channel layout");
     RCN_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "rcn_wmsa: pointers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     int rc = -1;
-    if (ws == 8 && head_dim == 8) rc = launch_wmsa<8, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
-    else if (ws == 8 && head_dim == 16) rc = launch_wmsa<8, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
-    else if (ws == 8 && head_dim == 32) rc = launch_wmsa<8, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
-    else if (ws == 4 && head_dim == 32) rc = launch_wmsa<4, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
-    else if (ws == 4 && head_dim == 16) rc = launch_wmsa<4, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
-    else if (ws == 4 && head_dim == 8) rc = launch_wmsa<4, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, s);
+    if (ws == 8 && head_dim == 8) rc = launch_wmsa<8, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 8 && head_dim == 16) rc = launch_wmsa<8, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 8 && head_dim == 32) rc = launch_wmsa<8, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 4 && head_dim == 32) rc = launch_wmsa<4, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 4 && head_dim == 16) rc = launch_wmsa<4, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 4 && head_dim == 8) rc = launch_wmsa<4, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
     if (rc != 0) {
         set_error("rcn_wmsa: (window %d, head_dim %d) unsupported", ws, head_dim);
         return RCN_ERR_UNSUPPORTED;

@@ -169,7 +169,7 @@ class ResidualBlock(_Block):
         self.conv2 = conv3x3(out_ch, out_ch)
         self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
 
-    def _f(self, x, out=None, extra_identity=False, presplit=None, emit_split=False, keep_fp32=True):
+    def _f(self, x, out=None, extra_identity=False, presplit=None, emit_split=False, keep_fp32=True, split_out=None):
         """extra_identity: also add x once more (ConvTransBlock's ``conv_block(x) + x``).
         presplit / emit_split / keep_fp32: operand planes of x from its producer / planes of the result for its consumer."""
         t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, emit_split=True, keep_fp32=False, presplit=presplit)
@@ -177,7 +177,7 @@ class ResidualBlock(_Block):
         if extra_identity and self.skip is not None:
             raise ValueError("extra_identity needs in_ch == out_ch")
         return self.conv2._f(t, act=ACT_LRELU, slope=0.01, res=identity, res_scale=2.0 if extra_identity else 1.0, out=out,
-                             presplit=tsp, emit_split=emit_split, keep_fp32=keep_fp32)
+                             presplit=tsp, emit_split=emit_split, keep_fp32=keep_fp32, split_out=split_out)
 
 
 class AttentionBlock(_Block):

@@ -149,11 +149,54 @@ def pack(module) -> PackedConv:
 
 # ----------------------------------------------------------------------------- conv / linear
 class SplitOperand:
-    """bf16 hi/lo planes of one activation tensor for the tcgen05 engine (shareable between the convs that read it)."""
+    """bf16 hi/lo planes of one activation tensor for the tcgen05 engine (shareable between the convs that read it).
+    hi / lo are (N,H,W,Cp) bf16 tensors, possibly channel-slice views of a wider plane buffer (pixel stride = ld)."""
     __slots__ = ("hi", "lo", "key")
 
     def __init__(self, hi, lo, key):
         self.hi, self.lo, self.key = hi, lo, key
+
+    @property
+    def ld(self):
+        return plane_ld(self.hi)
+
+    def channels(self, c0, c1):
+        """Planes of the channel slice [c0, c1) -- what torch.split / torch.cat views are for the fp32 tensors."""
+        if self.key[7] != 1 or self.key[8]:
+            raise ValueError("only stride-1 operand planes can be sliced")
+        cp = plane_channels(c1 - c0)
+        if cp != c1 - c0:
+            raise ValueError(f"a {c1 - c0}-channel slice is not a valid plane width")
+        k = self.key
+        return SplitOperand(self.hi[..., c0:c1], None if self.lo is None else self.lo[..., c0:c1],
+                            (None, k[1], k[2], k[3], c1 - c0, None, cp, 1, False))
+
+
+def plane_ld(t):
+    """pixel stride (elements) of an (N,H,W,Cp) plane tensor / channel-slice view"""
+    N, H, W, C = t.shape
+    if C > 1 and t.stride(3) != 1:
+        raise ValueError("operand planes: channel dim must be contiguous")
+    ld = t.stride(2) if W > 1 else (t.stride(1) if H > 1 else (t.stride(0) if N > 1 else C))
+    if (H > 1 and t.stride(1) != W * ld) or (N > 1 and t.stride(0) != H * W * ld) or ld < C:
+        raise ValueError("operand planes: not an NHWC tensor or channel slice")
+    return ld
+
+
+def alloc_planes(N, H, W, C, device, passes=None) -> SplitOperand:
+    """Uninitialised stride-1 operand planes of an (N,H,W,C) tensor for producers to write (conv2d(split_out=...),
+    layernorm / wmsa emit); C must be a valid plane width."""
+    if plane_channels(C) != C:
+        raise ValueError(f"{C} channels is not a valid plane width")
+    if passes is None:
+        passes = 3 if _ENGINE == "bf16x3" else 1
+    hi = torch.empty((N, H, W, C), device=device, dtype=torch.bfloat16)
+    lo = torch.empty_like(hi) if passes == 3 else None
+    return SplitOperand(hi, lo, (None, N, H, W, C, None, C, 1, False))
+
+
+def planes_enabled() -> bool:
+    return _ENGINE != "fp32"
 
 
 def split_operand(x, cp, stride=1, in_square=False, passes=None) -> SplitOperand:
@@ -187,12 +230,15 @@ def shared_split(x, pcs, stride=1):
 
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
            cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None,
-           emit_split=False, keep_fp32=True):
+           emit_split=False, keep_fp32=True, split_out=None):
     """One conv / linear layer with its fused epilogue.
 
     x may be None when `presplit` carries operand planes that a previous tcgen05 conv emitted (conv->conv chains never
     materialise the fp32 intermediate).  emit_split=True returns (out, SplitOperand | None): the epilogue additionally
-    writes the NEXT layer's bf16 hi/lo planes; with keep_fp32=False `out` is None when that was possible."""
+    writes the NEXT layer's bf16 hi/lo planes; with keep_fp32=False `out` is None when that was possible.
+    split_out: planes allocated by the caller (e.g. one half of a concat's planes) to emit into; implies emit_split."""
+    if split_out is not None:
+        emit_split = True
     eng = engine or _ENGINE
     if x is None:
         if presplit is None or presplit.key[7] != 1:
@@ -214,6 +260,8 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     dev = x.device if x is not None else presplit.hi.device
     can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and plane_channels(Cs) == Cs and
                 (store != STORE_PS2 or epi == EPI_NONE) and pc.cout % 16 == 0)
+    if split_out is not None and not can_emit:
+        raise ValueError("conv2d: split_out given but this layer cannot emit operand planes")
     want_out = keep_fp32 or not can_emit or out is not None
     if want_out and out is None:
         if store in (STORE_NCHW, STORE_PS2_NCHW):
@@ -257,11 +305,10 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
         ok = (ldy % 4 == 0 and (out is None or out.data_ptr() % 16 == 0) and lda % 4 == 0 and ldr % 4 == 0 and
               (aux is None or aux.data_ptr() % 16 == 0) and (res is None or res.data_ptr() % 16 == 0))
         if ok:
-            passes_out = 3 if _ENGINE == "bf16x3" else 1
-            y_hi = torch.empty((N, Hs, Ws, Cs), device=dev, dtype=torch.bfloat16)
-            y_lo = torch.empty_like(y_hi) if passes_out == 3 else None
-            d.y_hi, d.y_lo, d.Cp_out = y_hi.data_ptr(), (y_lo.data_ptr() if y_lo is not None else None), Cs
-            sp_out = SplitOperand(y_hi, y_lo, (None, N, Hs, Ws, Cs, None, Cs, 1, False))
+            sp_out = split_out if split_out is not None else alloc_planes(N, Hs, Ws, Cs, dev)
+            if tuple(sp_out.hi.shape) != (N, Hs, Ws, Cs) or sp_out.key[7] != 1:
+                raise ValueError("conv2d: split_out planes do not have the stored output geometry")
+            d.y_hi, d.y_lo, d.Cp_out = sp_out.hi.data_ptr(), (sp_out.lo.data_ptr() if sp_out.lo is not None else None), sp_out.ld
         elif out is None:
             raise ValueError("conv2d: cannot drop the fp32 output of a layer whose epilogue is not 16-byte aligned")
     if use_tc:
@@ -273,6 +320,7 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
                 (k0[0] is None or (x is not None and k0[0] == x.data_ptr() and k0[5] == ldx)))
         if not same or (passes == 3 and sp.lo is None):
             raise ValueError("conv2d: presplit operand does not belong to this input / layer geometry")
+        d.ldp_in = sp.ld
         _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
                                         _stream()), "rcn_conv2d_tc")
     else:
@@ -280,27 +328,41 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     return (out, sp_out) if emit_split else out
 
 
-def layernorm(x, weight, bias, eps=1e-5, out=None, act=ACT_NONE):
+def layernorm(x, weight, bias, eps=1e-5, out=None, act=ACT_NONE, emit_split=False):
+    """emit_split=True: returns (None, SplitOperand) -- the result only exists as the consumer conv's operand planes -- when the
+    tcgen05 engine is active and C is a valid plane width; (out, None) otherwise."""
     N, H, W, C, ldx = geom(x, "layernorm.x")
+    sp = None
+    if emit_split and planes_enabled() and plane_channels(C) == C and out is None:
+        sp = alloc_planes(N, H, W, C, x.device)
+        _C.check(_C.lib().rcn_layernorm(_ptr(x), N * H * W, C, ldx, _ptr(weight), _ptr(bias), eps, _vp(0), 0, act,
+                                        _ptr(sp.hi), _ptr(sp.lo), sp.ld, _stream()), "rcn_layernorm")
+        return None, sp
     if out is None:
         out = empty(N, H, W, C, like=x)
     _, _, _, _, ldy = geom(out, "layernorm.out")
     _C.check(_C.lib().rcn_layernorm(_ptr(x), N * H * W, C, ldx, _ptr(weight), _ptr(bias), eps, _ptr(out), ldy, act,
-                                    _stream()), "rcn_layernorm")
-    return out
+                                    _vp(0), _vp(0), 0, _stream()), "rcn_layernorm")
+    return (out, None) if emit_split else out
 
 
-def wmsa(qkv, relpos, head_dim, ws, shifted, out=None):
+def wmsa(qkv, relpos, head_dim, ws, shifted, out=None, emit_split=False):
+    """emit_split=True: (None, SplitOperand) when the attention output can be handed to the projection layer as planes."""
     N, H, W, C3, ldq = geom(qkv, "wmsa.qkv")
     C = C3 // 3
+    _chk(relpos)
+    assert relpos.is_contiguous() and tuple(relpos.shape) == (C // head_dim, 2 * ws - 1, 2 * ws - 1)
+    if emit_split and planes_enabled() and plane_channels(C) == C and out is None:
+        sp = alloc_planes(N, H, W, C, qkv.device)
+        _C.check(_C.lib().rcn_wmsa(_ptr(qkv), N, H, W, C, ldq, head_dim, ws, int(shifted), _ptr(relpos), _vp(0), 0,
+                                   _ptr(sp.hi), _ptr(sp.lo), sp.ld, _stream()), "rcn_wmsa")
+        return None, sp
     if out is None:
         out = empty(N, H, W, C, like=qkv)
     _, _, _, _, ldo = geom(out, "wmsa.out")
-    _chk(relpos)
-    assert relpos.is_contiguous() and tuple(relpos.shape) == (C // head_dim, 2 * ws - 1, 2 * ws - 1)
     _C.check(_C.lib().rcn_wmsa(_ptr(qkv), N, H, W, C, ldq, head_dim, ws, int(shifted), _ptr(relpos), _ptr(out), ldo,
-                               _stream()), "rcn_wmsa")
-    return out
+                               _vp(0), _vp(0), 0, _stream()), "rcn_wmsa")
+    return (out, None) if emit_split else out
 
 
 # ----------------------------------------------------------------------------- layout

@@ -55,9 +55,10 @@ class ResidualBlockWithCA(nn.Module):
         self.ca = CALayer(out_ch, redution)
         self.skip = conv1x1(in_ch, out_ch) if in_ch != out_ch else None
 
-    def _f(self, x, out=None):
-        t = self.conv2._f(self.conv1._f(x, act=ACT_LRELU, slope=0.01))
-        identity = x if self.skip is None else self.skip._f(x)
+    def _f(self, x, out=None, presplit=None):
+        t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=presplit, emit_split=True, keep_fp32=False)
+        t = self.conv2._f(t, presplit=tsp)
+        identity = x if self.skip is None else self.skip._f(x, presplit=presplit)
         return self.ca._f(t, res=identity, out=out)
 
     def forward(self, x):
@@ -76,15 +77,20 @@ class SpatialFeatureTransform(nn.Module):
                                         Conv2d(n_features, n_features, 3, stride=1, padding=1))
         self.residual = residual
 
-    def _f(self, x, cond, extra=None, out=None):
-        """x*scale + shift + x (+ extra); both element-wise steps are conv epilogues."""
+    def _f(self, x, cond, extra=None, out=None, cond_split=None, split_out=None, keep_fp32=True):
+        """x*scale + shift + x (+ extra); both element-wise steps are conv epilogues.
+        cond_split: operand planes of cond (shared by every block of a level); split_out / keep_fp32: write the result as
+        (also / only) the operand planes of the layer that reads it."""
         if not self.residual:
             raise NotImplementedError("residual=False is never used by the reference")
-        sp = ops.shared_split(cond, [ops.pack(self.cond_scale[0]), ops.pack(self.cond_shift[0])])
+        sp = cond_split if cond_split is not None else \
+            ops.shared_split(cond, [ops.pack(self.cond_scale[0]), ops.pack(self.cond_shift[0])])
         s, ssp = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
         t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra, presplit=ssp)      # (scale + 1) * x (+ extra)
         h, hsp = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
-        return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp)                        # shift + ...
+        if split_out is None:
+            return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp)                    # shift + ...
+        return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp, split_out=split_out, keep_fp32=keep_fp32)[0]
 
     def forward(self, x, cond):
         return ops.to_nchw(self._f(ops.to_nhwc(x), ops.to_nhwc(cond)))
@@ -106,15 +112,27 @@ class ConvTransBlock_mzj(nn.Module):
         self.conv_block = ResidualBlockWithCA(conv_dim, conv_dim, 8)
         self.spatial_transform = SpatialFeatureTransform(cond_channels=conv_dim, n_features=conv_dim)
 
-    def _f(self, x, cond, out=None):
-        cd = self.conv_dim
-        both = self.conv1_1._f(x)
-        cat = torch.empty_like(both)
+    def _f(self, x, cond, out=None, cond_split=None):
+        cd, td = self.conv_dim, self.trans_dim
+        planes = ops.planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
+            ops.plane_channels(cd + td) == cd + td
+        if not planes:
+            both = self.conv1_1._f(x)
+            cat = torch.empty_like(both)
+            conv_identity = both[..., :cd]
+            cx = self.conv_block._f(conv_identity)
+            self.spatial_transform._f(cx, cond, extra=conv_identity, out=cat[..., :cd], cond_split=cond_split)
+            self.trans_block._f(both[..., cd:], out=cat[..., cd:])
+            return self.conv1_2._f(cat, res=x, out=out)
+        # tcgen05 engine: see ConvTransBlock._f -- the concat read by conv1_2 only exists as operand planes
+        both, bsp = self.conv1_1._f(x, emit_split=True)
+        N, H, W, _ = both.shape
+        csp = ops.alloc_planes(N, H, W, cd + td, both.device)
         conv_identity = both[..., :cd]
-        cx = self.conv_block._f(conv_identity)
-        self.spatial_transform._f(cx, cond, extra=conv_identity, out=cat[..., :cd])
-        self.trans_block._f(both[..., cd:], out=cat[..., cd:])
-        return self.conv1_2._f(cat, res=x, out=out)
+        cx = self.conv_block._f(conv_identity, presplit=bsp.channels(0, cd))
+        self.spatial_transform._f(cx, cond, extra=conv_identity, cond_split=cond_split, split_out=csp.channels(0, cd), keep_fp32=False)
+        self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
+        return self.conv1_2._f(None, res=x, out=out, presplit=csp)
 
     def forward(self, xx):
         x, cond = xx[0], xx[1]
@@ -319,8 +337,10 @@ class raw_compression_tcm_final(SliceCodecModel):
                                                    (self.gfm3, self.m_down3, self.m_down3_down))):
             for g in gfm:
                 fea = g._f(fea, vec)
+            csp = ops.shared_split(local[lvl], [ops.pack(blocks[0].spatial_transform.cond_scale[0]),
+                                                ops.pack(blocks[0].spatial_transform.cond_shift[0])])   # cond planes: once per level
             for blk in blocks:
-                fea = blk._f(fea, local[lvl])
+                fea = blk._f(fea, local[lvl], cond_split=csp)
             fea = down._f(fea)
         return fea, lsc_fea, local
 

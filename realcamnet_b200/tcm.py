@@ -51,13 +51,14 @@ class WMSA(nn.Module):
             p.view(2 * window_size - 1, 2 * window_size - 1, self.n_heads).transpose(1, 2).transpose(0, 1).contiguous())
         self.linear = Linear(input_dim, output_dim)
 
-    def _f(self, x, res=None, out=None):
-        qkv = self.embedding_layer._f(x)
+    def _f(self, x, res=None, out=None, presplit=None):
+        """x may be None when `presplit` carries its operand planes (LayerNorm output)."""
+        qkv = self.embedding_layer._f(x, presplit=presplit)
         rel = self.relative_position_params
         if not rel.is_contiguous():
             rel = rel.contiguous()
-        o = ops.wmsa(qkv, rel.detach(), self.head_dim, self.window_size, self.type != 'W')
-        return self.linear._f(o, res=res, out=out)
+        o, osp = ops.wmsa(qkv, rel.detach(), self.head_dim, self.window_size, self.type != 'W', emit_split=True)
+        return self.linear._f(o, res=res, out=out, presplit=osp)
 
     def forward(self, x):
         return self._f(x.contiguous())
@@ -78,12 +79,16 @@ class Block(nn.Module):
         self.ln2 = nn.LayerNorm(input_dim)
         self.mlp = nn.Sequential(Linear(input_dim, 4 * input_dim), nn.GELU(), Linear(4 * input_dim, output_dim))
 
-    def _f(self, x, out=None):
-        t = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps)
-        x1 = self.msa._f(t, res=x)
-        t = ops.layernorm(x1, self.ln2.weight, self.ln2.bias, self.ln2.eps)
-        h, hsp = self.mlp[0]._f(t, act=ACT_GELU, emit_split=True, keep_fp32=False)   # 4C-wide hidden: planes only
-        return self.mlp[2]._f(h, res=x1, out=out, presplit=hsp)
+    def _f(self, x, out=None, split_out=None, keep_fp32=True):
+        """LayerNorm and attention outputs only exist as the next contraction's bf16 operand planes (tcgen05 engine).
+        split_out / keep_fp32: also / only write the block output as planes for the layer that reads it."""
+        t, tsp = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps, emit_split=True)
+        x1 = self.msa._f(t, res=x, presplit=tsp)
+        t, tsp = ops.layernorm(x1, self.ln2.weight, self.ln2.bias, self.ln2.eps, emit_split=True)
+        h, hsp = self.mlp[0]._f(t, act=ACT_GELU, emit_split=True, keep_fp32=False, presplit=tsp)   # 4C-wide hidden: planes only
+        if split_out is None:
+            return self.mlp[2]._f(h, res=x1, out=out, presplit=hsp)
+        return self.mlp[2]._f(h, res=x1, out=out, presplit=hsp, split_out=split_out, keep_fp32=keep_fp32)[0]
 
     def forward(self, x):
         return self._f(x.contiguous())
@@ -102,13 +107,25 @@ class ConvTransBlock(nn.Module):
         self.conv1_2 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
         self.conv_block = ResidualBlock(conv_dim, conv_dim)
 
-    def _f(self, x, out=None):
-        cd = self.conv_dim
-        both = self.conv1_1._f(x)                      # torch.split -> channel views
-        cat = torch.empty_like(both)
-        self.conv_block._f(both[..., :cd], out=cat[..., :cd], extra_identity=True)
-        self.trans_block._f(both[..., cd:], out=cat[..., cd:])
-        return self.conv1_2._f(cat, res=x, out=out)     # x + conv1_2(cat(conv_x, trans_x))
+    def _f(self, x, out=None, presplit=None):
+        cd, td = self.conv_dim, self.trans_dim
+        planes = ops.planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
+            ops.plane_channels(cd + td) == cd + td
+        if not planes:
+            both = self.conv1_1._f(x, presplit=presplit)   # torch.split -> channel views
+            cat = torch.empty_like(both)
+            self.conv_block._f(both[..., :cd], out=cat[..., :cd], extra_identity=True)
+            self.trans_block._f(both[..., cd:], out=cat[..., cd:])
+            return self.conv1_2._f(cat, res=x, out=out)     # x + conv1_2(cat(conv_x, trans_x))
+        # tcgen05 engine: conv1_1 also emits the planes its conv half is read through, and the concat that conv1_2 reads only
+        # exists as operand planes written half by half by the two branches (no fp32 cat, no split passes)
+        both, bsp = self.conv1_1._f(x, presplit=presplit, emit_split=True)
+        N, H, W, _ = both.shape
+        csp = ops.alloc_planes(N, H, W, cd + td, both.device)
+        self.conv_block._f(both[..., :cd], extra_identity=True, presplit=bsp.channels(0, cd), split_out=csp.channels(0, cd),
+                           keep_fp32=False)
+        self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
+        return self.conv1_2._f(None, res=x, out=out, presplit=csp)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
