@@ -95,6 +95,8 @@ typedef struct rcn_conv_desc {
     void* y_hi; void* y_lo; int Cp_out;   /* Cp_out = pixel stride of the emitted planes (>= stored channels: a channel slice of a
                                            * wider plane buffer, e.g. one half of a concat the next layer reads) */
     int ldp_in;          /* rcn_conv2d_tc: pixel stride of the INPUT planes x_hi/x_lo in elements (0 = Cp, dense planes) */
+    int ps_perm;         /* rcn_conv2d_tc with RCN_STORE_PS2: w_hi/w_lo were packed with ps_perm = 1 (rows grouped by sub-pixel),
+                          * which lets the pixel-shuffle store write 64 contiguous bytes per pixel like the NHWC store */
 } rcn_conv_desc;
 
 int rcn_conv2d(const rcn_conv_desc* d, void* stream);
@@ -232,8 +234,9 @@ int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int s
 /* stride-2 layers: the four polyphase planes x[:, py::2, px::2, :] as (4N, H/2, W/2, Cp) bf16 hi/lo, plane index
  * (py*2+px)*N + n -- each filter tap of a stride-2 conv then reads ONE plane at unit stride (TMA box per tap). */
 int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream);
-/* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand) */
-int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream);
+/* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand).  ps_perm != 0 (Cout % 64 == 0): row
+ * 64g + 16s + c holds conv channel 64g + 4c + s, i.e. the four PixelShuffle(2) sub-pixels s of 16 shuffled channels c. */
+int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, void* hi, void* lo, void* stream);
 
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */

@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
         ("cscale", c_void_p), ("cshift", c_void_p),
         ("res", c_void_p), ("ldres", c_int), ("res_pre", c_int),
         ("act", c_int), ("slope", c_float), ("res_scale", c_float),
-        ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int),
+        ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int), ("ps_perm", c_int),
     ]
 
 
@@ -37,7 +37,7 @@ PROTOTYPES = {
     "rcn_conv2d_tc": (_I, [POINTER(ConvDesc), _P, _P, _P, _P, _I, _I, _P]),
     "rcn_split_bf16": (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
     "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _P, _P, _P]),
+    "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),

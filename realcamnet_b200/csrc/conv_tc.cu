@@ -238,8 +238,9 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
 // the 4 float4s of one pixel's 16 columns and every global access of the warp covers 8 pixels x 64 contiguous bytes:
 //   item `it` of a lane = pixel (y0 + 2q + (it >> 1), x0 + (lane >> 2) + 8 (it & 1)), float4 `lane & 3` of the slab row.
 //   NHWC store : slab row = 16 consecutive channels; float4 c = channels cb + 16hh + 4c ..+3 of that pixel.
-//   pixel shuffle: slab row = [sub-pixel 0: 4 shuffled channels | sub 1 | sub 2 | sub 3]; float4 c = shuffled channels
-//                (cb + 16hh)/4 ..+3 of OUTPUT pixel (2y + (c >> 1), 2x + (c & 1)).
+//   pixel shuffle (weights packed with ps_perm: accumulator column 64g + 16s + c holds conv channel 64g + 4c + s): quarter hh is
+//                sub-pixel s = hh, i.e. OUTPUT pixel (2y + (hh >> 1), 2x + (hh & 1)), and its slab row = 16 consecutive shuffled
+//                channels cb/4 ..+15 of that pixel -- the same 64-byte-contiguous store pattern as the NHWC case.
 // The residual (or aux) operand of all 16 items is requested BEFORE the wait on the accumulator barrier, so its HBM latency
 // hides behind the MMAs of this tile; the TMEM load of quarter hh+1 is in flight while quarter hh is finished.
 template <int ACT, int EPI>
@@ -254,16 +255,18 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
     for (int it = 0; it < 4; ++it) okp[it] = (hy + (it >> 1) < r.H) && (wx + 8 * (it & 1) < r.W);
     // stored-tensor geometry of the lane's items
     long long pix0;
-    int sx, sy, chb, chs;      // pixel steps for x + 8 / y + 1; first stored channel of quarter 0 and its step per quarter
+    int sx, sy, chb, chs, Wst;      // pixel steps for x + 8 / y + 1; first stored channel of quarter 0 and its step per quarter
     if (!ps) {
         pix0 = ((long long)n * r.H + hy) * r.W + wx;
-        sx = 8; sy = r.W; chb = cb + 4 * chunk; chs = 16;
+        sx = 8; sy = r.W; chb = cb + 4 * chunk; chs = 16; Wst = 0;
     } else {
-        const int Ws = 2 * r.W;
-        pix0 = ((long long)n * 2 * r.H + 2 * hy + (chunk >> 1)) * Ws + 2 * wx + (chunk & 1);
-        sx = 16; sy = 2 * Ws; chb = cb >> 2; chs = 4;
+        Wst = 2 * r.W;
+        pix0 = ((long long)n * 2 * r.H + 2 * hy) * Wst + 2 * wx;
+        sx = 16; sy = 2 * Wst; chb = (cb >> 2) + 4 * chunk; chs = 0;
     }
-    const int lane_cols = ps ? 0 : 4 * chunk;   // columns of a quarter that must exist for this lane's float4 to be valid
+    const int lane_cols = 4 * chunk;   // columns of a quarter that must exist for this lane's float4 to be valid
+    // stored pixel of quarter hh relative to ip[it]: pixel shuffle -> sub-pixel (hh >> 1, hh & 1)
+#define RCN_QOFF(hh) (ps ? (long long)((hh) >> 1) * Wst + ((hh) & 1) : 0ll)
     long long ip[4];
 #pragma unroll
     for (int it = 0; it < 4; ++it) ip[it] = pix0 + (it & 1) * sx + (long long)(it >> 1) * sy;
@@ -278,7 +281,8 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             pre[hh][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pre_ptr && (16 * hh + lane_cols < wcols) && okp[it]) pre[hh][it] = ldg4(pre_ptr + ip[it] * pre_ld + chb + chs * hh);
+            if (pre_ptr && (16 * hh + lane_cols < wcols) && okp[it])
+                pre[hh][it] = ldg4(pre_ptr + (ip[it] + RCN_QOFF(hh)) * pre_ld + chb + chs * hh);
         }
     }
     const bool prof = (r.flags & EF_PROF) && blockIdx.x == 0 && threadIdx.x == 64;
@@ -298,7 +302,8 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
         const bool ah = 16 * hh + lane_cols < wcols;
         const int ch = chb + chs * hh;
         // per-channel parameters of this lane's 4 elements (conv channel index of element e: c0 + ce * e)
-        const int c0 = ps ? (cb + 16 * hh + chunk) : ch, ce = ps ? 4 : 1;
+        const int c0 = ps ? (cb + 16 * chunk + hh) : ch, ce = ps ? 4 : 1;
+        const long long qoff = RCN_QOFF(hh);
         float bi[4] = {0.f, 0.f, 0.f, 0.f}, cs[4] = {1.f, 1.f, 1.f, 1.f}, csh[4] = {0.f, 0.f, 0.f, 0.f};
         if (ah) {
             if (sbias) {
@@ -318,16 +323,14 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             sec[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (has_aux && has_res && ah && okp[it]) sec[it] = ldg4(r.aux + ip[it] * r.ldaux + ch);
+            if (has_aux && has_res && ah && okp[it]) sec[it] = ldg4(r.aux + (ip[it] + qoff) * r.ldaux + ch);
         }
         // ---- transpose: row `lane` <- the 16 accumulator columns of this quarter
         tmem_wait_ld16(v);
         const uint32_t wrow = slab + (uint32_t)lane * 64u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            float4 t;
-            if (!ps) t = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
-            else t = make_float4(__uint_as_float(v[k]), __uint_as_float(v[4 + k]), __uint_as_float(v[8 + k]), __uint_as_float(v[12 + k]));
+            const float4 t = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
             sts4(wrow + 16u * (uint32_t)(k ^ wsw), t);
         }
         if (16 * (hh + 1) < wcols) tmem_ld16_async(taddr + 16 * (hh + 1), v);   // next quarter in flight
@@ -355,7 +358,7 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                 val[e] = fmaf(r.rpost, rv[e], val[e]);
             }
             if (r.flags & EF_NOSTORE) continue;
-            if (r.flags & EF_Y) *reinterpret_cast<float4*>(r.y + ip[it] * r.ldy + ch) = make_float4(val[0], val[1], val[2], val[3]);
+            if (r.flags & EF_Y) *reinterpret_cast<float4*>(r.y + (ip[it] + qoff) * r.ldy + ch) = make_float4(val[0], val[1], val[2], val[3]);
             if (r.flags & EF_HI) {
                 // the consumer's tcgen05 operand planes: x = hi + lo in bf16 (same rounding as rcn_split_bf16)
                 __nv_bfloat16 hb[4], lb[4];
@@ -364,13 +367,14 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                     hb[e] = __float2bfloat16_rn(val[e]);
                     lb[e] = __float2bfloat16_rn(val[e] - __bfloat162float(hb[e]));
                 }
-                const long long po = ip[it] * r.cpo + ch;
+                const long long po = (ip[it] + qoff) * r.cpo + ch;
                 *reinterpret_cast<uint2*>(r.y_hi + po) = *reinterpret_cast<uint2*>(hb);
                 if (r.flags & EF_LO) *reinterpret_cast<uint2*>(r.y_lo + po) = *reinterpret_cast<uint2*>(lb);
             }
         }
     }
     if (prof) atomicAdd(&g_tcprof[1], (unsigned long long)(clock64() - tp1));
+#undef RCN_QOFF
 }
 
 // Generic epilogue straight from the accumulator registers (one pixel row per lane): NCHW / pixel-shuffle-to-NCHW stores
@@ -679,14 +683,18 @@ __global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N
 }
 
 // OIHW fp32 -> [Cout][k*k][Cp] bf16 hi / lo (K-major rows for the B operand)
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp,
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp, int ps_perm,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
     const long long total = (long long)Cout * k * k * Cp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cp);
         long long t = i / Cp;
         const int tap = (int)(t % (k * k));
-        const int co = (int)(t / (k * k));
+        int co = (int)(t / (k * k));
+        if (ps_perm) {   // packed row 64g + 16s + cc  <-  conv channel 64g + 4cc + s (pixel-shuffle sub-pixel s, shuffled channel cc)
+            const int g = co >> 6, rr = co & 63;
+            co = (g << 6) + ((rr & 15) << 2) + (rr >> 4);
+        }
         const float v = (c < Cin) ? w[((long long)co * Cin + c) * k * k + tap] : 0.f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
@@ -818,12 +826,13 @@ extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, i
     return RCN_OK;
 }
 
-extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, void* hi, void* lo, void* stream) {
+extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, void* hi, void* lo, void* stream) {
     RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && cp_ok(Cp), "rcn_pack_conv_weight_tc: bad arguments");
+    RCN_CHECK_ARG(!ps_perm || Cout % 64 == 0, "rcn_pack_conv_weight_tc: the pixel-shuffle row order needs Cout %% 64 == 0");
     const long long total = (long long)Cout * k * k * Cp;
     long long blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
-    pack_weight_tc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, k, Cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    pack_weight_tc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, k, Cp, ps_perm, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_pack_conv_weight_tc");
     return RCN_OK;
@@ -891,10 +900,11 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
     // epilogue variant (mirrors the alignment rules of the 16-byte path)
     const bool vec = ((d->store == RCN_STORE_NHWC && (d->Cout & 3) == 0) ||
-                      (d->store == RCN_STORE_PS2 && (d->Cout & 15) == 0 && d->epi == RCN_EPI_NONE)) &&
+                      (d->store == RCN_STORE_PS2 && d->ps_perm && (d->Cout & 63) == 0 && d->epi == RCN_EPI_NONE && !d->cscale)) &&
                      ((d->ldy & 3) == 0) && (!d->y || (reinterpret_cast<uintptr_t>(d->y) & 15) == 0) &&
                      (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
                      (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
+    RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
     const TcKernel kern = select_kernel(d->act, d->epi, vec);
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;

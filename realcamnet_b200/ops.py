@@ -100,11 +100,20 @@ def plane_channels(c: int) -> int:
 
 
 class PackedConv:
-    __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo")
+    __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo", "w_src", "w_hi_ps", "w_lo_ps")
 
     def __init__(self, w, bias, k, cin, cout, cp=0, w_hi=None, w_lo=None):
         self.w, self.bias, self.k, self.cin, self.cout = w, bias, k, cin, cout
         self.cp, self.w_hi, self.w_lo = cp, w_hi, w_lo
+        self.w_src = self.w_hi_ps = self.w_lo_ps = None
+
+    def ps_weights(self):
+        """bf16 planes with rows grouped by PixelShuffle(2) sub-pixel (packed on first use by a pixel-shuffle store)."""
+        if self.w_hi_ps is None:
+            self.w_hi_ps, self.w_lo_ps = torch.empty_like(self.w_hi), torch.empty_like(self.w_lo)
+            _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(self.w_src), self.cout, self.cin, self.k, self.cp, 1, _ptr(self.w_hi_ps),
+                                                      _ptr(self.w_lo_ps), _stream()), "rcn_pack_conv_weight_tc")
+        return self.w_hi_ps, self.w_lo_ps
 
 
 _pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
@@ -130,8 +139,9 @@ def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
         pc.cp = cp
         pc.w_hi = torch.empty((cout, k * k * cp), device=w.device, dtype=torch.bfloat16)
         pc.w_lo = torch.empty_like(pc.w_hi)
-        _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(w), cout, cin, k, cp, _ptr(pc.w_hi), _ptr(pc.w_lo), _stream()),
+        _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(w), cout, cin, k, cp, 0, _ptr(pc.w_hi), _ptr(pc.w_lo), _stream()),
                  "rcn_pack_conv_weight_tc")
+        pc.w_src = w
     return pc
 
 
@@ -259,7 +269,7 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
         raise ValueError("conv2d: operand planes can only feed the tcgen05 engine")
     dev = x.device if x is not None else presplit.hi.device
     can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and plane_channels(Cs) == Cs and
-                (store != STORE_PS2 or epi == EPI_NONE) and pc.cout % 16 == 0)
+                (store != STORE_PS2 or (epi == EPI_NONE and cscale is None and pc.cout % 64 == 0)) and pc.cout % 16 == 0)
     if split_out is not None and not can_emit:
         raise ValueError("conv2d: split_out given but this layer cannot emit operand planes")
     want_out = keep_fp32 or not can_emit or out is not None
@@ -321,7 +331,11 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
         if not same or (passes == 3 and sp.lo is None):
             raise ValueError("conv2d: presplit operand does not belong to this input / layer geometry")
         d.ldp_in = sp.ld
-        _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(pc.w_hi), _ptr(pc.w_lo), pc.cp, passes,
+        w_hi, w_lo = pc.w_hi, pc.w_lo
+        if store == STORE_PS2 and pc.cout % 64 == 0 and epi == EPI_NONE and cscale is None:
+            w_hi, w_lo = pc.ps_weights()          # rows grouped by sub-pixel: 64-byte contiguous pixel-shuffle stores
+            d.ps_perm = 1
+        _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(w_hi), _ptr(w_lo), pc.cp, passes,
                                         _stream()), "rcn_conv2d_tc")
     else:
         _C.check(_C.lib().rcn_conv2d(ctypes.byref(d), _stream()), "rcn_conv2d")

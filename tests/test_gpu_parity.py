@@ -125,6 +125,50 @@ def test_conv2d_epilogues_and_views(dev, engine):
     assert rel(ops.to_nchw(y), F.leaky_relu(F.pixel_shuffle(F.conv2d(x, w4, None, padding=1), 2), 0.01) + r4) < CONV_TOL
 
 
+def test_operand_plane_emission_and_views(dev):
+    """tcgen05 engine: planes emitted by producers (pixel-shuffle store with sub-pixel-grouped weights, channel slices of a
+    shared concat buffer, LayerNorm) equal a split of the fp32 result, and a consumer reading plane views matches torch."""
+    from realcamnet_b200 import ops
+
+    old = ops.get_engine()
+    ops.set_engine("bf16x3")
+    try:
+        g = torch.Generator().manual_seed(21)
+        N, H, W, C = 1, 24, 40, 64
+        x = torch.randn(N, C, H, W, generator=g)
+        xn = ops.to_nhwc(x.to(dev))
+        # pixel-shuffle producer: fp32 result + planes, with a residual in the shuffled geometry
+        w4 = torch.randn(256, C, 3, 3, generator=g) / (9 * C) ** 0.5
+        b4 = torch.randn(256, generator=g)
+        r4 = torch.randn(N, 64, 2 * H, 2 * W, generator=g)
+        p4 = ops.pack_weight(w4.to(dev), b4.to(dev))
+        y, sp = ops.conv2d(xn, p4, store=ops.STORE_PS2, res=ops.to_nhwc(r4.to(dev)), act=ops.ACT_LRELU, slope=0.01, emit_split=True)
+        ref = F.leaky_relu(F.pixel_shuffle(F.conv2d(x, w4, b4, padding=1), 2), 0.01) + r4
+        assert sp is not None and rel(ops.to_nchw(y), ref) < CONV_TOL
+        assert rel((sp.hi.float() + sp.lo.float()).permute(0, 3, 1, 2), ref) < CONV_TOL
+        # two producers write the halves of one concat's planes; the consumer reads the concat, another reads one half
+        wa = torch.randn(64, C, 1, 1, generator=g) / C ** 0.5
+        wb = torch.randn(64, C, 3, 3, generator=g) / (9 * C) ** 0.5
+        pa, pb = ops.pack_weight(wa.to(dev), None), ops.pack_weight(wb.to(dev), None)
+        cat = ops.alloc_planes(N, H, W, 128, dev)
+        ops.conv2d(xn, pa, split_out=cat.channels(0, 64), keep_fp32=False)
+        ops.conv2d(xn, pb, act=ops.ACT_RELU, split_out=cat.channels(64, 128), keep_fp32=False)
+        ref_cat = torch.cat([F.conv2d(x, wa), F.relu(F.conv2d(x, wb, padding=1))], dim=1)
+        wc = torch.randn(32, 128, 3, 3, generator=g) / (9 * 128) ** 0.5
+        out = ops.conv2d(None, ops.pack_weight(wc.to(dev), None), presplit=cat)
+        assert rel(ops.to_nchw(out), F.conv2d(ref_cat, wc, padding=1)) < CONV_TOL
+        wd = torch.randn(48, 64, 3, 3, generator=g) / (9 * 64) ** 0.5
+        out = ops.conv2d(None, ops.pack_weight(wd.to(dev), None), presplit=cat.channels(64, 128))
+        assert rel(ops.to_nchw(out), F.conv2d(ref_cat[:, 64:], wd, padding=1)) < CONV_TOL
+        # LayerNorm straight into planes
+        lw, lb = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        none, lsp = ops.layernorm(xn, lw.to(dev), lb.to(dev), emit_split=True)
+        assert none is None
+        assert rel(lsp.hi.float() + lsp.lo.float(), F.layer_norm(x.permute(0, 2, 3, 1), (C,), lw, lb)) < 1e-5
+    finally:
+        ops.set_engine(old)
+
+
 def test_small_ops(dev):
     from realcamnet_b200 import ops
 
