@@ -165,6 +165,12 @@ def test_operand_plane_emission_and_views(dev):
         none, lsp = ops.layernorm(xn, lw.to(dev), lb.to(dev), emit_split=True)
         assert none is None
         assert rel(lsp.hi.float() + lsp.lo.float(), F.layer_norm(x.permute(0, 2, 3, 1), (C,), lw, lb)) < 1e-5
+        # vectorised LayerNorm kernels (C = 64 / 128), fp32 output, on a channel-slice view with a ragged pixel count
+        for Cn in (64, 128):
+            t = torch.randn(1, 23, 29, Cn + 64, generator=g)
+            wv, bv = torch.randn(Cn, generator=g), torch.randn(Cn, generator=g)
+            yv = ops.layernorm(t.to(dev)[..., 64:], wv.to(dev), bv.to(dev), act=ops.ACT_HSWISH)
+            assert rel(yv, F.hardswish(F.layer_norm(t[..., 64:], (Cn,), wv, bv))) < 1e-5
     finally:
         ops.set_engine(old)
 
@@ -486,6 +492,30 @@ def test_cuda_graph_replay_is_bit_identical_to_eager(final_pair):
         assert c["strings"] == eager["strings"]
     finally:
         m.enable_cuda_graphs(False)
+
+
+def test_frame_pipeline_roundtrip_ragged_frame(final_pair):
+    """BASELINE config 4 in miniature: a ragged packed frame -> zero-padded tiles -> per-tile compress -> RCNB container
+    (two partial containers merged, as two ranks would produce) -> decompress -> stitched frame == per-tile forward."""
+    from realcamnet_b200 import container, frame, tiler
+
+    gold, m, sd, x, xd = final_pair
+    dev = xd[0].device
+    g = torch.Generator().manual_seed(17)
+    fr = torch.rand(4, 300, 600, generator=g)                 # 2 x 3 grid of 256-tiles, ragged right and bottom
+    cond = frame.frame_condition(fr)
+    a = frame.compress_frame(m, fr, 256, cond=cond, tile_indices=[0, 2, 4])
+    b = frame.compress_frame(m, fr, 256, cond=cond, tile_indices=[1, 3, 5])
+    blob = frame.merge_containers([a, b])
+    assert blob == frame.compress_frame(m, fr, 256, cond=cond)             # deterministic, order-independent
+    hdr, recs = container.unpack(blob)
+    assert (hdr.H, hdr.W, hdr.ny, hdr.nx, hdr.n_tiles) == (300, 600, 2, 3, 6)
+    out = frame.decompress_frame(m, blob)
+    assert tuple(out.shape) == (1, 3, 600, 1200)
+    tiles, meta = tiler.split_frame(fr, 256)
+    t = 5                                                                   # bottom-right tile: mostly padding
+    fwd = m([tiles[t:t + 1].to(dev), cond.to(dev), tiler.tile_coords(meta, 256, t, device=dev)])
+    assert torch.equal(out[:, :, 512:, 1024:], fwd["x_hat"].clamp(0, 1)[:, :, :600 - 512, :1200 - 1024])
 
 
 def test_batch_and_nonsquare_tiles(dev, engine):
