@@ -147,7 +147,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tile", type=int, default=2048, help="packed tile side T (BASELINE config[1]: 2048)")
-    ap.add_argument("--cpu-tile", type=int, default=256, help="tile side of the bounded CPU sample")
+    ap.add_argument("--cpu-tile", type=int, default=1024, help="tile side of the bounded CPU sample (4x1024x1024: ~5 s per pass on 16 cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--engine", default=os.environ.get("RCN_CONV_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16"],
@@ -286,9 +286,9 @@ def main():
     ach = kflop / (kms / 1e3) / 1e12        # ALGORITHMIC FLOPs of the convolution (2*k*k*Cin*Cout per output pixel) / time
     issued = work / (kms / 1e3) / 1e12      # what the tensor pipe executed (3 bf16 MMAs per product in the bf16x3 engine)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the one `ncu --set full` capture of THIS launch at
-    # T=2048 (profiles/r1_conv_tcgen05_ncu_full.md: 2.156 + 2.107 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
+    # T=2048 (profiles/r1_final_conv_tcgen05_ncu_full.md: 2.161 + 2.109 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
     # other tile sizes were not captured.
-    traffic = {("bf16x3", 2048): 4.263066e9, ("fp32", 2048): 4.257296e9}.get((args.engine, T))
+    traffic = {("bf16x3", 2048): 4.269627e9, ("fp32", 2048): 4.257296e9}.get((args.engine, T))
     roofline = {"kernel": kname + " -- 3x3 128->128 @ full res (g_s tail)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kms, "peak_source": peaks["_src"] + ", " + peak_note,
@@ -300,10 +300,10 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, dt, cores = run_cpu_reference(args.cpu_tile, 1, 1)
+        v, dt, cores = run_cpu_reference(args.cpu_tile, 2, 1)
         cpu = {"value": v, "unit": "MP/s", "cores": cores, "kind": "port",
                "sample": f"oracle restatement (raw2bit.py:1766-1855 + rANS) on one 4x{args.cpu_tile}x{args.cpu_tile} tile, "
-                         f"torch CPU fp32, {cores} threads (best of all-cores/32/16 probed on the warm-up), 1 timed pass ({dt:.2f} s); host has {os.cpu_count()} logical cores"}
+                         f"torch CPU fp32, {cores} threads (best of all-cores/32/16 probed on the warm-up), 2 timed passes ({dt:.2f} s each); host has {os.cpu_count()} logical cores"}
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
