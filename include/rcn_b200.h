@@ -95,6 +95,8 @@ typedef struct rcn_conv_desc {
     void* y_hi; void* y_lo; int Cp_out;   /* Cp_out = pixel stride of the emitted planes (>= stored channels: a channel slice of a
                                            * wider plane buffer, e.g. one half of a concat the next layer reads) */
     int ldp_in;          /* rcn_conv2d_tc: pixel stride of the INPUT planes x_hi/x_lo in elements (0 = Cp, dense planes) */
+    int planes_s2;       /* emitted planes y_hi/y_lo use the polyphase layout of rcn_split_bf16_s2 ((4N, H/2, W/2, Cp_out): the next layer
+                          * is a stride-2 conv); stride-1 NHWC layers with even H, W only */
     int ps_perm;         /* rcn_conv2d_tc with RCN_STORE_PS2: w_hi/w_lo were packed with ps_perm = 1 (rows grouped by sub-pixel),
                           * which lets the pixel-shuffle store write 64 contiguous bytes per pixel like the NHWC store */
 } rcn_conv_desc;

@@ -22,7 +22,7 @@ class ConvDesc(ctypes.Structure):
         ("cscale", c_void_p), ("cshift", c_void_p),
         ("res", c_void_p), ("ldres", c_int), ("res_pre", c_int),
         ("act", c_int), ("slope", c_float), ("res_scale", c_float),
-        ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int), ("ps_perm", c_int),
+        ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int), ("planes_s2", c_int), ("ps_perm", c_int),
     ]
 
 

@@ -204,11 +204,11 @@ __device__ __forceinline__ void epi_release(uint64_t* empty_bar, int lane) {
 struct EpiRegs {
     float* y; const float* res; const float* aux; const float* cscale; const float* cshift;
     __nv_bfloat16* y_hi; __nv_bfloat16* y_lo;
-    int H, W, Cout, ldy, ldres, ldaux, cpo;
+    int H, W, N, Cout, ldy, ldres, ldaux, cpo;
     float slope, rpre, rpost;   // residual weights: v = act(v + rpre*res) + rpost*res  (0 when absent)
     uint32_t flags;
 };
-enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256 };
+enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512 };
 template <typename T>
 __device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
@@ -218,15 +218,15 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
     EpiRegs r;
     r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
     r.y_hi = reinterpret_cast<__nv_bfloat16*>(p.y_hi); r.y_lo = reinterpret_cast<__nv_bfloat16*>(p.y_lo);
-    r.H = p.H; r.W = p.W; r.Cout = p.Cout; r.ldy = p.ldy; r.ldres = p.ldres; r.ldaux = p.ldaux; r.cpo = p.Cp_out;
+    r.H = p.H; r.W = p.W; r.N = p.N; r.Cout = p.Cout; r.ldy = p.ldy; r.ldres = p.ldres; r.ldaux = p.ldaux; r.cpo = p.Cp_out;
     r.slope = p.slope;
     r.rpre = (p.res && p.res_pre) ? p.res_scale : 0.f;
     r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
     r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
               (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
-              ((dbg & 128) ? EF_PROF : 0);
+              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0);
     opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
-    opaque(r.H); opaque(r.W); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
+    opaque(r.H); opaque(r.W); opaque(r.N); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
     opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
     return r;
 }
@@ -367,7 +367,13 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                     hb[e] = __float2bfloat16_rn(val[e]);
                     lb[e] = __float2bfloat16_rn(val[e] - __bfloat162float(hb[e]));
                 }
-                const long long po = (ip[it] + qoff) * r.cpo + ch;
+                long long po = (ip[it] + qoff) * r.cpo + ch;
+                if (r.flags & EF_S2OUT) {
+                    // polyphase layout of a stride-2 consumer: pixel (h, w) -> plane (h&1)*2 + (w&1), position (h>>1, w>>1)
+                    const int h = hy + (it >> 1), w = wx + 8 * (it & 1);
+                    const long long plane = (long long)(((h & 1) * 2 + (w & 1)) * r.N + n);
+                    po = ((plane * (r.H >> 1) + (h >> 1)) * (r.W >> 1) + (w >> 1)) * r.cpo + ch;
+                }
                 *reinterpret_cast<uint2*>(r.y_hi + po) = *reinterpret_cast<uint2*>(hb);
                 if (r.flags & EF_LO) *reinterpret_cast<uint2*>(r.y_lo + po) = *reinterpret_cast<uint2*>(lb);
             }
@@ -852,6 +858,8 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
                       "rcn_conv2d_tc: operand-plane emission needs an NHWC / pixel-shuffle store, a plane pixel stride Cp_out >= the "
                       "stored channels (multiple of 8) and 16-byte aligned tensors");
     }
+    RCN_CHECK_ARG(!d->planes_s2 || (d->y_hi && d->store == RCN_STORE_NHWC && d->stride == 1 && d->H % 2 == 0 && d->W % 2 == 0),
+                  "rcn_conv2d_tc: polyphase plane emission needs a stride-1 NHWC layer with even H and W");
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
     RCN_CHECK_ARG(d->Cout <= BIAS_MAX, "rcn_conv2d_tc: Cout %d > %d unsupported", d->Cout, BIAS_MAX);

@@ -135,9 +135,12 @@ class ResidualBlockWithStride(_Block):
         self.gdn = GDN(out_ch)
         self.skip = conv1x1(in_ch, out_ch, stride=stride) if (stride != 1 or in_ch != out_ch) else None
 
-    def _f(self, x, out=None):
+    def _f(self, x, out=None, presplit=None):
+        """presplit: operand planes of x emitted by its producer for this stride (x may then be None when a skip conv exists)."""
         # conv1 and the 1x1 skip read the same tensor with the same stride: one bf16 split serves both
-        sp = ops.shared_split(x, [ops.pack(self.conv1), ops.pack(self.skip)], self.conv1.stride[0]) if self.skip is not None else None
+        sp = presplit
+        if sp is None and self.skip is not None:
+            sp = ops.shared_split(x, [ops.pack(self.conv1), ops.pack(self.skip)], self.conv1.stride[0])
         t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
         t = self.conv2._f(t, presplit=tsp)
         identity = x if self.skip is None else self.skip._f(x, presplit=sp)

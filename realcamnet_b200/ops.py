@@ -193,16 +193,17 @@ def plane_ld(t):
     return ld
 
 
-def alloc_planes(N, H, W, C, device, passes=None) -> SplitOperand:
-    """Uninitialised stride-1 operand planes of an (N,H,W,C) tensor for producers to write (conv2d(split_out=...),
-    layernorm / wmsa emit); C must be a valid plane width."""
+def alloc_planes(N, H, W, C, device, passes=None, stride=1) -> SplitOperand:
+    """Uninitialised operand planes of an (N,H,W,C) tensor for producers to write (conv2d(split_out=...), layernorm / wmsa
+    emit); C must be a valid plane width.  stride=2: the polyphase layout a stride-2 consumer reads (4N, H/2, W/2, C)."""
     if plane_channels(C) != C:
         raise ValueError(f"{C} channels is not a valid plane width")
     if passes is None:
         passes = 3 if _ENGINE == "bf16x3" else 1
-    hi = torch.empty((N, H, W, C), device=device, dtype=torch.bfloat16)
+    shape = (N, H, W, C) if stride == 1 else (4 * N, H // 2, W // 2, C)
+    hi = torch.empty(shape, device=device, dtype=torch.bfloat16)
     lo = torch.empty_like(hi) if passes == 3 else None
-    return SplitOperand(hi, lo, (None, N, H, W, C, None, C, 1, False))
+    return SplitOperand(hi, lo, (None, N, H, W, C, None, C, stride, False))
 
 
 def planes_enabled() -> bool:
@@ -240,20 +241,21 @@ def shared_split(x, pcs, stride=1):
 
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
            cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None,
-           emit_split=False, keep_fp32=True, split_out=None):
+           emit_split=False, keep_fp32=True, split_out=None, emit_stride=1):
     """One conv / linear layer with its fused epilogue.
 
     x may be None when `presplit` carries operand planes that a previous tcgen05 conv emitted (conv->conv chains never
     materialise the fp32 intermediate).  emit_split=True returns (out, SplitOperand | None): the epilogue additionally
     writes the NEXT layer's bf16 hi/lo planes; with keep_fp32=False `out` is None when that was possible.
-    split_out: planes allocated by the caller (e.g. one half of a concat's planes) to emit into; implies emit_split."""
+    split_out: planes allocated by the caller (e.g. one half of a concat's planes) to emit into; implies emit_split.
+    emit_stride=2: the emitted planes use the polyphase layout of a stride-2 consumer (no rcn_split_bf16_s2 pass)."""
     if split_out is not None:
         emit_split = True
     eng = engine or _ENGINE
     if x is None:
-        if presplit is None or presplit.key[7] != 1:
-            raise ValueError("conv2d: x=None needs stride-1 operand planes from a previous layer")
-        N, H, W = presplit.hi.shape[0], presplit.hi.shape[1], presplit.hi.shape[2]
+        if presplit is None or presplit.key[7] != stride:
+            raise ValueError("conv2d: x=None needs operand planes from a previous layer, emitted for this layer's stride")
+        N, H, W = presplit.key[1:4]
         Cin, ldx = presplit.key[4], 0
     else:
         N, H, W, Cin, ldx = geom(x, "conv2d.x")
@@ -270,6 +272,8 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     dev = x.device if x is not None else presplit.hi.device
     can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and plane_channels(Cs) == Cs and
                 (store != STORE_PS2 or (epi == EPI_NONE and cscale is None and pc.cout % 64 == 0)) and pc.cout % 16 == 0)
+    if emit_stride == 2:
+        can_emit = can_emit and store == STORE_NHWC and stride == 1 and Ho % 2 == 0 and Wo % 2 == 0
     if split_out is not None and not can_emit:
         raise ValueError("conv2d: split_out given but this layer cannot emit operand planes")
     want_out = keep_fp32 or not can_emit or out is not None
@@ -315,9 +319,11 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
         ok = (ldy % 4 == 0 and (out is None or out.data_ptr() % 16 == 0) and lda % 4 == 0 and ldr % 4 == 0 and
               (aux is None or aux.data_ptr() % 16 == 0) and (res is None or res.data_ptr() % 16 == 0))
         if ok:
-            sp_out = split_out if split_out is not None else alloc_planes(N, Hs, Ws, Cs, dev)
-            if tuple(sp_out.hi.shape) != (N, Hs, Ws, Cs) or sp_out.key[7] != 1:
+            sp_out = split_out if split_out is not None else alloc_planes(N, Hs, Ws, Cs, dev, stride=emit_stride)
+            want_shape = (N, Hs, Ws, Cs) if emit_stride == 1 else (4 * N, Hs // 2, Ws // 2, Cs)
+            if tuple(sp_out.hi.shape) != want_shape or sp_out.key[7] != emit_stride:
                 raise ValueError("conv2d: split_out planes do not have the stored output geometry")
+            d.planes_s2 = int(emit_stride == 2)
             d.y_hi, d.y_lo, d.Cp_out = sp_out.hi.data_ptr(), (sp_out.lo.data_ptr() if sp_out.lo is not None else None), sp_out.ld
         elif out is None:
             raise ValueError("conv2d: cannot drop the fp32 output of a layer whose epilogue is not 16-byte aligned")

@@ -112,7 +112,8 @@ class ConvTransBlock_mzj(nn.Module):
         self.conv_block = ResidualBlockWithCA(conv_dim, conv_dim, 8)
         self.spatial_transform = SpatialFeatureTransform(cond_channels=conv_dim, n_features=conv_dim)
 
-    def _f(self, x, cond, out=None, cond_split=None):
+    def _f(self, x, cond, out=None, cond_split=None, emit_stride=0):
+        """emit_stride=2: returns (fea | None, polyphase operand planes) for a stride-2 consumer that is the only reader."""
         cd, td = self.conv_dim, self.trans_dim
         planes = ops.planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
             ops.plane_channels(cd + td) == cd + td
@@ -123,7 +124,8 @@ class ConvTransBlock_mzj(nn.Module):
             cx = self.conv_block._f(conv_identity)
             self.spatial_transform._f(cx, cond, extra=conv_identity, out=cat[..., :cd], cond_split=cond_split)
             self.trans_block._f(both[..., cd:], out=cat[..., cd:])
-            return self.conv1_2._f(cat, res=x, out=out)
+            fea = self.conv1_2._f(cat, res=x, out=out)
+            return (fea, None) if emit_stride else fea
         # tcgen05 engine: see ConvTransBlock._f -- the concat read by conv1_2 only exists as operand planes
         both, bsp = self.conv1_1._f(x, emit_split=True)
         N, H, W, _ = both.shape
@@ -132,6 +134,8 @@ class ConvTransBlock_mzj(nn.Module):
         cx = self.conv_block._f(conv_identity, presplit=bsp.channels(0, cd))
         self.spatial_transform._f(cx, cond, extra=conv_identity, cond_split=cond_split, split_out=csp.channels(0, cd), keep_fp32=False)
         self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
+        if emit_stride:
+            return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=True, keep_fp32=False, emit_stride=emit_stride)
         return self.conv1_2._f(None, res=x, out=out, presplit=csp)
 
     def forward(self, xx):
@@ -222,10 +226,12 @@ class HybridConditionModule(nn.Module):
         y = self.dec_1._f(x4, cat1)
         y = self.dec_2._f(y, cat2)
         y = self.dec_3._f(y, cat3)
-        y = self.out_conv._f(y)
-        # the three CondNets read y through a stride-2 3x3 conv: one polyphase split serves all of them
-        heads = [self.CondNet1[0], self.CondNet2[0], self.CondNet3[0]]
-        sp = ops.shared_split(y, [ops.pack(h) for h in heads], stride=2)
+        # the three CondNets read y through a stride-2 3x3 conv only: out_conv writes their (shared) polyphase operand planes itself
+        y, sp = self.out_conv.conv._f(y, act=self.out_conv._act[0], slope=self.out_conv._act[1], emit_split=True, keep_fp32=False,
+                                      emit_stride=2)
+        if sp is None:
+            heads = [self.CondNet1[0], self.CondNet2[0], self.CondNet3[0]]
+            sp = ops.shared_split(y, [ops.pack(h) for h in heads], stride=2)
         t, tsp = self.CondNet1[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
         c1 = self.CondNet1[2]._f(t, presplit=tsp)
         c2 = self.CondNet2[2]._f(self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp))
@@ -330,8 +336,9 @@ class raw_compression_tcm_final(SliceCodecModel):
         lsc_fea = self.lsc._f(coord)
         rsp = ops.shared_split(raw, [ops.pack(self.conv_first), ops.pack(self.local_condition.in_conv.conv)])   # both read raw
         local = self.local_condition._f(raw, presplit=rsp)
-        fea = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, presplit=rsp)   # conv_first(x) * (lsc + 1)
-        fea = self.conv_down._f(fea)
+        # conv_first(x) * (lsc + 1): only conv_down (stride 2) reads it -> written once, as polyphase operand planes
+        fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, presplit=rsp, emit_split=True, keep_fp32=False, emit_stride=2)
+        fea = self.conv_down._f(fea, presplit=fsp)
         for lvl, (gfm, blocks, down) in enumerate(((self.gfm1, self.m_down1, self.m_down1_down),
                                                    (self.gfm2, self.m_down2, self.m_down2_down),
                                                    (self.gfm3, self.m_down3, self.m_down3_down))):
@@ -339,9 +346,13 @@ class raw_compression_tcm_final(SliceCodecModel):
                 fea = g._f(fea, vec)
             csp = ops.shared_split(local[lvl], [ops.pack(blocks[0].spatial_transform.cond_scale[0]),
                                                 ops.pack(blocks[0].spatial_transform.cond_shift[0])])   # cond planes: once per level
-            for blk in blocks:
-                fea = blk._f(fea, local[lvl], cond_split=csp)
-            fea = down._f(fea)
+            fsp = None
+            for j, blk in enumerate(blocks):
+                if j == len(blocks) - 1:     # the level's last block feeds the stride-2 `down` layer only
+                    fea, fsp = blk._f(fea, local[lvl], cond_split=csp, emit_stride=2)
+                else:
+                    fea = blk._f(fea, local[lvl], cond_split=csp)
+            fea = down._f(fea, presplit=fsp)
         return fea, lsc_fea, local
 
     def _g_s(self, y_hat, clamp=False):

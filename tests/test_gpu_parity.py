@@ -160,6 +160,14 @@ def test_operand_plane_emission_and_views(dev):
         wd = torch.randn(48, 64, 3, 3, generator=g) / (9 * 64) ** 0.5
         out = ops.conv2d(None, ops.pack_weight(wd.to(dev), None), presplit=cat.channels(64, 128))
         assert rel(ops.to_nchw(out), F.conv2d(ref_cat[:, 64:], wd, padding=1)) < CONV_TOL
+        # polyphase emission for a stride-2 consumer == rcn_split_bf16_s2 of the fp32 result; the consumer reads it without x
+        y_full = ops.conv2d(xn, pb, act=ops.ACT_RELU)
+        none, s2 = ops.conv2d(xn, pb, act=ops.ACT_RELU, emit_split=True, keep_fp32=False, emit_stride=2)
+        ref_s2 = ops.split_operand(y_full, 64, stride=2)
+        assert none is None and torch.equal(s2.hi, ref_s2.hi) and torch.equal(s2.lo, ref_s2.lo)
+        we = torch.randn(32, 64, 3, 3, generator=g) / (9 * 64) ** 0.5
+        out = ops.conv2d(None, ops.pack_weight(we.to(dev), None), stride=2, presplit=s2)
+        assert rel(ops.to_nchw(out), F.conv2d(F.relu(F.conv2d(x, wb, padding=1)), we, stride=2, padding=1)) < CONV_TOL
         # LayerNorm straight into planes
         lw, lb = torch.randn(C, generator=g), torch.randn(C, generator=g)
         none, lsp = ops.layernorm(xn, lw.to(dev), lb.to(dev), emit_split=True)
