@@ -134,21 +134,31 @@ __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, 
             *reinterpret_cast<float4*>(vs + t * HD + d) = c;
         }
     }
+    // relative-position bias of this block's heads, pre-multiplied by log2(e) (scores are kept in the log2 domain so that the
+    // softmax needs one MUFU.EX2 per score)
+    constexpr int RP = (2 * WS - 1) * (2 * WS - 1);
+    constexpr float LOG2E = 1.4426950408889634f;
+    float* rps = sm + (size_t)blockDim.y * 2 * P * HD;   // [HPB][RP]
+    for (int i = threadIdx.y * P + t; i < (int)blockDim.y * RP; i += P * (int)blockDim.y) {
+        const int hh = blockIdx.y * blockDim.y + i / RP;
+        rps[i] = hh < nheads ? relpos[(size_t)hh * RP + (i % RP)] * LOG2E : 0.f;
+    }
     __syncthreads();
     if (!active) return;
-    const float scale = rsqrtf((float)HD);
+    const float qscale = rsqrtf((float)HD) * LOG2E;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) q[d] *= qscale;
     const bool rq = shifted && (wy == nwh - 1) && (py >= WS - sh);
     const bool cq = shifted && (wx == nww - 1) && (px >= WS - sh);
-    const float* rp = relpos + (size_t)head * (2 * WS - 1) * (2 * WS - 1);
+    const float* rp = rps + hl * RP + (py + WS - 1) * (2 * WS - 1) + (px + WS - 1);
     float s[P];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-        float a = 0.f;
+        const int jy = j / WS, jx = j - jy * WS;
+        float a = rp[-(jy * (2 * WS - 1) + jx)];
 #pragma unroll
         for (int d = 0; d < HD; ++d) a = fmaf(q[d], ks[j * HD + d], a);
-        const int jy = j / WS, jx = j - jy * WS;
-        a = a * scale + rp[(py - jy + WS - 1) * (2 * WS - 1) + (px - jx + WS - 1)];
         if (shifted) {
             const bool rk = (wy == nwh - 1) && (jy >= WS - sh);
             const bool ck = (wx == nww - 1) && (jx >= WS - sh);
@@ -159,17 +169,18 @@ __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, 
     }
     float den = 0.f;
 #pragma unroll
-    for (int j = 0; j < P; ++j) { s[j] = expf(s[j] - mx); den += s[j]; }
+    for (int j = 0; j < P; ++j) { s[j] = exp2f(s[j] - mx); den += s[j]; }
     const float inv = 1.f / den;
     float o[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
 #pragma unroll
     for (int j = 0; j < P; ++j) {
-        const float pj = s[j] * inv;
 #pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = fmaf(pj, vs[j * HD + d], o[d]);
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(s[j], vs[j * HD + d], o[d]);
     }
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] *= inv;
     const long long opix = (long long)(n * H + gy) * W + gx;
     if (out) {
         float* op = out + opix * ldo + head * HD;
@@ -202,7 +213,7 @@ int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shift
     if (hpb < 1) hpb = 1;
     dim3 block(P, hpb);
     dim3 grid((unsigned)(N * (H / WS) * (W / WS)), (nheads + hpb - 1) / hpb);
-    const size_t smem = (size_t)hpb * 2 * P * HD * sizeof(float);
+    const size_t smem = ((size_t)hpb * 2 * P * HD + (size_t)hpb * (2 * WS - 1) * (2 * WS - 1)) * sizeof(float);
     auto kern = wmsa_kernel<WS, HD>;
     if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, block, smem, s>>>(qkv, H, W, C, ldq, shifted, relpos, out, ldo, nheads, out_hi, out_lo, ldp);
