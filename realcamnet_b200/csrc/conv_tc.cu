@@ -85,6 +85,22 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the MMAs of one pipeline stage: KSTEPS k16 steps x (3 split passes | 1 pass), fully unrolled with constant descriptor advances
+template <int PASSES, int KSTEPS>
+__device__ __forceinline__ void issue_stage(uint32_t tmem_d, uint64_t a_hi, uint64_t b_hi, uint64_t a_lo, uint64_t b_lo, uint32_t idesc,
+                                            uint32_t acc0) {
+#pragma unroll
+    for (int j = 0; j < KSTEPS; ++j) {
+        const uint64_t adv = (uint64_t)(2 * j);   // 16 bf16 = 32 B along K inside the swizzle atom, in 16-byte descriptor units
+        if (PASSES == 3) {
+            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, j == 0 ? acc0 : 1u);
+            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, 1u);
+        } else {
+            umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, j == 0 ? acc0 : 1u);
+        }
+    }
+}
 
 // K-major swizzled operand tile: rows of bk*2 bytes (128 / 64 / 32), 8-row groups 8*bk*2 bytes apart
 __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int bk) {
@@ -108,7 +124,7 @@ struct TcParams {
     int passes;   // 1 or 3
     int stages;
     int s2;       // stride-2 conv: A planes are the 4 polyphase components stacked on the batch axis ((py*2+px)*N + n)
-    int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math
+    int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math, 16 centre-tap A loads only
 };
 
 #ifndef RCN_TC_EPI_WARPS
@@ -511,9 +527,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (warp == 0) {
         // ================= TMA producer =================
         if (lane == 0) {
-            const bool loadA = !(P.dbg & 4);
+            const bool loadA_all = !(P.dbg & 4);
             const uint32_t b_tx = (uint32_t)(P.Ntile * BLOCK_K * 2), a_tx = (uint32_t)(128 * BLOCK_K * 2);   // bytes the boxes really carry
-            const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (b_tx + (loadA ? a_tx : 0u));
             int stage = 0;
             uint32_t phase = 0;
             const uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
@@ -529,6 +544,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     const int ky = tap / p.k, kx = tap - ky * p.k;
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + (size_t)stage * stage_bytes;
+                    // perf triage: dbg & 16 fetches the A boxes of the centre tap only (what a halo-tile load would cost in L2 -> smem
+                    // traffic); the other taps multiply stale but finite shared-memory contents
+                    const bool loadA = loadA_all && (!(P.dbg & 16) || tap == (p.k * p.k) / 2);
+                    const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (b_tx + (loadA ? a_tx : 0u));
                     mbar_expect_tx(&full_bar[stage], tx_bytes);
                     // input box origin for this tap.  stride 1: shifted box of the same plane.  stride 2 (pad k/2):
                     // input row 2y+ky-pad lives in polyphase plane py = (ky-pad)&1 at row y + floor((ky-pad)/2).
@@ -552,44 +571,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t local = 0;
-            for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
-                const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
-                int nact = p.Cout - n0;
-                if (nact > P.Ntile) nact = P.Ntile;
-                nact = (nact + 15) & ~15;
-                const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-                const uint32_t ab = local & 1;
-                mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        // All 32 lanes run this loop convergently -- uniform control flow and uniform values, so descriptors, addresses and loop
+        // state live in the uniform datapath -- and the single-thread instructions (tcgen05.mma, tcgen05.commit) are predicated
+        // on one elected lane inside the asm.  Issued from an `if (lane == 0)` region the same loop cost ~9 SASS instructions
+        // (PLOP3 / ELECT / R2UR.BROADCAST / ...) per MMA, ~1600 cycles per 12-MMA pipeline stage: the issuing thread, not the
+        // tensor pipe, the TMA fill or the epilogue, bounded every layer (ncu: producer waiting on free stages, MMA warp never
+        // waiting on data, tensor pipe 56 % active).
+        // warp-uniform copies (REDUX / VOTE results live in uniform registers) of the two values that come from memory
+        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
+        const uint32_t smem0 = __reduce_or_sync(0xffffffffu, smem_u32(smem));
+        const int ksteps = BLOCK_K / 16;
+        int stage = 0;
+        uint32_t phase = 0;
+        uint32_t local = 0;
+        if (lane == 0)
+        for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
+            const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
+            int nact = p.Cout - n0;
+            if (nact > P.Ntile) nact = P.Ntile;
+            nact = (nact + 15) & ~15;
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t ab = local & 1;
+            mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_u + ab * 128;
+            uint32_t acc = 0;
+            for (int it = 0; it < kiters; ++it) {
+                mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + ab * 128;
-                uint32_t acc = 0;
-                for (int it = 0; it < kiters; ++it) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
-                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
-                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
-#pragma unroll 4
-                    for (int j = 0; j < ((P.dbg & 2) ? 0 : BLOCK_K / 16); ++j) {
-                        const uint64_t adv = (uint64_t)((j * 32) >> 4);  // 16 bf16 = 32 B along K inside the swizzle atom
-                        if (P.passes == 3) {
-                            umma_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, acc);
-                            acc = 1;
-                            umma_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1);
-                        }
-                        umma_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, acc);
-                        acc = 1;
+                const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
+                const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
+                const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
+                               b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
+                if (!(P.dbg & 2)) {
+                    if (P.passes == 3) {
+                        if (ksteps == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else if (ksteps == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                    } else {
+                        if (ksteps == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else if (ksteps == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tmem_full[ab]);
+                acc = 1;
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
+            umma_commit(&tmem_full[ab]);
         }
         __syncwarp();
     } else {
