@@ -12,10 +12,12 @@
 // weights are split as x = hi + lo (two bf16 planes) and hi*hi + lo*hi + hi*lo is accumulated in
 // fp32 -- ~16 mantissa bits, which keeps the 1e-3 parity bar through the ~100-layer path.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..9 = epilogue (TMEM lane quarter = warp_id % 4, one 64-column half of the accumulator per warp).
-// mbarrier ring: full[s] (TMA -> MMA), empty[s] (tcgen05.commit -> TMA), tmem_full[2] (last commit of a tile ->
-// epilogue), tmem_empty[2] (8 epilogue warps -> MMA issuer): the accumulator is double-buffered in TMEM.
+// Warp roles (352 threads): warp 0 = TMA producer (one lane); warps 1-2 = MMA issuers (one lane each; warp 1 also owns the TMEM
+// allocation).  Long-K layers (3x3) split every pipeline stage's k16 steps between the two issuers, each accumulating into its own
+// TMEM accumulator -- a single issuing thread, not the tensor pipe, bounded those layers -- and the epilogue adds the two partial
+// accumulators in a fixed order.  Warps 3-10 = epilogue (TMEM lane quarter = warp_id % 4; each warp drains Ntile/2 or 64 columns).
+// mbarrier ring: full[s] (TMA -> MMA warps), empty[s] (tcgen05.commit of every issuer -> TMA), tmem_full[2] (last commits of a
+// tile -> epilogue), tmem_empty[2] (8 epilogue warps -> MMA issuers): the accumulators are double-buffered in TMEM (4 x 128 columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -124,6 +126,8 @@ struct TcParams {
     int passes;   // 1 or 3
     int stages;
     int s2;       // stride-2 conv: A planes are the 4 polyphase components stacked on the batch axis ((py*2+px)*N + n)
+    int nmma;     // MMA-issuing warps: 2 for long K loops (3x3 layers), 1 otherwise
+    int wcw;      // accumulator columns per epilogue warp: 64, or Ntile / 2 when that keeps all 8 warps busy (Ntile = 64, 96)
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math, 16 centre-tap A loads only
 };
 
@@ -134,7 +138,9 @@ constexpr int EPI_WARPS = RCN_TC_EPI_WARPS;   // EPI_WARPS / 4 warps per TMEM la
 constexpr int WCOLS = 128 / (EPI_WARPS / 4);  // 64 (8 warps) or 32 (16 warps)
 constexpr int QN = WCOLS / 16;                // 16-column quarters per warp and tile
 constexpr int EPI_THREADS = EPI_WARPS * 32;
-constexpr int TC_THREADS = 64 + EPI_THREADS;
+constexpr int MMA_WARPS = 2;             // warps 1, 2: each issues half of a stage's k16 steps into its own TMEM accumulator
+constexpr int EPI_WARP0 = 1 + MMA_WARPS; // first epilogue warp
+constexpr int TC_THREADS = 32 * EPI_WARP0 + EPI_THREADS;
 constexpr int SLAB_FLOATS = 32 * 16;     // warp-private transposition slab: 32 pixel rows x 16 floats, 16-byte chunks XOR-swizzled
 constexpr int STG_BYTES = EPI_WARPS * SLAB_FLOATS * 4;   // 16 KB
 // The bias vector is staged in shared memory once per CTA: with ~220 KB of the SM's 228 KB carved out as shared memory there
@@ -207,6 +213,20 @@ __device__ __forceinline__ void tmem_wait_ld16(uint32_t* v) {
                  :
                  : "memory");
 }
+// The accumulator of a tile is the sum of the two MMA warps' partial accumulators (columns +0 and +128 of the tile's TMEM
+// buffer): a fixed summation order, so results stay bit-reproducible (the codec needs encoder == decoder arithmetic).
+__device__ __forceinline__ void tmem_ld16x2_async(uint32_t taddr, uint32_t* v, uint32_t* w, bool dual) {
+    tmem_ld16_async(taddr, v);
+    if (dual) tmem_ld16_async(taddr + 128, w);
+}
+__device__ __forceinline__ void tmem_wait_sum16(uint32_t* v, uint32_t* w, bool dual) {
+    tmem_wait_ld16(v);
+    if (dual) {
+        tmem_wait_ld16(w);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(w[i]));
+    }
+}
 __device__ __forceinline__ void epi_release(uint64_t* empty_bar, int lane) {
     tc_fence_before();
     __syncwarp();
@@ -224,13 +244,14 @@ struct EpiRegs {
     float slope, rpre, rpost;   // residual weights: v = act(v + rpre*res) + rpost*res  (0 when absent)
     uint32_t flags;
 };
-enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512 };
+enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512,
+       EF_DUAL = 1024 };
 template <typename T>
 __device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
 __device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
-__device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg) {
+__device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg, bool dual) {
     EpiRegs r;
     r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
     r.y_hi = reinterpret_cast<__nv_bfloat16*>(p.y_hi); r.y_lo = reinterpret_cast<__nv_bfloat16*>(p.y_lo);
@@ -240,7 +261,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
     r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
     r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
               (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
-              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0);
+              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0);
     opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
     opaque(r.H); opaque(r.W); opaque(r.N); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
     opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
@@ -259,7 +280,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
 //                channels cb/4 ..+15 of that pixel -- the same 64-byte-contiguous store pattern as the NHWC case.
 // The residual (or aux) operand of all 16 items is requested BEFORE the wait on the accumulator barrier, so its HBM latency
 // hides behind the MMAs of this tile; the TMEM load of quarter hh+1 is in flight while quarter hh is finished.
-template <int ACT, int EPI>
+template <int ACT, int EPI, bool DUAL>
 __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int epi, uint32_t slab, uint32_t sbias, uint32_t taddr,
                                                   uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0,
                                                   int cb, int wcols, int q, int lane) {
@@ -301,15 +322,16 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                 pre[hh][it] = ldg4(pre_ptr + (ip[it] + RCN_QOFF(hh)) * pre_ld + chb + chs * hh);
         }
     }
-    const bool prof = (r.flags & EF_PROF) && blockIdx.x == 0 && threadIdx.x == 64;
+    const bool prof = (r.flags & EF_PROF) && blockIdx.x == 0 && threadIdx.x == 32 * EPI_WARP0;
+    constexpr bool dual = DUAL;
     long long tp0 = 0, tp1 = 0;
     if (prof) tp0 = clock64();
     mbar_wait(full_bar, parity);
     tc_fence_after();
     if (prof) { tp1 = clock64(); atomicAdd(&g_tcprof[0], (unsigned long long)(tp1 - tp0)); atomicAdd(&g_tcprof[2], 1ull); }
     if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
-    uint32_t v[16];
-    tmem_ld16_async(taddr, v);
+    uint32_t v[16], w2[16];
+    tmem_ld16x2_async(taddr, v, w2, dual);
     const int wsw = (lane >> 1) & 3;   // write-side swizzle of row `lane`
     const int rsw = (r0 >> 1) & 3;     // read-side swizzle of rows r0 + 8*it
 #pragma unroll
@@ -342,14 +364,14 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
             if (has_aux && has_res && ah && okp[it]) sec[it] = ldg4(r.aux + (ip[it] + qoff) * r.ldaux + ch);
         }
         // ---- transpose: row `lane` <- the 16 accumulator columns of this quarter
-        tmem_wait_ld16(v);
+        tmem_wait_sum16(v, w2, dual);
         const uint32_t wrow = slab + (uint32_t)lane * 64u;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const float4 t = make_float4(__uint_as_float(v[4 * k]), __uint_as_float(v[4 * k + 1]), __uint_as_float(v[4 * k + 2]), __uint_as_float(v[4 * k + 3]));
             sts4(wrow + 16u * (uint32_t)(k ^ wsw), t);
         }
-        if (16 * (hh + 1) < wcols) tmem_ld16_async(taddr + 16 * (hh + 1), v);   // next quarter in flight
+        if (16 * (hh + 1) < wcols) tmem_ld16x2_async(taddr + 16 * (hh + 1), v, w2, dual);   // next quarter in flight
         else epi_release(empty_bar, lane);                                      // last TMEM read of this tile by this warp
         __syncwarp();
         float4 acc[4];
@@ -453,7 +475,7 @@ __device__ __forceinline__ void rows_block(const EpiRegs& r, int act, int epi, i
         }
     }
 }
-template <int ACT, int EPI>
+template <int ACT, int EPI, bool DUAL>
 __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, int epi, int store, uint32_t sbias, uint32_t taddr,
                                                    uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0, int cb,
                                                    int wcols, int q, int lane) {
@@ -465,10 +487,10 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, in
     const bool ok = ho < r.H && wo < r.W;
 #pragma unroll 1
     for (int c0 = 0; c0 < wcols; c0 += 16) {
-        uint32_t v[16];
+        uint32_t v[16], w2[16];
         __syncwarp();
-        tmem_ld16_async(taddr + c0, v);
-        tmem_wait_ld16(v);
+        tmem_ld16x2_async(taddr + c0, v, w2, DUAL);
+        tmem_wait_sum16(v, w2, DUAL);
         if (c0 + 16 >= wcols) epi_release(empty_bar, lane);
         if (ok) rows_block<ACT, EPI>(r, act, epi, store, sbias, v, n, ho, wo, cb + c0, wcols - c0 > 16 ? 16 : wcols - c0);
     }
@@ -484,7 +506,7 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, in
 #else
 #define RCN_TC_BOUNDS __launch_bounds__(TC_THREADS, 1)
 #endif
-template <int ACT, int EPI, bool VEC>
+template <int ACT, int EPI, bool VEC, bool DUAL>
 __global__ void RCN_TC_BOUNDS
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
@@ -503,12 +525,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int pad = p.k >> 1;
+    const int ksteps = BLOCK_K / 16;
+    constexpr int nmma = DUAL ? MMA_WARPS : 1;
     const int chunks = P.Cp / BLOCK_K;
     const int kiters = p.k * p.k * chunks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nmma); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], nmma); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (p.bias) {
@@ -516,7 +540,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     const uint32_t sbias = p.bias ? smem_u32(sbias_mem) : 0u;   // shared-space address (0 = no bias)
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     tc_fence_before();
@@ -569,22 +593,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer =================
-        // All 32 lanes run this loop convergently -- uniform control flow and uniform values, so descriptors, addresses and loop
-        // state live in the uniform datapath -- and the single-thread instructions (tcgen05.mma, tcgen05.commit) are predicated
-        // on one elected lane inside the asm.  Issued from an `if (lane == 0)` region the same loop cost ~9 SASS instructions
-        // (PLOP3 / ELECT / R2UR.BROADCAST / ...) per MMA, ~1600 cycles per 12-MMA pipeline stage: the issuing thread, not the
-        // tensor pipe, the TMA fill or the epilogue, bounded every layer (ncu: producer waiting on free stages, MMA warp never
-        // waiting on data, tensor pipe 56 % active).
-        // warp-uniform copies (REDUX / VOTE results live in uniform registers) of the two values that come from memory
+    } else if (warp < EPI_WARP0) {
+        // ================= MMA issuers (warps 1 and 2) =================
+        // The single thread that issues tcgen05.mma is the bottleneck of every layer with a long K loop: ptxas wraps each UTCHMMA
+        // issued from divergent code in an ELECT / PLOP3 / BRA.U.ANY sequence, ~120 cycles per MMA against the 64-90 the tensor
+        // pipe needs for M128 x N128 x K16 (ncu: producer waiting on free stages, MMA warp never waiting on data, tensor pipe 56 %
+        // active).  So TWO warps issue: warp 1 the first half of each stage's k16 steps, warp 2 the second half, each into its own
+        // TMEM accumulator (the epilogue adds the two in a fixed order).  Everything read from memory is first made warp-uniform
+        // (REDUX results live in uniform registers) so that descriptors and addresses stay in the uniform datapath.
+        const int mw = warp - 1;
+        const int spw = ksteps / nmma;       // k16 steps of a stage issued by each warp
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
         const uint32_t smem0 = __reduce_or_sync(0xffffffffu, smem_u32(smem));
-        const int ksteps = BLOCK_K / 16;
         int stage = 0;
         uint32_t phase = 0;
         uint32_t local = 0;
-        if (lane == 0)
+        if (lane == 0 && mw < nmma)
         for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
             const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
             int nact = p.Cout - n0;
@@ -592,30 +616,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             nact = (nact + 15) & ~15;
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t ab = local & 1;
-            mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+            mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator pair
             tc_fence_after();
-            const uint32_t tmem_d = tmem_u + ab * 128;
+            const uint32_t tmem_d = tmem_u + ab * 256 + (uint32_t)mw * 128;
             uint32_t acc = 0;
             for (int it = 0; it < kiters; ++it) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
-                const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
-                const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
-                               b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
+                // this warp's k16 steps start koff * 32 bytes into the swizzle atom
+                const uint32_t koff = (uint32_t)(mw * spw) * 2u;
+                const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K) + koff, b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K) + koff;
+                const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K) + koff,
+                               b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K) + koff;
                 if (!(P.dbg & 2)) {
                     if (P.passes == 3) {
-                        if (ksteps == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else if (ksteps == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        if (spw == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else if (spw == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                         else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                     } else {
-                        if (ksteps == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else if (ksteps == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        if (spw == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        else if (spw == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                         else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                     }
                 }
                 acc = 1;
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+                umma_commit(&empty_bar[stage]);  // frees the smem slot once both warps' MMAs have retired (barrier count = nmma)
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tmem_full[ab]);
@@ -624,15 +650,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     } else {
         // ================= epilogue: TMEM -> registers -> (warp-private transposition slab) -> fused element-wise -> global
         const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp_id % 4)
-        const int jsub = (warp - 2) >> 2;  // which WCOLS-column slice of the accumulator this warp drains
-        const uint32_t slab = smem_u32(stg + (warp - 2) * SLAB_FLOATS);
-        const EpiRegs er = make_epi_regs(p, P.dbg);
+        const int jsub = (warp - EPI_WARP0) >> 2;  // which WCOLS-column slice of the accumulator this warp drains
+        const uint32_t slab = smem_u32(stg + (warp - EPI_WARP0) * SLAB_FLOATS);
+        const EpiRegs er = make_epi_regs(p, P.dbg, DUAL);
         int act = p.act, epi = p.epi, store = p.store;
         opaque(act); opaque(epi); opaque(store);
         uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
         opaque(tiles_n); opaque(tiles_x); opaque(tiles_y);
-        int Ntile = P.Ntile;
-        opaque(Ntile);
+        int Ntile = P.Ntile, wcw = P.wcw;
+        opaque(Ntile); opaque(wcw);
         uint32_t local = 0;
         for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {   // total_tiles < 2^31 (host-checked)
             const int nt = (int)(t % tiles_n);
@@ -643,23 +669,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * Ntile;
             int ncols = er.Cout - n0;
             if (ncols > Ntile) ncols = Ntile;
-            int wcols = ncols - WCOLS * jsub;
-            if (wcols > WCOLS) wcols = WCOLS;
+            int wcols = ncols - wcw * jsub;
+            if (wcols > wcw) wcols = wcw;
             const uint32_t ab = local & 1;
-            const uint32_t taddr = tmem_base + ab * 128 + ((uint32_t)(q * 32) << 16) + (uint32_t)(WCOLS * jsub);
+            const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(wcw * jsub);
             if constexpr (VEC)
-                epilogue_tile_vec<ACT, EPI>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
-                                            n0 + WCOLS * jsub, wcols, q, lane);
+                epilogue_tile_vec<ACT, EPI, DUAL>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                                            n0 + wcw * jsub, wcols, q, lane);
             else
-                epilogue_tile_rows<ACT, EPI>(er, act, epi, store, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
-                                             n0 + WCOLS * jsub, wcols, q, lane);
+                epilogue_tile_rows<ACT, EPI, DUAL>(er, act, epi, store, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                                             n0 + wcw * jsub, wcols, q, lane);
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
 }
 
@@ -781,10 +807,10 @@ bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int 
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
-template <int ACT, int EPI, bool VEC>
-TcKernel tc_variant() {
+template <int ACT, int EPI, bool VEC, bool DUAL>
+TcKernel tc_variant_d() {
     static bool attr_set = false;   // once per instantiation
-    TcKernel k = conv_tc_kernel<ACT, EPI, VEC>;
+    TcKernel k = conv_tc_kernel<ACT, EPI, VEC, DUAL>;
     if (!attr_set) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set = true;
@@ -792,36 +818,41 @@ TcKernel tc_variant() {
     return k;
 }
 
-// (act, epi, 16-byte path?) -> instantiation; combinations the path never uses share the generic (-1, -1) variant
-TcKernel select_kernel(int act, int epi, bool vec) {
+template <int ACT, int EPI, bool VEC>
+TcKernel tc_variant(bool dual) {
+    return dual ? tc_variant_d<ACT, EPI, VEC, true>() : tc_variant_d<ACT, EPI, VEC, false>();
+}
+
+// (act, epi, 16-byte path?, two MMA warps?) -> instantiation; combinations the path never uses share the generic (-1, -1) variant
+TcKernel select_kernel(int act, int epi, bool vec, bool dual) {
     if (vec) {
         if (epi == RCN_EPI_NONE) {
             switch (act) {
-                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true>();
-                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true>();
-                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true>();
-                case RCN_ACT_GELU: return tc_variant<RCN_ACT_GELU, 0, true>();
-                case RCN_ACT_SIGMOID: return tc_variant<RCN_ACT_SIGMOID, 0, true>();
-                case RCN_ACT_HALF_TANH: return tc_variant<RCN_ACT_HALF_TANH, 0, true>();
-                case RCN_ACT_HSWISH: return tc_variant<RCN_ACT_HSWISH, 0, true>();
-                default: return tc_variant<-1, -1, true>();
+                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true>(dual);
+                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true>(dual);
+                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true>(dual);
+                case RCN_ACT_GELU: return tc_variant<RCN_ACT_GELU, 0, true>(dual);
+                case RCN_ACT_SIGMOID: return tc_variant<RCN_ACT_SIGMOID, 0, true>(dual);
+                case RCN_ACT_HALF_TANH: return tc_variant<RCN_ACT_HALF_TANH, 0, true>(dual);
+                case RCN_ACT_HSWISH: return tc_variant<RCN_ACT_HSWISH, 0, true>(dual);
+                default: return tc_variant<-1, -1, true>(dual);
             }
         }
         if (act == RCN_ACT_NONE) {
             switch (epi) {
-                case RCN_EPI_GDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_GDN, true>();
-                case RCN_EPI_IGDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_IGDN, true>();
-                case RCN_EPI_MUL_AUXP1: return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true>();
-                case RCN_EPI_MULP1_AUX: return tc_variant<RCN_ACT_NONE, RCN_EPI_MULP1_AUX, true>();
-                case RCN_EPI_SIGMOID_GATE: return tc_variant<RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE, true>();
+                case RCN_EPI_GDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_GDN, true>(dual);
+                case RCN_EPI_IGDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_IGDN, true>(dual);
+                case RCN_EPI_MUL_AUXP1: return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true>(dual);
+                case RCN_EPI_MULP1_AUX: return tc_variant<RCN_ACT_NONE, RCN_EPI_MULP1_AUX, true>(dual);
+                case RCN_EPI_SIGMOID_GATE: return tc_variant<RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE, true>(dual);
                 default: break;
             }
         }
-        return tc_variant<-1, -1, true>();
+        return tc_variant<-1, -1, true>(dual);
     }
-    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) return tc_variant<RCN_ACT_NONE, 0, false>();
-    if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) return tc_variant<RCN_ACT_CLAMP01, 0, false>();
-    return tc_variant<-1, -1, false>();
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) return tc_variant<RCN_ACT_NONE, 0, false>(dual);
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) return tc_variant<RCN_ACT_CLAMP01, 0, false>(dual);
+    return tc_variant<-1, -1, false>(dual);
 }
 
 }  // namespace
@@ -914,6 +945,10 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.tiles_y = (P.d.H + TILE_H - 1) / TILE_H;
     const int bk = Cp >= 64 ? 64 : Cp;
     P.bk = bk;
+    // two issuing warps pay off when the K loop is long (3x3: 9+ stages per tile); short loops (1x1) are bound by the epilogue,
+    // which the second accumulator makes more expensive
+    P.nmma = (d->k == 3 && bk >= 32) ? MMA_WARPS : 1;
+    P.wcw = (!ps && nt >= 64 && nt % 32 == 0) ? nt / 2 : WCOLS;
     P.a_bytes = 128 * bk * 2;                          // 16 / 8 / 4 KB
     P.b_bytes = (nt * bk * 2 + 1023) & ~1023;
     const int stage_bytes = (passes == 3 ? 2 : 1) * (P.a_bytes + P.b_bytes);
@@ -942,7 +977,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
                      (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
                      (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
     RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
-    const TcKernel kern = select_kernel(d->act, d->epi, vec);
+    const TcKernel kern = select_kernel(d->act, d->epi, vec, P.nmma == 2);
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
     RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");
