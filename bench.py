@@ -286,9 +286,9 @@ def main():
     ach = kflop / (kms / 1e3) / 1e12        # ALGORITHMIC FLOPs of the convolution (2*k*k*Cin*Cout per output pixel) / time
     issued = work / (kms / 1e3) / 1e12      # what the tensor pipe executed (3 bf16 MMAs per product in the bf16x3 engine)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the one `ncu --set full` capture of THIS launch at
-    # T=2048 (profiles/r1_final_conv_tcgen05_ncu_full.md: 2.161 + 2.109 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
+    # T=2048 (profiles/r1_final_conv_tcgen05_ncu_full.md: 2.150 + 2.109 GB; profiles/r1_conv_fp32_ncu_full.md: 2.155 + 2.102 GB);
     # other tile sizes were not captured.
-    traffic = {("bf16x3", 2048): 4.269627e9, ("fp32", 2048): 4.257296e9}.get((args.engine, T))
+    traffic = {("bf16x3", 2048): 4.259602e9, ("fp32", 2048): 4.257296e9}.get((args.engine, T))
     roofline = {"kernel": kname + " -- 3x3 128->128 @ full res (g_s tail)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
                 "ms_per_launch": kms, "peak_source": peaks["_src"] + ", " + peak_note,
