@@ -13,7 +13,7 @@
 // fp32 -- ~16 mantissa bits, which keeps the 1e-3 parity bar through the ~100-layer path.
 //
 // Warp roles (352 threads): warp 0 = TMA producer (one lane); warps 1-2 = MMA issuers (one lane each; warp 1 also owns the TMEM
-// allocation).  Long-K layers (3x3) split every pipeline stage's k16 steps between the two issuers, each accumulating into its own
+// allocation).  Long-K layers (3x3) alternate their pipeline stages between the two issuers, each accumulating into its own
 // TMEM accumulator -- a single issuing thread, not the tensor pipe, bounded those layers -- and the epilogue adds the two partial
 // accumulators in a fixed order.  Warps 3-10 = epilogue (TMEM lane quarter = warp_id % 4; each warp drains Ntile/2 or 64 columns).
 // mbarrier ring: full[s] (TMA -> MMA warps), empty[s] (tcgen05.commit of every issuer -> TMA), tmem_full[2] (last commits of a
@@ -531,7 +531,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int kiters = p.k * p.k * chunks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], nmma); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], nmma); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -598,11 +598,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // The single thread that issues tcgen05.mma is the bottleneck of every layer with a long K loop: ptxas wraps each UTCHMMA
         // issued from divergent code in an ELECT / PLOP3 / BRA.U.ANY sequence, ~120 cycles per MMA against the 64-90 the tensor
         // pipe needs for M128 x N128 x K16 (ncu: producer waiting on free stages, MMA warp never waiting on data, tensor pipe 56 %
-        // active).  So TWO warps issue: warp 1 the first half of each stage's k16 steps, warp 2 the second half, each into its own
+        // active).  So TWO warps issue -- warp 1 the even pipeline stages of a tile, warp 2 the odd ones -- each into its own
         // TMEM accumulator (the epilogue adds the two in a fixed order).  Everything read from memory is first made warp-uniform
         // (REDUX results live in uniform registers) so that descriptors and addresses stay in the uniform datapath.
         const int mw = warp - 1;
-        const int spw = ksteps / nmma;       // k16 steps of a stage issued by each warp
         const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
         const uint32_t smem0 = __reduce_or_sync(0xffffffffu, smem_u32(smem));
         int stage = 0;
@@ -621,27 +620,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t tmem_d = tmem_u + ab * 256 + (uint32_t)mw * 128;
             uint32_t acc = 0;
             for (int it = 0; it < kiters; ++it) {
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
-                // this warp's k16 steps start koff * 32 bytes into the swizzle atom
-                const uint32_t koff = (uint32_t)(mw * spw) * 2u;
-                const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K) + koff, b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K) + koff;
-                const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K) + koff,
-                               b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K) + koff;
-                if (!(P.dbg & 2)) {
-                    if (P.passes == 3) {
-                        if (spw == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else if (spw == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                    } else {
-                        if (spw == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else if (spw == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                if (nmma == 1 || (it & 1) == mw) {      // with two issuers, pipeline stages alternate between them
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
+                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
+                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
+                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
+                    if (!(P.dbg & 2)) {
+                        if (P.passes == 3) {
+                            if (ksteps == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else if (ksteps == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        } else {
+                            if (ksteps == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else if (ksteps == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        }
                     }
+                    acc = 1;
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once this stage's MMAs have retired
                 }
-                acc = 1;
-                umma_commit(&empty_bar[stage]);  // frees the smem slot once both warps' MMAs have retired (barrier count = nmma)
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
             umma_commit(&tmem_full[ab]);
@@ -947,7 +946,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.bk = bk;
     // two issuing warps pay off when the K loop is long (3x3: 9+ stages per tile); short loops (1x1) are bound by the epilogue,
     // which the second accumulator makes more expensive
-    P.nmma = (d->k == 3 && bk >= 32) ? MMA_WARPS : 1;
+    P.nmma = (d->k == 3) ? MMA_WARPS : 1;   // 9+ stages per tile
     P.wcw = (!ps && nt >= 64 && nt % 32 == 0) ? nt / 2 : WCOLS;
     P.a_bytes = 128 * bk * 2;                          // 16 / 8 / 4 KB
     P.b_bytes = (nt * bk * 2 + 1023) & ~1023;
