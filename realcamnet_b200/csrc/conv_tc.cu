@@ -640,6 +640,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                     }
                     acc = 1;
                     umma_commit(&empty_bar[stage]);  // frees the smem slot once this stage's MMAs have retired
+                } else if (P.stages & 1) {
+                    // With an odd number of stages a slot is consumed alternately by the two issuers.  A warp that skipped the
+                    // other warp's fills could get two phases ahead of a slot's barrier, and a parity wait cannot tell phase n
+                    // from phase n+2 (it would consume stale data): observe every fill in order.  (Even stage counts give every
+                    // slot a fixed owner.)
+                    mbar_wait(&full_bar[stage], phase);
                 }
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
@@ -958,6 +964,8 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     {
         const char* e = getenv("RCN_TC_DEBUG");
         P.dbg = e ? atoi(e) : 0;
+        const char* nm = getenv("RCN_TC_NMMA");      // perf / fault triage: force the number of MMA-issuing warps
+        if (nm && (atoi(nm) == 1 || atoi(nm) == 2)) P.nmma = atoi(nm);
         const char* st = getenv("RCN_TC_STAGES");
         if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
     }

@@ -80,6 +80,30 @@ def test_conv2d_plain_and_activations(dev, engine, case):
         assert rel(y, F.pixel_shuffle(ref, 2).clamp(0, 1)) < CONV_TOL
 
 
+@pytest.mark.parametrize("case", [(1, 256, 256, 128, 128, 3, 1), (1, 512, 512, 128, 128, 3, 2), (1, 192, 320, 64, 64, 3, 1)])
+def test_conv2d_many_tiles_per_sm(dev, case):
+    """Persistent-kernel regression: 3-4 tiles per SM with a 3-stage ring and two MMA-issuing warps (a parity-aliasing race between
+    the issuers once produced wrong results exactly at these sizes while smaller and larger maps passed)."""
+    from realcamnet_b200 import ops
+
+    old = ops.get_engine()
+    ops.set_engine("bf16x3")
+    try:
+        N, H, W, Cin, Cout, k, s = case
+        g = torch.Generator().manual_seed(sum(case))
+        x = torch.randn(N, Cin, H, W, generator=g)
+        w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+        b = torch.randn(Cout, generator=g)
+        pc = ops.pack_weight(w.to(dev), b.to(dev))
+        xn = ops.to_nhwc(x.to(dev))
+        ref = F.leaky_relu(F.conv2d(x, w, b, stride=s, padding=k // 2), 0.1)
+        for _ in range(3):          # the race was timing dependent
+            y = ops.to_nchw(ops.conv2d(xn, pc, stride=s, act=ops.ACT_LRELU, slope=0.1))
+            assert rel(y, ref) < CONV_TOL, case
+    finally:
+        ops.set_engine(old)
+
+
 def test_conv2d_epilogues_and_views(dev, engine):
     from realcamnet_b200 import ops
 

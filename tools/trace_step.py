@@ -22,12 +22,20 @@ eng = sys.argv[2] if len(sys.argv) > 2 else "bf16x3"
 mode = sys.argv[3] if len(sys.argv) > 3 else "forward"
 ops.set_engine(eng)
 dev = torch.device("cuda:0")
-m = raw2bit.raw_compression_tcm_final()
-weights.fill_(m, seed=0)
-m = m.to(dev).eval()
-m.update()
-x = [t.to(dev) for t in inputs.make_inputs(T, seed=1234)]
-run = (lambda: m(x, emit_strings=True)) if mode == "forward" else (lambda: m.compress(x))
+if mode == "gma":      # GMA_Block(dim 80) on a batch-32 T x T token map (BASELINE config 3)
+    from realcamnet_b200 import groupmix
+    m = groupmix.GMA_Block(80, 8)
+    weights.fill_(m, seed=0)
+    m = m.to(dev).eval()
+    xg = torch.randn(32, T * T, 80, device=dev)
+    run = lambda: m(xg, (T, T))
+else:
+    m = raw2bit.raw_compression_tcm_final()
+    weights.fill_(m, seed=0)
+    m = m.to(dev).eval()
+    m.update()
+    x = [t.to(dev) for t in inputs.make_inputs(T, seed=1234)]
+    run = (lambda: m(x, emit_strings=True)) if mode == "forward" else (lambda: m.compress(x))
 for _ in range(2):
     run()
 torch.cuda.synchronize()
