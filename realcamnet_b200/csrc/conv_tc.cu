@@ -527,11 +527,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int pad = p.k >> 1;
     const int ksteps = BLOCK_K / 16;
     constexpr int nmma = DUAL ? MMA_WARPS : 1;
+    // How two issuers share the K loop.  Stages of >= 2 k16 steps: both consume EVERY stage, half of its k16 steps each (slot barriers
+    // count two commits).  Single-step stages (16-channel layers): stages alternate by the GLOBAL stage counter, with an even
+    // ring size (host-enforced) so that every slot has a fixed owner.  Either way no warp ever skips a phase of a barrier it waits
+    // on -- a parity wait cannot tell phase n from phase n+2, and an earlier scheme that alternated stages within a tile produced
+    // stale-slot reads / spin-limit traps at exactly the tile counts where one issuer ran a ring ahead of the other.
+    const bool splitk = DUAL && ksteps >= 2;
     const int chunks = P.Cp / BLOCK_K;
     const int kiters = p.k * p.k * chunks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < P.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], splitk ? 2 : 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], nmma); mbar_init(&tmem_empty[b], EPI_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -607,6 +613,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int stage = 0;
         uint32_t phase = 0;
         uint32_t local = 0;
+        uint32_t gstage = 0;       // stages consumed by this CTA so far (all tiles)
         if (lane == 0 && mw < nmma)
         for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
             const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
@@ -619,33 +626,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             tc_fence_after();
             const uint32_t tmem_d = tmem_u + ab * 256 + (uint32_t)mw * 128;
             uint32_t acc = 0;
-            for (int it = 0; it < kiters; ++it) {
-                if (nmma == 1 || (it & 1) == mw) {      // with two issuers, pipeline stages alternate between them
+            for (int it = 0; it < kiters; ++it, ++gstage) {
+                if (nmma == 1 || splitk || (int)(gstage & 1u) == mw) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
-                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K), b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K);
-                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K),
-                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K);
+                    const uint32_t koff = splitk ? (uint32_t)(mw * (ksteps >> 1)) * 2u : 0u;   // this warp's k16 steps (32 B each)
+                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K) + koff, b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K) + koff;
+                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K) + koff,
+                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K) + koff;
+                    const int spw = splitk ? (ksteps >> 1) : ksteps;
                     if (!(P.dbg & 2)) {
                         if (P.passes == 3) {
-                            if (ksteps == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else if (ksteps == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            if (spw == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else if (spw == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                             else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                         } else {
-                            if (ksteps == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else if (ksteps == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            if (spw == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else if (spw == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                             else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                         }
                     }
                     acc = 1;
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once this stage's MMAs have retired
-                } else if (P.stages & 1) {
-                    // With an odd number of stages a slot is consumed alternately by the two issuers.  A warp that skipped the
-                    // other warp's fills could get two phases ahead of a slot's barrier, and a parity wait cannot tell phase n
-                    // from phase n+2 (it would consume stale data): observe every fill in order.  (Even stage counts give every
-                    // slot a fixed owner.)
-                    mbar_wait(&full_bar[stage], phase);
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once this warp's MMAs on it have retired
                 }
                 if (++stage == P.stages) { stage = 0; phase ^= 1; }
             }
@@ -960,6 +963,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     int stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 512) / stage_bytes;
     if (stages > 12) stages = 12;
     if (stages < 2) stages = 2;
+    if (P.nmma == 2 && bk == 16 && stages > 2) stages &= ~1;   // single-step stages alternate between the issuers: fixed slot owners need an even ring
     P.stages = stages;
     {
         const char* e = getenv("RCN_TC_DEBUG");
