@@ -105,3 +105,35 @@ def test_roundtrip_python_equals_c(rate):
     b = dec.decode(idx[n // 2:])
     assert np.array_equal(np.concatenate([a, b]), sym)
     assert rans.decode_with_indexes(b_py, idx, cdf.tolist(), sizes, offs) == sym.tolist()
+
+
+@pytest.mark.parametrize("rate", ["low", "mid", "high"])
+def test_full_size_roundtrip_native_coder_equals_oracle(rate):
+    """BASELINE config 5 at the config-2 size (5 242 880 symbols = the y latent of a 2048^2 tile): the native C++ coder's stream equals
+    the plain-C oracle's byte for byte, and decode(encode(symbols)) == symbols -- the size-independent properties of the range coder."""
+    import numpy as np
+    import torch
+
+    from oracle import cai, refpath
+    from realcamnet_b200 import entropy_models as em
+
+    n = 320 * 128 * 128
+    g = np.random.default_rng({"low": 11, "mid": 12, "high": 13}[rate])
+    lo, hi = {"low": (0.11, 0.5), "mid": (0.5, 4.0), "high": (4.0, 64.0)}[rate]
+    sigma = np.exp(g.uniform(np.log(lo), np.log(hi), n)).astype(np.float32)
+    sigma[g.random(n) < 0.001] = 256.0
+    sym = np.round(sigma * g.standard_normal(n)).astype(np.int32)
+    out = g.random(n) < 1e-4
+    sym[out] = g.choice([-5000, 5000], size=int(out.sum()))            # bypass-coded outliers
+    gc = cai.GaussianConditional(None)
+    gc.update_scale_table(cai.get_scale_table())
+    idx = gc.build_indexes(torch.from_numpy(sigma)).numpy().astype(np.int32)
+    cdf, sizes, offs = refpath._tables(gc)
+    ours = em.rans_encode(sym, idx, cdf, sizes, offs)
+    assert ours == refpath.encode_stream(sym, idx, gc)
+    d = em.RansDecoder()
+    d.set_stream(ours)
+    assert np.array_equal(d.decode_stream(idx, cdf, sizes, offs), sym)
+    d.close()
+    bits = 8.0 * len(ours) / n
+    assert {"low": 0.0, "mid": 1.0, "high": 4.0}[rate] < bits < {"low": 1.5, "mid": 4.5, "high": 8.5}[rate], bits
