@@ -298,6 +298,37 @@ def main():
                 "step_tflops": world * FLOP_PER_PACKED_POS * T * T * args.steps / (ms / 1e3) / 1e12}
     del a, o
 
+    # ---- second view: the dominant HBM-bound kernel class (1x1 conv 128->128 + LeakyReLU at full resolution, planes in / planes out:
+    # the lens-shading MLP layers, LiteISP.py:363-378).  Algorithmic bytes = operand planes read once + result planes written once.
+    roofline_hbm = None
+    if args.engine != "fp32":
+        try:
+            g1 = torch.Generator().manual_seed(3)
+            pc1 = ops.pack_weight((torch.randn(128, 128, 1, 1, generator=g1) / 11.3).to(dev), torch.randn(128, generator=g1).to(dev))
+            a1 = torch.randn(1, T, T, 128, device=dev)
+            sp1 = ops.split_operand(a1, pc1.cp, passes=3 if args.engine == "bf16x3" else 1)
+            f1 = lambda: ops.conv2d(a1, pc1, act=ops.ACT_LRELU, slope=0.1, presplit=sp1, emit_split=True, keep_fp32=False)
+            for _ in range(3):
+                f1()
+            torch.cuda.synchronize()
+            h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            h0.record()
+            for _ in range(reps):
+                f1()
+            h1.record()
+            torch.cuda.synchronize()
+            hms = h0.elapsed_time(h1) / reps
+            per_el = 8 if args.engine == "bf16x3" else 4          # bf16 hi (+ lo) in, bf16 hi (+ lo) out
+            hbytes = float(T) * T * 128 * per_el
+            hpeak = float(peaks.get("hbm_gbs", 6650.0))
+            roofline_hbm = {"kernel": "conv_tc_kernel -- 1x1 128->128 + LeakyReLU @ full res, operand planes in / out (lens-shading MLP layer)",
+                            "bound": "hbm", "achieved": hbytes / (hms / 1e3) / 1e9, "peak": hpeak, "unit": "GB/s",
+                            "frac": hbytes / (hms / 1e3) / 1e9 / hpeak, "traffic": None, "ms_per_launch": hms,
+                            "algorithmic_bytes_per_launch": hbytes, "peak_source": peaks["_src"] + ", burst copy bandwidth"}
+            del a1, sp1
+        except Exception as e:      # an extra view must never cost the bench line
+            roofline_hbm = {"error": str(e)[:200]}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, dt, cores = run_cpu_reference(args.cpu_tile, 2, 1)
@@ -316,7 +347,7 @@ def main():
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
                 "packed_positions_per_s": value * 0.25e6, "tiles_per_s": value / mp_tile}
         print(json.dumps(line))
     if world > 1:
