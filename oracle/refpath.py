@@ -607,6 +607,22 @@ def liteisp_gfm_lsc_forward(sd, x):
     return conv(sd, "tail.2", F.pixel_shuffle(conv(sd, "tail.0", u1), 2))
 
 
+@torch.no_grad()
+def liteisp_forward(sd, x):
+    """LiteISPNet.forward, LiteISP.py:2385-2412: the GFM_LSC network without colour condition, lens shading and modulation
+    (only x[0], the packed RAW tile, is read)."""
+    raw = x[0]
+    h = conv(sd, "head.0", raw) if "head.0.weight" in sd else conv(sd, "head", raw)
+    d1 = dwt_forward(conv(sd, "down1.2", rca_group(sd, "down1.1", conv(sd, "down1.0", h))))
+    d2 = dwt_forward(rca_group(sd, "down2.1", conv(sd, "down2.0", d1)))
+    d3 = dwt_forward(rca_group(sd, "down3.1", conv(sd, "down3.0", d2)))
+    m = conv(sd, "middle.3", rca_group(sd, "middle.2", rca_group(sd, "middle.1", conv(sd, "middle.0", d3)))) + d3
+    u3 = conv(sd, "up3.2", rca_group(sd, "up3.1", dwt_inverse(m))) + d2
+    u2 = conv(sd, "up2.2", rca_group(sd, "up2.1", dwt_inverse(u3))) + d1
+    u1 = conv(sd, "up1.2", rca_group(sd, "up1.1", dwt_inverse(u2))) + h
+    return conv(sd, "tail.2", F.pixel_shuffle(conv(sd, "tail.0", u1), 2))
+
+
 # ----------------------------------------------------------------------------- GroupMix
 def _bn(sd, p, x):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],

@@ -158,3 +158,40 @@ class LiteISPNet_GFM_LSC(nn.Module):
         u1 = self.up1._f(u2, res=h)
         t = self.tail[0]._f(u1, store=ops.STORE_PS2)
         return self.tail[2]._f(t, store=ops.STORE_NCHW)
+
+
+class LiteISPNet(nn.Module):
+    """models/LiteISP.py:2322-2412: the plain LiteISP UNet -- LiteISPNet_GFM_LSC without colour condition, lens shading and
+    modulation blocks (ch_1 = 64).  forward(x) reads x[0], the packed RAW tile (N,4,H,W), and returns (N,3,2H,2W)."""
+
+    def __init__(self):
+        super().__init__()
+        ch_1, ch_2, ch_3, n_blocks = 64, 128, 128, 4
+        self.head = N.seq(N.conv(4, ch_1, mode='C'))
+        self.down1 = N.seq(N.conv(ch_1, ch_1, mode='C'), N.RCAGroup(in_channels=ch_1, out_channels=ch_1, nb=n_blocks),
+                           N.conv(ch_1, ch_1, mode='C'), N.DWTForward(ch_1))
+        self.down2 = N.seq(N.conv(ch_1 * 4, ch_1, mode='C'), N.RCAGroup(in_channels=ch_1, out_channels=ch_1, nb=n_blocks),
+                           N.DWTForward(ch_1))
+        self.down3 = N.seq(N.conv(ch_1 * 4, ch_2, mode='C'), N.RCAGroup(in_channels=ch_2, out_channels=ch_2, nb=n_blocks),
+                           N.DWTForward(ch_2))
+        self.middle = N.seq(N.conv(ch_2 * 4, ch_3, mode='C'), N.RCAGroup(in_channels=ch_3, out_channels=ch_3, nb=n_blocks),
+                            N.RCAGroup(in_channels=ch_3, out_channels=ch_3, nb=n_blocks), N.conv(ch_3, ch_2 * 4, mode='C'))
+        self.up3 = N.seq(N.DWTInverse(ch_2 * 4), N.RCAGroup(in_channels=ch_2, out_channels=ch_2, nb=n_blocks),
+                         N.conv(ch_2, ch_1 * 4, mode='C'))
+        self.up2 = N.seq(N.DWTInverse(ch_1 * 4), N.RCAGroup(in_channels=ch_1, out_channels=ch_1, nb=n_blocks),
+                         N.conv(ch_1, ch_1 * 4, mode='C'))
+        self.up1 = N.seq(N.DWTInverse(ch_1 * 4), N.RCAGroup(in_channels=ch_1, out_channels=ch_1, nb=n_blocks),
+                         N.conv(ch_1, ch_1, mode='C'))
+        self.tail = N.seq(N.conv(ch_1, ch_1 * 4, mode='C'), nn.PixelShuffle(upscale_factor=2), N.conv(ch_1, 3, mode='C'))
+
+    def forward(self, x):
+        h = self.head._f(ops.to_nhwc(x[0]))
+        d1 = self.down1._f(h)
+        d2 = self.down2._f(d1)
+        d3 = self.down3._f(d2)
+        m = self.middle._f(d3, res=d3)
+        u3 = self.up3._f(m, res=d2)
+        u2 = self.up2._f(u3, res=d1)
+        u1 = self.up1._f(u2, res=h)
+        t = self.tail[0]._f(u1, store=ops.STORE_PS2)
+        return self.tail[2]._f(t, store=ops.STORE_NCHW)

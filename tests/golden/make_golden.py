@@ -91,6 +91,15 @@ def extra(ref):
     xx = torch.randn(1, 320, 32, 32, generator=torch.Generator().manual_seed(902))
     np.savez_compressed(os.path.join(OUT, "gma_atten.npz"), x=xx.numpy(), out=g(xx).numpy())
 
+    # ---- LiteISPNet, the plain UNet variant (LiteISP.py:2322-2412)
+    m = ref.LiteISP.LiteISPNet().eval()
+    weights.fill_(m, seed=0)
+    x = inputs.make_inputs(256, seed=1237)
+    o = m(x)
+    np.savez_compressed(os.path.join(OUT, "liteisp_plain_T256.npz"), out_sub=o[:, :, ::2, ::2].numpy(),
+                        out_abs_sum=np.float64(o.double().abs().sum()),
+                        weights_abs_sum=np.float64(weights.checksum(m.state_dict())["abs_sum"]))
+
     # ---- TCM, the RGB baseline with the same entropy model (tcm.py:320-637), 256x256
     m = ref.tcm.TCM().eval()
     weights.fill_(m, seed=0)

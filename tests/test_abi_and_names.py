@@ -89,14 +89,16 @@ def test_update_builds_the_oracle_tables():
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference only exists in the authoring container")
-@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200", "tcm", "convgma", "gmaatten", "gmablock"])
+@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200", "tcm", "convgma", "gmaatten", "gmablock", "liteisp_plain"])
 def test_state_dict_names_match_reference(which):
     from oracle import ref_import
 
     ref = ref_import.import_reference()
     from realcamnet_b200 import LiteISP, groupmix, raw2bit, tcm
 
-    if which == "tcm":
+    if which == "liteisp_plain":
+        a, b = ref.LiteISP.LiteISPNet(), LiteISP.LiteISPNet()
+    elif which == "tcm":
         a, b = ref.tcm.TCM(), tcm.TCM()
     elif which == "convgma":
         a, b = ref.raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.), raw2bit.ConvGMABlock(64, 80, 10, drop_path=0.)

@@ -386,6 +386,20 @@ def test_liteisp_matches_oracle_and_fixture(dev, engine, golden_dir):
     assert abs(float(out.double().abs().sum()) - float(gold["out_abs_sum"])) / float(gold["out_abs_sum"]) < 1e-4
 
 
+def test_liteisp_plain_matches_fixture(dev, engine, golden_dir):
+    """LiteISPNet (LiteISP.py:2322-2412) against the fixture the unmodified reference produced."""
+    from realcamnet_b200 import LiteISP
+
+    gold = np.load(os.path.join(golden_dir, "liteisp_plain_T256.npz"))
+    m = LiteISP.LiteISPNet()
+    weights.fill_(m, seed=0)
+    x = inputs.make_inputs(256, seed=1237)
+    out = m.to(dev).eval()([t.to(dev) for t in x])
+    assert tuple(out.shape) == (1, 3, 512, 512)
+    assert rel(out[:, :, ::2, ::2], torch.from_numpy(gold["out_sub"])) < TOL
+    assert abs(float(out.double().abs().sum()) - float(gold["out_abs_sum"])) / float(gold["out_abs_sum"]) < 1e-4
+
+
 @pytest.fixture(scope="module", params=["fp32", "bf16x3"])
 def final_pair(request, dev, golden_dir):
     from realcamnet_b200 import ops as _ops

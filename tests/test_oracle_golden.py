@@ -134,3 +134,16 @@ def test_tcm_matches_reference_fixture(golden_dir):
     assert c["strings"][0][0] == g["y_string"].tobytes() and c["strings"][1][0] == g["z_string"].tobytes()
     d = refpath.tcm_decompress(sd, c["strings"], c["shape"])
     np.testing.assert_array_equal(d["x_hat"][:, :, ::2, ::2].numpy(), g["dec_x_hat_sub"])
+
+
+def test_liteisp_plain_matches_reference_fixture(golden_dir):
+    """LiteISPNet (LiteISP.py:2322-2412), SURVEY 8f-4: the oracle restatement == the unmodified reference."""
+    from realcamnet_b200 import LiteISP
+
+    g = np.load(os.path.join(golden_dir, "liteisp_plain_T256.npz"))
+    m = LiteISP.LiteISPNet()
+    weights.fill_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert abs(weights.checksum(sd)["abs_sum"] - float(g["weights_abs_sum"])) < 1e-3
+    o = refpath.liteisp_forward(sd, inputs.make_inputs(256, seed=1237))
+    np.testing.assert_array_equal(o[:, :, ::2, ::2].numpy(), g["out_sub"])
