@@ -112,7 +112,7 @@ def run_cpu_reference(T, steps, warmup):
     so the thread count is probed (all cores, 32, 16) on the warm-up pass and the fastest is used and reported."""
     import torch
 
-    from oracle import inputs, weights
+    from realcamnet_b200 import synthetic as inputs, synthetic as weights
     from realcamnet_b200 import raw2bit  # parameter names/shapes only; nothing of it runs in this leg
 
     cores = os.cpu_count() or 1
@@ -177,7 +177,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from oracle import inputs, weights          # seeded synthetic inputs / deterministic weights only
+    from realcamnet_b200 import synthetic as inputs, synthetic as weights    # seeded inputs / name-keyed weights (not the oracle)
     from realcamnet_b200 import ops, raw2bit
 
     if not torch.cuda.is_available():

@@ -17,5 +17,6 @@ Contents
 ``ref_import.py`` imports the *unmodified* reference from /root/reference (only in
                   the authoring container) behind stub modules, to validate the
                   restatement and to generate tests/golden fixtures
-``weights.py``    name-keyed deterministic weight initialisation shared by fixtures
+``weights.py`` / ``inputs.py``  re-exports of realcamnet_b200/synthetic.py (seeded inputs and name-keyed deterministic
+                  weights live outside this package so that bench.py and the tools never import it)
 """

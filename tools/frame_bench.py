@@ -18,7 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from oracle import weights
+from realcamnet_b200 import synthetic as weights
 from realcamnet_b200 import container, frame, raw2bit, tiler
 from realcamnet_b200 import dist as rdist
 

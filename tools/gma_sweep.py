@@ -14,7 +14,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import weights
+from realcamnet_b200 import synthetic as weights
 from realcamnet_b200 import groupmix, ops
 
 dev = torch.device("cuda:0")

@@ -2,7 +2,7 @@
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import inputs, weights
+from realcamnet_b200 import synthetic as inputs, synthetic as weights
 from realcamnet_b200 import ops, raw2bit
 
 dev = torch.device("cuda:0")

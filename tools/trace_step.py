@@ -14,7 +14,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from oracle import inputs, weights
+from realcamnet_b200 import synthetic as inputs, synthetic as weights
 from realcamnet_b200 import _C, ops, raw2bit
 
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
