@@ -215,6 +215,25 @@ struct rcn_rans_decoder {
     std::vector<uint32_t> words;
     size_t pos;
     uint64_t x;
+    // per-CDF-row search accelerator, built on first use of a row: lut[b] = symbol whose interval holds cumulative value b << 8
+    const int32_t* lut_cdfs = nullptr;
+    int lut_stride = 0;
+    std::vector<std::vector<uint16_t>> lut;
+    const uint16_t* row_lut(const int32_t* cdfs, int stride, int ci, const int32_t* row, int size) {
+        if (cdfs != lut_cdfs || stride != lut_stride) { lut.clear(); lut_cdfs = cdfs; lut_stride = stride; }
+        if ((size_t)ci >= lut.size()) lut.resize((size_t)ci + 1);
+        std::vector<uint16_t>& t = lut[(size_t)ci];
+        if (t.empty()) {
+            t.resize(256);
+            int sym = 0;
+            for (int b = 0; b < 256; ++b) {
+                const int32_t cum = b << 8;
+                while (sym + 2 < size && row[sym + 1] <= cum) ++sym;
+                t[(size_t)b] = (uint16_t)sym;
+            }
+        }
+        return t.data();
+    }
     inline void refill() {
         if (x < kLow) { x = (x << 32) | (pos < words.size() ? words[pos] : 0u); ++pos; }
     }
@@ -253,9 +272,9 @@ extern "C" int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long
         const int32_t* row = cdfs + (long long)ci * cdf_stride;
         const int size = cdf_sizes[ci], sentinel = size - 2;
         const uint32_t cum = (uint32_t)(d->x & 0xFFFFu);
-        // first entry strictly greater than cum, minus one (rows are strictly increasing)
-        const int32_t* it = std::upper_bound(row, row + size, (int32_t)cum);
-        const int s = (int)(it - row) - 1;
+        // symbol s with row[s] <= cum < row[s+1] (rows are strictly increasing): start from the 256-bucket table, walk forward
+        int s = d->row_lut(cdfs, cdf_stride, ci, row, size)[cum >> 8];
+        while (row[s + 1] <= (int32_t)cum) ++s;
         const uint32_t start = (uint32_t)row[s], freq = (uint32_t)(row[s + 1] - row[s]);
         d->x = (uint64_t)freq * (d->x >> kProbBits) + cum - start;
         d->refill();
