@@ -42,3 +42,49 @@ def test_container_roundtrip_and_errors():
     merged = frame.merge_containers([a, b])
     h3, t3 = container.unpack(merged)
     assert h3 == hdr and t3 == t2
+
+
+class _StubCodec(torch.nn.Module):
+    """Stands in for raw_compression_tcm_final in the HOST-logic test below: compress() serialises the tile and its coordinate map,
+    decompress() returns the tile's first three channels upsampled x2 -- enough to check tile order, padding, coordinates, container
+    and stitching of realcamnet_b200.frame without a GPU."""
+
+    def __init__(self):
+        super().__init__()
+        self.p = torch.nn.Parameter(torch.zeros(1))
+        self.coords = {}
+
+    def compress(self, x):
+        raw, cond, coord = x
+        assert tuple(cond.shape) == (1, 4, 256, 256) and tuple(coord.shape) == (1, 2) + tuple(raw.shape[2:])
+        y = raw.contiguous().numpy().tobytes()
+        z = coord[0, :, [0, -1]][:, :, [0, -1]].contiguous().numpy().tobytes()      # the four corner coordinates
+        return {"strings": [[y], [z]], "shape": torch.Size([raw.shape[2] // 64, raw.shape[3] // 64])}
+
+    def decompress(self, strings, shape):
+        T = int(shape[0]) * 64
+        raw = torch.frombuffer(bytearray(strings[0][0]), dtype=torch.float32).reshape(1, 4, T, T)
+        return {"x_hat": raw[:, :3].repeat_interleave(2, -1).repeat_interleave(2, -2)}
+
+
+def test_frame_host_logic_with_stub_codec():
+    g = torch.Generator().manual_seed(8)
+    fr = torch.rand(4, 300, 600, generator=g)                      # 2 x 3 grid of 256-tiles, ragged right and bottom
+    m = _StubCodec()
+    blob = frame.compress_frame(m, fr, 256)
+    parts = [frame.compress_frame(m, fr, 256, tile_indices=idx) for idx in ([0, 3], [4, 1], [5, 2])]   # three "ranks", any order
+    assert frame.merge_containers(parts) == blob
+    hdr, recs = container.unpack(blob)
+    assert (hdr.H, hdr.W, hdr.tile, hdr.ny, hdr.nx, hdr.n_tiles) == (300, 600, 256, 2, 3, 6)
+    # per-tile coordinate maps cover [-1, 1] over the PADDED frame: corners of tile 0 and tile 5
+    c0 = torch.frombuffer(bytearray(recs[0].z), dtype=torch.float32).reshape(2, 2, 2)
+    c5 = torch.frombuffer(bytearray(recs[5].z), dtype=torch.float32).reshape(2, 2, 2)
+    assert float(c0[0, 0, 0]) == -1.0 and float(c0[1, 0, 0]) == -1.0
+    assert abs(float(c5[0, 1, 1]) - 1.0) < 1e-6 and abs(float(c5[1, 1, 1]) - 1.0) < 1e-6
+    out = frame.decompress_frame(m, blob)
+    assert tuple(out.shape) == (1, 3, 600, 1200)
+    assert torch.equal(out[0], fr[:3].repeat_interleave(2, -1).repeat_interleave(2, -2))
+    with pytest.raises(ValueError):
+        frame.decompress_frame(m, parts[0])                         # a partial container cannot be decoded to a frame
+    with pytest.raises(ValueError):
+        frame.compress_frame(m, fr, 192)                            # tile side must be a multiple of 128 and >= 256
