@@ -204,8 +204,9 @@ long long rcn_rans_encode_packed(const uint32_t* packed, const uint32_t* raw, co
 /* RansDecoder.set_stream / decode_stream (models/raw2bit.py:1996-1997,2013): state persists across calls */
 typedef struct rcn_rans_decoder rcn_rans_decoder;
 rcn_rans_decoder* rcn_rans_decoder_create(const uint8_t* stream, long long nbytes);
+/* indexes[i] must lie in [0, n_rows); a corrupt / truncated stream or an out-of-range index returns RCN_ERR_INVALID */
 int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long long n, const int32_t* cdfs, int cdf_stride,
-                    const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out);
+                    int n_rows, const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out);
 void rcn_rans_decoder_destroy(rcn_rans_decoder* d);
 /* compressai._CXX.pmf_to_quantized_cdf: cdf has n+1 entries (used by update(), models/raw2bit.py:1759-1764) */
 int rcn_pmf_to_quantized_cdf(const float* pmf, int n, int precision, int32_t* cdf);

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "rcn_rans_encode": (_L, [_P, _P, _L, _P, _I, _P, _P, _P, _L]),
     "rcn_rans_encode_packed": (_L, [_P, _P, _P, _L, _P, _L]),
     "rcn_rans_decoder_create": (_P, [_P, _L]),
-    "rcn_rans_decode": (_I, [_P, _P, _L, _P, _I, _P, _P, _P]),
+    "rcn_rans_decode": (_I, [_P, _P, _L, _P, _I, _I, _P, _P, _P]),
     "rcn_rans_decoder_destroy": (None, [_P]),
     "rcn_pmf_to_quantized_cdf": (_I, [_P, _I, _I, _P]),
 }

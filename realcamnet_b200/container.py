@@ -4,7 +4,7 @@ The reference returns bare Python lists -- ``{"strings": [[y_bytes], [z_bytes]],
 (models/raw2bit.py:1960) -- which cannot be stored or sent.  This module defines the length-prefixed wire format the frame
 pipeline uses; it is host-side byte packing only (little-endian, no alignment padding):
 
-  header   "RCNB" | u16 version=1 | u16 model_id | u32 frame_H | u32 frame_W | u16 tile | u16 grid_ny | u16 grid_nx | u32 n_tiles
+  header   "RCNB" | u16 version=2 | u16 model_id | u32 frame_H | u32 frame_W | u16 tile | u16 grid_ny | u16 grid_nx | u32 n_tiles
   per tile u32 index | u16 z_h | u16 z_w | u32 len_y | u32 len_z | y bytes | z bytes
   trailer  u32 CRC-32 of everything before it
 
@@ -17,7 +17,7 @@ import zlib
 from typing import Dict, List, NamedTuple, Tuple
 
 MAGIC = b"RCNB"
-VERSION = 1
+VERSION = 2       # v2: tile coordinate maps are normalised by the unpadded frame size (tiler.tile_coords)
 _HEADER = struct.Struct("<4sHHIIHHHI")
 _TILE = struct.Struct("<IHHII")
 
@@ -71,7 +71,7 @@ def unpack(blob: bytes) -> Tuple[FrameHeader, Dict[int, TileStreams]]:
             raise ValueError("container truncated inside a tile record")
         index, zh, zw, ly, lz = _TILE.unpack_from(body, off)
         off += _TILE.size
-        if off + ly + lz > len(body) or index in tiles:
+        if off + ly + lz > len(body) or index in tiles or index >= max(ny * nx, 1):
             raise ValueError("container tile record is inconsistent")
         tiles[index] = TileStreams(index, (zh, zw), body[off:off + ly], body[off + ly:off + ly + lz])
         off += ly + lz

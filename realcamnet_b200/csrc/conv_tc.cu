@@ -815,15 +815,51 @@ bool make_w_map(CUtensorMap* m, const void* base, int Cout, long long Ktot, int 
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams);
 
+constexpr int MAX_DEVICES = 64;
+inline int current_device() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
+}
+
 template <int ACT, int EPI, bool VEC, bool DUAL>
 TcKernel tc_variant_d() {
-    static bool attr_set = false;   // once per instantiation
+    static bool attr_set[MAX_DEVICES] = {};   // function attributes are per device: once per (instantiation, device)
     TcKernel k = conv_tc_kernel<ACT, EPI, VEC, DUAL>;
-    if (!attr_set) {
+    const int dev = current_device();
+    if (!attr_set[dev]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        attr_set = true;
+        attr_set[dev] = true;
     }
     return k;
+}
+
+// perf / fault triage knobs, read from the environment ONCE per process (not on every launch)
+struct TcDebugEnv {
+    int dbg = 0, nmma = 0, stages = 0;
+    TcDebugEnv() {
+        const char* e = getenv("RCN_TC_DEBUG");
+        dbg = e ? atoi(e) : 0;
+        const char* nm = getenv("RCN_TC_NMMA");      // force the number of MMA-issuing warps
+        if (nm && (atoi(nm) == 1 || atoi(nm) == 2)) nmma = atoi(nm);
+        const char* st = getenv("RCN_TC_STAGES");
+        if (st && atoi(st) >= 2) stages = atoi(st);
+    }
+};
+const TcDebugEnv& tc_debug_env() {
+    static const TcDebugEnv env;
+    return env;
+}
+
+int sm_count() {
+    static int sms[MAX_DEVICES] = {};
+    const int dev = current_device();
+    if (!sms[dev]) {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        sms[dev] = n > 0 ? n : 148;
+    }
+    return sms[dev];
 }
 
 template <int ACT, int EPI, bool VEC>
@@ -966,12 +1002,10 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     if (P.nmma == 2 && bk == 16 && stages > 2) stages &= ~1;   // single-step stages alternate between the issuers: fixed slot owners need an even ring
     P.stages = stages;
     {
-        const char* e = getenv("RCN_TC_DEBUG");
-        P.dbg = e ? atoi(e) : 0;
-        const char* nm = getenv("RCN_TC_NMMA");      // perf / fault triage: force the number of MMA-issuing warps
-        if (nm && (atoi(nm) == 1 || atoi(nm) == 2)) P.nmma = atoi(nm);
-        const char* st = getenv("RCN_TC_STAGES");
-        if (st && atoi(st) >= 2 && atoi(st) <= stages) P.stages = stages = atoi(st);
+        const TcDebugEnv& env = tc_debug_env();
+        P.dbg = env.dbg;
+        if (env.nmma) P.nmma = env.nmma;
+        if (env.stages && env.stages <= stages) P.stages = stages = env.stages;
     }
     const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 512;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
@@ -992,13 +1026,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
     RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");
-    static int num_sms = 0;
-    if (!num_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (num_sms <= 0) num_sms = 148;
-    }
+    const int num_sms = sm_count();
     const unsigned grid = (unsigned)(P.total_tiles < num_sms ? P.total_tiles : num_sms);  // persistent: one CTA per SM
     kern<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, mw_hi, mw_lo, P);
     count_launch();

@@ -261,16 +261,26 @@ extern "C" rcn_rans_decoder* rcn_rans_decoder_create(const uint8_t* stream, long
 
 extern "C" void rcn_rans_decoder_destroy(rcn_rans_decoder* d) { delete d; }
 
+// The stream and the indexes are untrusted input (a bitstream container can be crafted): every table row index is range-checked,
+// the bypass length is bounded by what a 32-bit payload needs, and reading past the end of the stream is an error.
 extern "C" int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long long n, const int32_t* cdfs, int cdf_stride,
-                               const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out) {
-    if (!d || !indexes || !cdfs || !cdf_sizes || !offsets || !out || n < 0) {
+                               int n_rows, const int32_t* cdf_sizes, const int32_t* offsets, int32_t* out) {
+    if (!d || !indexes || !cdfs || !cdf_sizes || !offsets || !out || n < 0 || n_rows <= 0 || cdf_stride < 2) {
         rcn::set_error("rcn_rans_decode: bad arguments");
         return RCN_ERR_INVALID;
     }
     for (long long i = 0; i < n; ++i) {
         const int ci = indexes[i];
+        if (ci < 0 || ci >= n_rows) {
+            rcn::set_error("rcn_rans_decode: index %d at position %lld is outside the %d-row CDF table", ci, i, n_rows);
+            return RCN_ERR_INVALID;
+        }
         const int32_t* row = cdfs + (long long)ci * cdf_stride;
         const int size = cdf_sizes[ci], sentinel = size - 2;
+        if (size < 2 || size > cdf_stride) {
+            rcn::set_error("rcn_rans_decode: CDF row %d has size %d (stride %d)", ci, size, cdf_stride);
+            return RCN_ERR_INVALID;
+        }
         const uint32_t cum = (uint32_t)(d->x & 0xFFFFu);
         // symbol s with row[s] <= cum < row[s+1] (rows are strictly increasing): start from the 256-bucket table, walk forward
         int s = d->row_lut(cdfs, cdf_stride, ci, row, size)[cum >> 8];
@@ -282,13 +292,21 @@ extern "C" int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long
         if (s == sentinel) {
             uint32_t digit = d->nibble();
             int nb = (int)digit;
-            while (digit == kNibbleMax) { digit = d->nibble(); nb += (int)digit; }
+            while (digit == kNibbleMax && nb <= 8) { digit = d->nibble(); nb += (int)digit; }
+            if (nb > 8) {   // a 32-bit payload needs at most 8 nibbles
+                rcn::set_error("rcn_rans_decode: corrupt stream (bypass length %d nibbles at position %lld)", nb, i);
+                return RCN_ERR_INVALID;
+            }
             uint32_t raw = 0;
             for (int j = 0; j < nb; ++j) raw |= d->nibble() << (j * kNibbleBits);
             v = (int)(raw >> 1);
             v = (raw & 1u) ? -v - 1 : v + sentinel;
         }
         out[i] = v + offsets[ci];
+    }
+    if (d->pos > d->words.size()) {
+        rcn::set_error("rcn_rans_decode: truncated or corrupt stream (read %zu words past its end)", d->pos - d->words.size());
+        return RCN_ERR_INVALID;
     }
     return RCN_OK;
 }

@@ -118,7 +118,7 @@ class RansDecoder:
         indexes = _i32(indexes).reshape(-1)
         cdf, cdf_length, offset = _i32(cdf), _i32(cdf_length).reshape(-1), _i32(offset).reshape(-1)
         out = np.empty(indexes.size, dtype=np.int32)
-        _C.check(_C.lib().rcn_rans_decode(self._h, _ip(indexes), indexes.size, _ip(cdf), cdf.shape[1], _ip(cdf_length),
+        _C.check(_C.lib().rcn_rans_decode(self._h, _ip(indexes), indexes.size, _ip(cdf), cdf.shape[1], cdf.shape[0], _ip(cdf_length),
                                           _ip(offset), _ip(out)), "rcn_rans_decode")
         return out
 
@@ -157,8 +157,9 @@ class EntropyModel(nn.Module):
         if self._offset.numel() == 0:
             raise RuntimeError("call update() before compress()/decompress() (models/raw2bit.py:1759-1764)")
         key = (self._quantized_cdf.data_ptr(), self._quantized_cdf._version)
-        if self._host_tables is None or self._host_tables[0] != key:
-            self._host_tables = (key, (_i32(self._quantized_cdf), _i32(self._cdf_length).reshape(-1), _i32(self._offset).reshape(-1)))
+        if self._host_tables is None or self._host_tables[0] != key or self._host_tables[2] is not self._quantized_cdf:
+            self._host_tables = (key, (_i32(self._quantized_cdf), _i32(self._cdf_length).reshape(-1), _i32(self._offset).reshape(-1)),
+                                 self._quantized_cdf)
         return self._host_tables[1]
 
     def _pmf_to_cdf(self, pmf, tail_mass, pmf_length, max_length):

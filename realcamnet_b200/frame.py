@@ -64,14 +64,24 @@ def compress_frame(model, frame: torch.Tensor, tile: int, cond: Optional[torch.T
     return container.pack(container.FrameHeader(model_id, H, W, tile, ny, nx, len(recs)), recs)
 
 
-def decompress_frame(model, blob: bytes) -> torch.Tensor:
-    """RCNB container -> (1,3,2H,2W) sRGB frame in [0,1] (padding removed).  Every tile of the grid must be present."""
+def decompress_frame(model, blob: bytes, model_id: int = 0) -> torch.Tensor:
+    """RCNB container -> (1,3,2H,2W) sRGB frame in [0,1] (padding removed).  Every tile of the grid must be present.
+    The container is untrusted input (CRC-32 is not authentication): geometry fields are validated before anything is
+    allocated from them."""
     hdr, tiles = container.unpack(blob)
+    if hdr.model_id != model_id:
+        raise ValueError(f"container was written by model {hdr.model_id}, this decoder is model {model_id}")
+    if hdr.tile % 128 or hdr.tile < 256 or hdr.tile > 8192:
+        raise ValueError(f"container tile side {hdr.tile} is not a valid codec tile")
+    if (hdr.ny, hdr.nx) != tiler.tile_grid(hdr.H, hdr.W, hdr.tile) or hdr.H <= 0 or hdr.W <= 0:
+        raise ValueError("container grid does not match its frame size")
     if len(tiles) != hdr.ny * hdr.nx:
         raise ValueError(f"container holds {len(tiles)} of {hdr.ny * hdr.nx} tiles")
     outs = []
     for t in range(hdr.ny * hdr.nx):
         rec = tiles[t]
+        if tuple(rec.shape) != (hdr.tile // 64, hdr.tile // 64):
+            raise ValueError(f"tile {t}: hyper-latent shape {rec.shape} does not belong to a {hdr.tile}-tile")
         outs.append(model.decompress([[rec.y], [rec.z]], rec.shape)["x_hat"])
     return tiler.stitch(outs, (hdr.H, hdr.W, hdr.ny, hdr.nx), hdr.tile, scale=2)
 

@@ -30,9 +30,18 @@ def _ptr(t):
     return _vp(t.data_ptr()) if t is not None else _vp(0)
 
 
+def _on_current_device(t, name="tensor"):
+    """Kernels are launched on the CURRENT device's current stream (one process per GPU): a tensor of another device would be
+    dereferenced by the wrong GPU, so that is an error here rather than an illegal address (or a silent peer access) later."""
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"{name}: tensor lives on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()} "
+                           "(use torch.cuda.set_device / torch.cuda.device around the call)")
+
+
 def _chk(t, name="tensor"):
     if not (t.is_cuda and t.dtype == torch.float32):
         raise TypeError(f"{name}: expected a CUDA float32 tensor, got {t.device} {t.dtype}")
+    _on_current_device(t, name)
 
 
 def geom(t, name="tensor"):
@@ -148,12 +157,20 @@ def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
 def pack(module) -> PackedConv:
     """Cached packing of an nn.Conv2d / nn.Linear parameter holder (re-packed if the weights change)."""
     w, b = module.weight, getattr(module, "bias", None)
-    key = (w.data_ptr(), w._version, None if b is None else (b.data_ptr(), b._version), str(w.device))
+    # identity (not address) of the source tensors + their in-place version counters: a replaced parameter that happens to
+    # reuse a freed address at version 0 must not hit
+    key = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()), str(w.device))
     hit = _pack_cache.get(module)
-    if hit is not None and hit[0] == key:
+    if hit is not None and hit[0] == key and hit[2]() is w and (b is None or hit[3]() is b):
         return hit[1]
+    if isinstance(module, torch.nn.Conv2d):
+        k = module.kernel_size[0]
+        if (module.padding[0] != k // 2 or module.padding[1] != k // 2 or module.dilation != (1, 1) or module.groups != 1 or
+                module.kernel_size[0] != module.kernel_size[1] or module.stride[0] != module.stride[1] or
+                module.padding_mode != "zeros"):
+            raise NotImplementedError(f"conv engine: only square kernels with padding k//2, dilation 1, groups 1 are on the path, got {module}")
     pc = pack_weight(w, b)
-    _pack_cache[module] = (key, pc)
+    _pack_cache[module] = (key, pc, weakref.ref(w), weakref.ref(b) if b is not None else None)
     return pc
 
 
@@ -257,6 +274,7 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
             raise ValueError("conv2d: x=None needs operand planes from a previous layer, emitted for this layer's stride")
         N, H, W = presplit.key[1:4]
         Cin, ldx = presplit.key[4], 0
+        _on_current_device(presplit.hi, "conv2d.presplit")
     else:
         N, H, W, Cin, ldx = geom(x, "conv2d.x")
     if Cin != pc.cin:

@@ -197,7 +197,26 @@ class SliceCodecModel(CompressionModel):
     entropy kernels and the range coder hand-off.  Sub-classes provide the parameter-holding sub-modules under the reference
     names (h_a, h_mean_s, h_scale_s, atten_*, cc_*_transforms, lrp_transforms, entropy_bottleneck, gaussian_conditional)."""
 
+    def _invalidate_graphs(self):
+        """Captured graphs hold raw pointers to packed weights, GDN / entropy-bottleneck parameters and the CDF tables: whatever
+        replaces or rewrites those must drop them (StageRunner additionally fingerprints in-place edits, see _state_version)."""
+        self.__dict__.pop("_graph_cache", None)
+        self.__dict__.pop("_graph_tensors", None)
+
+    def _state_version(self):
+        """Cheap fingerprint of every parameter / buffer: in-place writes (optimizer steps, copy_, load_state_dict) bump
+        torch's per-tensor version counter; rebinding goes through update() / _apply(), which invalidate explicitly."""
+        ts = self.__dict__.get("_graph_tensors")
+        if ts is None:
+            ts = self.__dict__["_graph_tensors"] = [t for t in list(self.parameters()) + list(self.buffers())]
+        return sum(t._version for t in ts)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate_graphs()
+        return super()._apply(fn, *args, **kwargs)
+
     def update(self, scale_table=None, force=False):
+        self._invalidate_graphs()
         if scale_table is None:
             scale_table = get_scale_table()
         updated = self.gaussian_conditional.update_scale_table(scale_table, force=force)
@@ -219,6 +238,7 @@ class SliceCodecModel(CompressionModel):
             key = f"entropy_bottleneck.{name}"
             if key in state_dict and getattr(eb, name).numel() == 0:
                 getattr(eb, name).resize_(state_dict[key].size())
+        self._invalidate_graphs()
         return super().load_state_dict(state_dict, strict=strict)
 
     def _scale_table_dev(self):
@@ -320,7 +340,7 @@ class SliceCodecModel(CompressionModel):
     def enable_cuda_graphs(self, flag=True):
         """Replay forward()/compress() as CUDA graphs (see StageRunner for the aliasing rule of the returned tensors)."""
         self._use_graphs = bool(flag)
-        self.__dict__.pop("_graph_cache", None)
+        self._invalidate_graphs()
         return self
 
     # ------------------------------------------------------------------------------ shared stages
@@ -402,9 +422,14 @@ class StageRunner:
         if getattr(model, "_use_graphs", False):
             full = (key, ops.get_engine()) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
             cache = model.__dict__.setdefault("_graph_cache", {})
+            ver = model._state_version()
+            if cache.get("_version") != ver:        # weights / tables were edited in place since the graphs were captured
+                cache.clear()
+                cache["_version"] = ver
             self.entry = cache.get(full)
             if self.entry is None:
                 self.entry = cache[full] = self._capture()
+                cache["_version"] = model._state_version()   # lazy initialisation during the warm-up pass may touch buffers
         self.A = None
 
     def _capture(self):

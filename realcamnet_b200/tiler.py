@@ -28,13 +28,14 @@ def split_frame(frame: torch.Tensor, tile: int) -> Tuple[torch.Tensor, Tuple[int
 
 
 def tile_coords(meta: Tuple[int, int, int, int], tile: int, index: int, device=None) -> torch.Tensor:
-    """(1,2,tile,tile) normalised pixel-centre coordinates of tile `index` inside its (padded) frame:
-    channel 0 = x in [-1,1] along W, channel 1 = y in [-1,1] along H."""
+    """(1,2,tile,tile) normalised pixel-centre coordinates of tile `index` inside its frame:
+    channel 0 = x in [-1,1] along W, channel 1 = y in [-1,1] along H, normalised by the REAL
+    (unpadded) frame size -- like the reference's inputs, which span [-1,1] over the actual image -- so the optical centre stays
+    at (0,0) whatever the tile size; zero-padded pixels simply fall outside [-1,1].  (RCNB container version 2 convention.)"""
     H, W, ny, nx = meta
     ty, tx = divmod(index, nx)
-    Hp, Wp = ny * tile, nx * tile
-    ys = (torch.arange(tile, device=device, dtype=torch.float32) + ty * tile) / max(Hp - 1, 1) * 2 - 1
-    xs = (torch.arange(tile, device=device, dtype=torch.float32) + tx * tile) / max(Wp - 1, 1) * 2 - 1
+    ys = (torch.arange(tile, device=device, dtype=torch.float32) + ty * tile) / max(H - 1, 1) * 2 - 1
+    xs = (torch.arange(tile, device=device, dtype=torch.float32) + tx * tile) / max(W - 1, 1) * 2 - 1
     yy, xx = torch.meshgrid(ys, xs, indexing="ij")
     return torch.stack([xx, yy])[None].contiguous()
 

@@ -55,6 +55,45 @@ def test_host_range_coder_matches_oracle_bytes():
     assert em.rans_encode(np.zeros(0, np.int32), np.zeros(0, np.int32), cdf, sizes, offs) == bytes([0, 0, 0, 0x80, 0, 0, 0, 0])
 
 
+def test_host_decoder_rejects_corrupt_input():
+    """The decoder treats the stream and the indexes as untrusted: out-of-range table rows, truncated streams and
+    impossible bypass lengths return an error instead of reading out of bounds."""
+    import numpy as np
+
+    from oracle import cai, refpath
+    from realcamnet_b200 import entropy_models as em
+
+    gc = cai.GaussianConditional(None)
+    gc.update_scale_table(cai.get_scale_table())
+    cdf, sizes, offs = refpath._tables(gc)
+    g = np.random.default_rng(11)
+    n = 4000
+    idx = g.integers(0, 64, n).astype(np.int32)
+    sym = np.round(g.standard_normal(n) * 3).astype(np.int32)
+    sym[::97] = 40000                                              # escapes
+    stream = em.rans_encode(sym, idx, cdf, sizes, offs)
+    for bad in (np.array([64], np.int32), np.array([-1], np.int32), np.array([1 << 20], np.int32)):
+        d = em.RansDecoder()
+        d.set_stream(stream)
+        with pytest.raises(RuntimeError, match="outside"):
+            d.decode_stream(bad, cdf, sizes, offs)
+    d = em.RansDecoder()
+    d.set_stream(stream[:len(stream) // 2 // 4 * 4])                # truncated: the decoder runs off the end
+    with pytest.raises(RuntimeError, match="truncated|corrupt"):
+        d.decode_stream(idx, cdf, sizes, offs)
+    # random garbage decodes to *something* or errors out, but never crashes / hangs
+    junk = g.integers(0, 256, 4096, dtype=np.uint8).tobytes()
+    d = em.RansDecoder()
+    d.set_stream(junk)
+    try:
+        d.decode_stream(idx, cdf, sizes, offs)
+    except RuntimeError:
+        pass
+    d = em.RansDecoder()
+    d.set_stream(stream)
+    assert np.array_equal(d.decode_stream(idx, cdf, sizes, offs), sym)
+
+
 def test_native_cdf_quantiser_matches_oracle():
     import numpy as np
 

@@ -76,11 +76,14 @@ def test_frame_host_logic_with_stub_codec():
     assert frame.merge_containers(parts) == blob
     hdr, recs = container.unpack(blob)
     assert (hdr.H, hdr.W, hdr.tile, hdr.ny, hdr.nx, hdr.n_tiles) == (300, 600, 256, 2, 3, 6)
-    # per-tile coordinate maps cover [-1, 1] over the PADDED frame: corners of tile 0 and tile 5
+    # per-tile coordinate maps cover [-1, 1] over the REAL 300 x 600 frame (container v2): corners of tile 0 and tile 5; the
+    # bottom-right corner of the padded grid (pixel 511, 767) lies outside the unit square
     c0 = torch.frombuffer(bytearray(recs[0].z), dtype=torch.float32).reshape(2, 2, 2)
     c5 = torch.frombuffer(bytearray(recs[5].z), dtype=torch.float32).reshape(2, 2, 2)
     assert float(c0[0, 0, 0]) == -1.0 and float(c0[1, 0, 0]) == -1.0
-    assert abs(float(c5[0, 1, 1]) - 1.0) < 1e-6 and abs(float(c5[1, 1, 1]) - 1.0) < 1e-6
+    assert abs(float(c5[0, 1, 1]) - (767 / 599 * 2 - 1)) < 1e-6 and abs(float(c5[1, 1, 1]) - (511 / 299 * 2 - 1)) < 1e-6
+    with pytest.raises(ValueError):
+        frame.decompress_frame(m, blob, model_id=7)                 # written by another model
     out = frame.decompress_frame(m, blob)
     assert tuple(out.shape) == (1, 3, 600, 1200)
     assert torch.equal(out[0], fr[:3].repeat_interleave(2, -1).repeat_interleave(2, -2))

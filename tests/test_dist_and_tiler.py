@@ -22,7 +22,13 @@ def test_tiler_roundtrip_ragged_frame():
     assert tuple(full.shape) == (1, 4, 540, 960)
     assert torch.equal(full[0, :, ::2, ::2], frame)
     c0, c39 = tiler.tile_coords(meta, 64, 0), tiler.tile_coords(meta, 64, 39)
-    assert c0[0, 0, 0, 0] == -1 and c0[0, 1, 0, 0] == -1 and abs(float(c39[0, 0, -1, -1]) - 1) < 1e-6 and abs(float(c39[0, 1, -1, -1]) - 1) < 1e-6
+    # coordinates are normalised by the REAL frame (270 x 480): the last real pixel is +1, padded pixels fall outside [-1, 1],
+    # and the frame centre is (0, 0) whatever the tile size
+    assert c0[0, 0, 0, 0] == -1 and c0[0, 1, 0, 0] == -1
+    assert abs(float(c39[0, 0, 0, 479 - 448]) - 1) < 1e-6 and abs(float(c39[0, 1, 269 - 256, 0]) - 1) < 1e-6
+    assert float(c39[0, 0, -1, -1]) > 1 and float(c39[0, 1, -1, -1]) > 1
+    big = tiler.tile_coords((270, 480, 1, 1), 512, 0)
+    assert torch.allclose(big[0, :, :64, :64], c0[0], atol=1e-6)
     assert rdist.my_tiles(40, 3, 8) == [3, 11, 19, 27, 35]
 
 

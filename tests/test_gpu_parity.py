@@ -239,16 +239,18 @@ def test_small_ops(dev):
 
 
 # ------------------------------------------------------------------------------------------- entropy kernels
-@pytest.mark.parametrize("rate", ["low", "mid", "high"])
-def test_gaussian_conditional_integer_exact(dev, rate):
-    """BASELINE config 5 stand-in: sigma sweep; symbols/indexes/bytes must match the oracle exactly."""
+@pytest.mark.parametrize("rate,shape", [("low", (1, 64, 32, 40)), ("mid", (1, 64, 32, 40)), ("high", (1, 64, 32, 40)),
+                                        ("mid", (1, 320, 128, 128)), ("high", (1, 320, 128, 128))])
+def test_gaussian_conditional_integer_exact(dev, rate, shape):
+    """BASELINE config 5 stand-in: sigma sweep; symbols/indexes/bytes must match the oracle exactly.
+    The (1,320,128,128) cases are the 5 242 880 symbols of one T=2048 tile (the bench configuration)."""
     from oracle import cai
     from realcamnet_b200 import entropy_models as em, ops
     from realcamnet_b200.tcm import get_scale_table
 
     g = torch.Generator().manual_seed({"low": 1, "mid": 2, "high": 3}[rate])
     lo, hi = {"low": (0.11, 0.5), "mid": (0.5, 4.0), "high": (4.0, 64.0)}[rate]
-    N, C, H, W = 1, 64, 32, 40
+    N, C, H, W = shape
     sigma = torch.exp(torch.rand(N, C, H, W, generator=g) * (np.log(hi) - np.log(lo)) + np.log(lo))
     sigma[torch.rand(N, C, H, W, generator=g) < 0.001] = 256.0
     sigma[torch.rand(N, C, H, W, generator=g) < 0.01] = -1.0  # below the 0.11 bound
@@ -579,6 +581,87 @@ def test_batch_and_nonsquare_tiles(dev, engine):
     ref = refpath.final_forward(sd, x)
     assert rel(out["y"], ref["y"]) < TOL
     assert refpath.psnr(out["x_hat"].cpu(), ref["x_hat"]) > 50.0
+
+
+def test_timed_configuration_T2048_matches_oracle(dev):
+    """The configuration bench.py times (one 4x2048x2048 tile, default engine policy, CUDA graphs on) against the oracle at
+    the SAME size: y <= 1e-3 rel, symbol mismatch < 1e-3, x_hat PSNR > 50 dB, and decompress(compress) == forward bit for bit.
+    The oracle pass costs ~20-30 s of host time and ~16 GB of host memory (64x the tiles per SM of the T=256 fixture, 2-4 GB
+    maps, >2^31-byte tensors)."""
+    from realcamnet_b200 import ops, raw2bit
+
+    T = int(os.environ.get("RCN_TEST_BIG_TILE", "2048"))
+    old = ops.get_engine()
+    ops.set_engine(os.environ.get("RCN_CONV_ENGINE", "bf16x3"))
+    try:
+        m = raw2bit.raw_compression_tcm_final()
+        weights.fill_(m, seed=0)
+        sd = cpu_sd(m)
+        m = m.to(dev).eval()
+        m.update()
+        m.enable_cuda_graphs(True)
+        x = inputs.make_inputs(T, seed=1234)
+        xd = [t.to(dev) for t in x]
+        for _ in range(2):      # capture + one pure replay
+            out = m(xd, emit_strings=True)
+        y = out["y"].cpu()
+        means = out["para"]["means"].cpu()
+        x_hat = out["x_hat"].cpu()
+        strings, shape = out["strings"], out["shape"]
+        d = m.decompress(strings, shape)
+        assert torch.equal(d["x_hat"], m(xd, emit_strings=True)["x_hat"].clamp(0, 1))
+        c = m.compress(xd)
+        assert c["strings"] == strings
+        del d, out
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+        ref = refpath.final_forward(sd, x)
+        assert rel(y, ref["y"]) < TOL
+        sym = torch.round(y - means)
+        ref_sym = torch.round(ref["para"]["y"] - ref["para"]["means"])
+        mismatch = float((sym != ref_sym).float().mean())
+        assert mismatch < 1e-3, f"{mismatch:.2e} of the symbols differ"
+        psnr = refpath.psnr(x_hat, ref["x_hat"])
+        assert psnr > 50.0, psnr
+        if mismatch == 0.0:
+            assert rel(x_hat, ref["x_hat"]) < TOL
+        print(f"T={T}: y rel {rel(y, ref['y']):.2e}, symbol mismatch {mismatch:.2e}, x_hat PSNR {psnr:.1f} dB, "
+              f"x_hat rel {rel(x_hat, ref['x_hat']):.2e}")
+    finally:
+        ops.set_engine(old)
+
+
+def test_graphed_calls_follow_weight_and_table_updates(dev):
+    """A captured graph must not outlive the weights / CDF tables it was captured with: after load_state_dict() or
+    update(force=True) a graphed call equals the eager call with the new state (tcm.py graph cache key)."""
+    from realcamnet_b200 import raw2bit
+
+    m = raw2bit.raw_compression_tcm_final()
+    weights.fill_(m, seed=0)
+    m = m.to(dev).eval()
+    m.update()
+    m.enable_cuda_graphs(True)
+    xd = [t.to(dev) for t in inputs.make_inputs(256, seed=77)]
+    first = m(xd, emit_strings=True)
+    y0, s0 = first["y"].clone(), first["strings"]
+    m2 = raw2bit.raw_compression_tcm_final()
+    weights.fill_(m2, seed=3)
+    m.load_state_dict(m2.state_dict())
+    m.update(force=True)
+    g = m(xd, emit_strings=True)
+    gy, gs, gx = g["y"].clone(), g["strings"], g["x_hat"].clone()
+    assert not torch.equal(gy, y0)
+    m.enable_cuda_graphs(False)
+    e = m(xd, emit_strings=True)
+    assert torch.equal(e["y"], gy) and e["strings"] == gs and torch.equal(e["x_hat"], gx)
+    # tables only: a different scale table changes indexes / bytes, and compress must stay decodable by the eager decompress
+    m.enable_cuda_graphs(True)
+    c0 = m.compress(xd)
+    m.update(scale_table=torch.exp(torch.linspace(np.log(0.2), np.log(200.0), 48)), force=True)
+    c1 = m.compress(xd)
+    assert c1["strings"][0][0] != c0["strings"][0][0]
+    d = m.decompress(c1["strings"], c1["shape"])
+    m.enable_cuda_graphs(False)
+    assert torch.equal(d["x_hat"], m(xd)["x_hat"].clamp(0, 1))
 
 
 def test_product_fails_loudly_without_library(monkeypatch):
