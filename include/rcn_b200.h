@@ -99,7 +99,14 @@ typedef struct rcn_conv_desc {
                           * is a stride-2 conv); stride-1 NHWC layers with even H, W only */
     int ps_perm;         /* rcn_conv2d_tc with RCN_STORE_PS2: w_hi/w_lo were packed with ps_perm = 1 (rows grouped by sub-pixel),
                           * which lets the pixel-shuffle store write 64 contiguous bytes per pixel like the NHWC store */
+    int in_fmt;          /* rcn_conv2d_tc: element format RCN_PLANE_* of the INPUT planes x_hi/x_lo and of the packed weights */
+    int out_fmt;         /* element format RCN_PLANE_* of the emitted planes y_hi/y_lo (what the NEXT layer's in_fmt will be) */
 } rcn_conv_desc;
+
+/* 16-bit element formats of the tcgen05 operand planes.  bf16 hi+lo (3 MMA passes) is the parity engine everywhere a
+ * quantisation decision depends on the result; fp16 (1 pass, 11 significand bits) is used by the per-stage precision policy for
+ * the post-quantisation synthesis tail, where only the 1e-3 bar on x_hat applies (models/raw2bit.py:1680-1682). */
+enum { RCN_PLANE_BF16 = 0, RCN_PLANE_F16 = 1 };
 
 int rcn_conv2d(const rcn_conv_desc* d, void* stream);
 
@@ -233,13 +240,14 @@ int rcn_groupmix_attention(const float* q, int ldq, const float* k, int ldk, con
 int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
                   int Cp, int passes, void* stream);
 /* fp32 NHWC (pixel stride ldx) -> zero-padded bf16 hi/lo planes; square != 0 feeds x*x (GDN norm pool) */
-int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream);
+/* fmt = RCN_PLANE_BF16 | RCN_PLANE_F16: element format of the planes written (lo may be NULL: single-pass consumers) */
+int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, int fmt, void* hi, void* lo, void* stream);
 /* stride-2 layers: the four polyphase planes x[:, py::2, px::2, :] as (4N, H/2, W/2, Cp) bf16 hi/lo, plane index
  * (py*2+px)*N + n -- each filter tap of a stride-2 conv then reads ONE plane at unit stride (TMA box per tap). */
-int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream);
+int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, int fmt, void* hi, void* lo, void* stream);
 /* OIHW fp32 weight -> [Cout][k*k][Cp] bf16 hi/lo (K-major rows of the B operand).  ps_perm != 0 (Cout % 64 == 0): row
  * 64g + 16s + c holds conv channel 64g + 4c + s, i.e. the four PixelShuffle(2) sub-pixels s of 16 shuffled channels c. */
-int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, void* hi, void* lo, void* stream);
+int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, int fmt, void* hi, void* lo, void* stream);
 
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */

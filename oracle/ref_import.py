@@ -7,8 +7,9 @@ in-repo modules that were never committed (``models/cbam.py``, ``models/AWISP_ut
 modules for those names in ``sys.modules`` -- ``compressai.*`` resolves to the restatement in
 ``oracle/cai.py`` -- after which the five reference files import without modification.
 
-``/root/reference`` does not exist on the GPU box: only ``tests/golden/make_golden.py`` and
-the container-only validation tests call this module.
+``/root/reference`` does not exist on the GPU box; there the modules come from ``oracle/_ref`` (the sourceless byte-code that
+``oracle/stage_ref.py`` compiles in the authoring container), when staged.  Callers: ``tests/golden/make_golden.py``, the
+validation tests and ``bench.py --impl reference`` / its ``cpu_baseline`` leg.
 """
 from __future__ import annotations
 
@@ -20,10 +21,25 @@ import torch
 import torch.nn as nn
 
 REFERENCE_ROOT = os.environ.get("RCN_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")     # oracle/stage_ref.py output (sourceless .pyc)
+
+
+def reference_root():
+    """The source tree in the authoring container, else the byte-compiled copy staged by oracle/stage_ref.py, else None."""
+    if os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "raw2bit.py")):
+        return REFERENCE_ROOT
+    if os.path.isfile(os.path.join(STAGED_ROOT, "models", "raw2bit.pyc")):
+        try:
+            ver = open(os.path.join(STAGED_ROOT, "PYTHON_VERSION")).read().strip()
+        except OSError:
+            ver = ""
+        if ver == f"{sys.version_info.major}.{sys.version_info.minor}":
+            return STAGED_ROOT
+    return None
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "raw2bit.py"))
+    return reference_root() is not None
 
 
 def _mod(name, **attrs):
@@ -111,11 +127,12 @@ def install_shims():
 
 def import_reference():
     """Returns a namespace with the reference modules: .networks .LiteISP .groupmix .tcm .raw2bit"""
-    if not reference_available():
-        raise RuntimeError(f"reference not present at {REFERENCE_ROOT}")
+    root = reference_root()
+    if root is None:
+        raise RuntimeError(f"reference not present at {REFERENCE_ROOT} and not staged under {STAGED_ROOT}")
     install_shims()
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import importlib
 
     ns = types.SimpleNamespace()

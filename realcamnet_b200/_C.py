@@ -23,6 +23,7 @@ class ConvDesc(ctypes.Structure):
         ("res", c_void_p), ("ldres", c_int), ("res_pre", c_int),
         ("act", c_int), ("slope", c_float), ("res_scale", c_float),
         ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int), ("planes_s2", c_int), ("ps_perm", c_int),
+        ("in_fmt", c_int), ("out_fmt", c_int),
     ]
 
 
@@ -35,9 +36,9 @@ PROTOTYPES = {
     "rcn_launch_count": (c_ulonglong, []),
     "rcn_conv2d": (_I, [POINTER(ConvDesc), _P]),
     "rcn_conv2d_tc": (_I, [POINTER(ConvDesc), _P, _P, _P, _P, _I, _I, _P]),
-    "rcn_split_bf16": (_I, [_P, _I, _L, _I, _I, _I, _P, _P, _P]),
-    "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
-    "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "rcn_split_bf16": (_I, [_P, _I, _L, _I, _I, _I, _I, _P, _P, _P]),
+    "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
+    "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),

@@ -20,6 +20,7 @@
 // tile -> epilogue), tmem_empty[2] (8 epilogue warps -> MMA issuers): the accumulators are double-buffered in TMEM (4 x 128 columns).
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <stdlib.h>
 
@@ -35,6 +36,15 @@ constexpr int TILE_H = 8, TILE_W = 16;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// operand-plane element formats (rcn_conv_desc.in_fmt / out_fmt): both are 16-bit, so planes, tensor maps and smem tiles are
+// format-agnostic; only the conversions and the MMA instruction descriptor differ
+__device__ __forceinline__ uint16_t to_plane(float v, int f16) {
+    return f16 ? __half_as_ushort(__float2half_rn(v)) : __bfloat16_as_ushort(__float2bfloat16_rn(v));
+}
+__device__ __forceinline__ float from_plane(uint16_t h, int f16) {
+    return f16 ? __half2float(__ushort_as_half(h)) : __bfloat162float(__ushort_as_bfloat16(h));
+}
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -128,6 +138,7 @@ struct TcParams {
     int s2;       // stride-2 conv: A planes are the 4 polyphase components stacked on the batch axis ((py*2+px)*N + n)
     int nmma;     // MMA-issuing warps: 2 for long K loops (3x3 layers), 1 otherwise
     int wcw;      // accumulator columns per epilogue warp: 64, or Ntile / 2 when that keeps all 8 warps busy (Ntile = 64, 96)
+    int in_f16;   // operand planes and packed weights are fp16 (kind::f16 with f16 A/B formats) instead of bf16
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math, 16 centre-tap A loads only
 };
 
@@ -245,7 +256,7 @@ struct EpiRegs {
     uint32_t flags;
 };
 enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512,
-       EF_DUAL = 1024 };
+       EF_DUAL = 1024, EF_F16OUT = 2048 };
 template <typename T>
 __device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
 __device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
@@ -261,7 +272,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
     r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
     r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
               (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
-              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0);
+              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0) | (p.out_fmt ? EF_F16OUT : 0);
     opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
     opaque(r.H); opaque(r.W); opaque(r.N); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
     opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
@@ -398,12 +409,13 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
             if (r.flags & EF_NOSTORE) continue;
             if (r.flags & EF_Y) *reinterpret_cast<float4*>(r.y + (ip[it] + qoff) * r.ldy + ch) = make_float4(val[0], val[1], val[2], val[3]);
             if (r.flags & EF_HI) {
-                // the consumer's tcgen05 operand planes: x = hi + lo in bf16 (same rounding as rcn_split_bf16)
-                __nv_bfloat16 hb[4], lb[4];
+                // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16)
+                const int f16 = (r.flags & EF_F16OUT) ? 1 : 0;
+                uint16_t hb[4], lb[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    hb[e] = __float2bfloat16_rn(val[e]);
-                    lb[e] = __float2bfloat16_rn(val[e] - __bfloat162float(hb[e]));
+                    hb[e] = to_plane(val[e], f16);
+                    lb[e] = to_plane(val[e] - from_plane(hb[e], f16), f16);
                 }
                 long long po = (ip[it] + qoff) * r.cpo + ch;
                 if (r.flags & EF_S2OUT) {
@@ -620,7 +632,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             int nact = p.Cout - n0;
             if (nact > P.Ntile) nact = P.Ntile;
             nact = (nact + 15) & ~15;
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), N >> 3 at 17, M >> 4 at 24
+            const uint32_t abfmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
+            const uint32_t idesc = (1u << 4) | abfmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             const uint32_t ab = local & 1;
             mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator pair
             tc_fence_after();
@@ -700,8 +714,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
 // ---------------------------------------------------------------- operand preparation
 // fp32 NHWC (ld) -> bf16 hi / lo planes (npix, Cp), zero-padded channels; optional x*x (GDN)
-__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long long npix, int C, int Cp, int square,
-                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long long npix, int C, int Cp, int square, int f16,
+                                  uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const long long total = npix * (Cp / 4);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c4 = (int)(i % (Cp / 4)) * 4;
@@ -713,11 +727,11 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long lon
             float t = (c < C) ? x[pix * ldx + c] : 0.f;
             v[j] = square ? t * t : t;
         }
-        __nv_bfloat16 h[4], l[4];
+        uint16_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            h[j] = __float2bfloat16_rn(v[j]);
-            l[j] = __float2bfloat16_rn(v[j] - __bfloat162float(h[j]));
+            h[j] = to_plane(v[j], f16);
+            l[j] = to_plane(v[j] - from_plane(h[j], f16), f16);
         }
         *reinterpret_cast<uint2*>(hi + pix * Cp + c4) = *reinterpret_cast<uint2*>(h);
         if (lo) *reinterpret_cast<uint2*>(lo + pix * Cp + c4) = *reinterpret_cast<uint2*>(l);
@@ -725,8 +739,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, long lon
 }
 
 // polyphase split for stride-2 convs: out[((py*2+px)*N + n), i, j, c] = x[n, 2i+py, 2j+px, c]
-__global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N, int H, int W, int C, int Cp,
-                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+__global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N, int H, int W, int C, int Cp, int f16,
+                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const int H2 = H / 2, W2 = W / 2;
     const long long total = (long long)N * H * W * (Cp / 4);
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -738,11 +752,11 @@ __global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = (c4 + j < C) ? x[(((long long)n * H + h) * W + w) * ldx + c4 + j] : 0.f;
-        __nv_bfloat16 hh[4], ll[4];
+        uint16_t hh[4], ll[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            hh[j] = __float2bfloat16_rn(v[j]);
-            ll[j] = __float2bfloat16_rn(v[j] - __bfloat162float(hh[j]));
+            hh[j] = to_plane(v[j], f16);
+            ll[j] = to_plane(v[j] - from_plane(hh[j], f16), f16);
         }
         const long long plane = (long long)((h & 1) * 2 + (w & 1)) * N + n;
         const long long o = ((plane * H2 + (h >> 1)) * W2 + (w >> 1)) * Cp + c4;
@@ -752,8 +766,8 @@ __global__ void split_bf16_s2_kernel(const float* __restrict__ x, int ldx, int N
 }
 
 // OIHW fp32 -> [Cout][k*k][Cp] bf16 hi / lo (K-major rows for the B operand)
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp, int ps_perm,
-                                      __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int Cp, int ps_perm, int f16,
+                                      uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
     const long long total = (long long)Cout * k * k * Cp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)(i % Cp);
@@ -765,9 +779,9 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, int Cout, int
             co = (g << 6) + ((rr & 15) << 2) + (rr >> 4);
         }
         const float v = (c < Cin) ? w[((long long)co * Cin + c) * k * k + tap] : 0.f;
-        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const uint16_t h = to_plane(v, f16);
         hi[i] = h;
-        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+        if (lo) lo[i] = to_plane(v - from_plane(h, f16), f16);
     }
 }
 
@@ -912,37 +926,37 @@ extern "C" int rcn_tc_prof(unsigned long long* out16, int reset) {
 
 static inline bool cp_ok(int Cp) { return Cp == 16 || Cp == 32 || (Cp > 0 && Cp % 64 == 0); }
 
-extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && cp_ok(Cp), "rcn_split_bf16: bad arguments");
+extern "C" int rcn_split_bf16(const float* x, int ldx, long long npix, int C, int Cp, int square, int fmt, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(x && hi && npix > 0 && C > 0 && Cp >= C && cp_ok(Cp) && (fmt == RCN_PLANE_BF16 || fmt == RCN_PLANE_F16), "rcn_split_bf16: bad arguments");
     const long long total = npix * (Cp / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    split_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, npix, C, Cp, square, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    split_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, npix, C, Cp, square, fmt, (uint16_t*)hi, (uint16_t*)lo);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_split_bf16");
     return RCN_OK;
 }
 
 // stride-2 operand: the four polyphase planes (py,px) of x, each (N, H/2, W/2, Cp), stacked on the batch axis
-extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(x && hi && N > 0 && C > 0 && Cp >= C && cp_ok(Cp), "rcn_split_bf16_s2: bad arguments");
+extern "C" int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int Cp, int fmt, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(x && hi && N > 0 && C > 0 && Cp >= C && cp_ok(Cp) && (fmt == RCN_PLANE_BF16 || fmt == RCN_PLANE_F16), "rcn_split_bf16_s2: bad arguments");
     RCN_CHECK_ARG(H % 2 == 0 && W % 2 == 0, "rcn_split_bf16_s2: H and W must be even");
     const long long total = (long long)N * H * W * (Cp / 4);
     long long blocks = (total + 255) / 256;
     if (blocks > 148 * 32) blocks = 148 * 32;
-    split_bf16_s2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, H, W, C, Cp, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    split_bf16_s2_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, N, H, W, C, Cp, fmt, (uint16_t*)hi, (uint16_t*)lo);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_split_bf16_s2");
     return RCN_OK;
 }
 
-extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, void* hi, void* lo, void* stream) {
-    RCN_CHECK_ARG(w_oihw && hi && lo && Cp >= Cin && cp_ok(Cp), "rcn_pack_conv_weight_tc: bad arguments");
+extern "C" int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, int fmt, void* hi, void* lo, void* stream) {
+    RCN_CHECK_ARG(w_oihw && hi && Cp >= Cin && cp_ok(Cp) && (fmt == RCN_PLANE_BF16 || fmt == RCN_PLANE_F16), "rcn_pack_conv_weight_tc: bad arguments");
     RCN_CHECK_ARG(!ps_perm || Cout % 64 == 0, "rcn_pack_conv_weight_tc: the pixel-shuffle row order needs Cout %% 64 == 0");
     const long long total = (long long)Cout * k * k * Cp;
     long long blocks = (total + 255) / 256;
     if (blocks > 4096) blocks = 4096;
-    pack_weight_tc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, k, Cp, ps_perm, (__nv_bfloat16*)hi, (__nv_bfloat16*)lo);
+    pack_weight_tc_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w_oihw, Cout, Cin, k, Cp, ps_perm, fmt, (uint16_t*)hi, (uint16_t*)lo);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_pack_conv_weight_tc");
     return RCN_OK;
@@ -983,6 +997,9 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     if (P.s2) { P.d.H = d->H / 2; P.d.W = d->W / 2; }   // the kernel works in output geometry (== polyphase plane geometry)
     P.Cp = Cp;
     P.passes = passes;
+    P.in_f16 = d->in_fmt == RCN_PLANE_F16;
+    RCN_CHECK_ARG((d->in_fmt == RCN_PLANE_BF16 || d->in_fmt == RCN_PLANE_F16) && (d->out_fmt == RCN_PLANE_BF16 || d->out_fmt == RCN_PLANE_F16),
+                  "rcn_conv2d_tc: unknown operand plane format");
     int nt = d->Cout >= 128 ? 128 : ((d->Cout + 15) & ~15);
     P.Ntile = nt;
     P.tiles_x = (P.d.W + TILE_W - 1) / TILE_W;

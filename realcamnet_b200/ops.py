@@ -85,21 +85,53 @@ def count_replayed(n: int):
 
 # ----------------------------------------------------------------------------- conv engine selection
 # "fp32"   : CUDA-core FFMA implicit GEMM (rcn_conv2d) for every layer -- exact-parity engine
-# "bf16x3" : tcgen05 engine with hi/lo split operands (3 MMAs per product, ~fp32-grade) where eligible
+# "bf16x3" : tcgen05 engine with bf16 hi/lo split operands (3 MMAs per product, ~fp32-grade) where eligible
+# "fp16"   : tcgen05 engine, single fp16 pass (11 significand bits).  NOT for layers whose result feeds a quantisation decision;
+#            the per-stage precision policy (raw2bit._g_s / tcm._g_s) scopes it to the post-quantisation synthesis tail
 # "bf16"   : tcgen05 engine, single bf16 pass (fast mode; does NOT meet the 1e-3 parity bar end to end)
+FMT_BF16, FMT_F16 = 0, 1
+_MODES = {"fp32": (0, FMT_BF16), "bf16x3": (3, FMT_BF16), "bf16": (1, FMT_BF16), "fp16": (1, FMT_F16)}   # name -> (MMA passes, plane format)
+_PLANE_DTYPE = {FMT_BF16: torch.bfloat16, FMT_F16: torch.float16}
 _ENGINE = os.environ.get("RCN_CONV_ENGINE", "bf16x3")
 _TC_MIN_CIN = 1   # every k in {1,3} layer is tcgen05-eligible (tiny Cin is zero-padded to one 64-channel K chunk)
 
 
 def set_engine(name: str):
     global _ENGINE
-    if name not in ("fp32", "bf16x3", "bf16"):
+    if name not in _MODES:
         raise ValueError(f"unknown conv engine {name!r}")
     _ENGINE = name
 
 
 def get_engine() -> str:
     return _ENGINE
+
+
+class engine_scope:
+    """with ops.engine_scope("fp16"): ...  -- the layers launched inside use that engine (None = leave as is).  Layers are
+    launched (or captured into a CUDA graph) synchronously from Python, so a scope is just a save / restore of the global."""
+
+    def __init__(self, name):
+        if name is not None and name not in _MODES:
+            raise ValueError(f"unknown conv engine {name!r}")
+        self.name, self.old = name, None
+
+    def __enter__(self):
+        global _ENGINE
+        self.old = _ENGINE
+        if self.name is not None:
+            _ENGINE = self.name
+        return self
+
+    def __exit__(self, *exc):
+        global _ENGINE
+        _ENGINE = self.old
+        return False
+
+
+def _mode(eng=None):
+    """(MMA passes, plane format) of an engine name"""
+    return _MODES[eng or _ENGINE]
 
 
 # ----------------------------------------------------------------------------- weights
@@ -109,20 +141,35 @@ def plane_channels(c: int) -> int:
 
 
 class PackedConv:
-    __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo", "w_src", "w_hi_ps", "w_lo_ps")
+    __slots__ = ("w", "bias", "k", "cin", "cout", "cp", "w_hi", "w_lo", "w_src", "w_hi_ps", "w_lo_ps", "_alt")
 
     def __init__(self, w, bias, k, cin, cout, cp=0, w_hi=None, w_lo=None):
         self.w, self.bias, self.k, self.cin, self.cout = w, bias, k, cin, cout
         self.cp, self.w_hi, self.w_lo = cp, w_hi, w_lo
         self.w_src = self.w_hi_ps = self.w_lo_ps = None
+        self._alt = {}
 
     def ps_weights(self):
         """bf16 planes with rows grouped by PixelShuffle(2) sub-pixel (packed on first use by a pixel-shuffle store)."""
         if self.w_hi_ps is None:
             self.w_hi_ps, self.w_lo_ps = torch.empty_like(self.w_hi), torch.empty_like(self.w_lo)
-            _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(self.w_src), self.cout, self.cin, self.k, self.cp, 1, _ptr(self.w_hi_ps),
-                                                      _ptr(self.w_lo_ps), _stream()), "rcn_pack_conv_weight_tc")
+            _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(self.w_src), self.cout, self.cin, self.k, self.cp, 1, FMT_BF16,
+                                                      _ptr(self.w_hi_ps), _ptr(self.w_lo_ps), _stream()), "rcn_pack_conv_weight_tc")
         return self.w_hi_ps, self.w_lo_ps
+
+    def tc_weights(self, fmt, ps_perm=False):
+        """(w_hi, w_lo) operand weights in plane format `fmt`, optionally with sub-pixel-grouped rows; other formats than bf16
+        are packed on first use (single-pass engines: hi only)."""
+        if fmt == FMT_BF16:
+            return self.ps_weights() if ps_perm else (self.w_hi, self.w_lo)
+        key = (fmt, bool(ps_perm))
+        hit = self._alt.get(key)
+        if hit is None:
+            hi = torch.empty(self.w_hi.shape, device=self.w_hi.device, dtype=_PLANE_DTYPE[fmt])
+            _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(self.w_src), self.cout, self.cin, self.k, self.cp, int(ps_perm), fmt,
+                                                      _ptr(hi), _vp(0), _stream()), "rcn_pack_conv_weight_tc")
+            hit = self._alt[key] = (hi, None)
+        return hit
 
 
 _pack_cache: "weakref.WeakKeyDictionary" = weakref.WeakKeyDictionary()
@@ -148,7 +195,7 @@ def pack_weight(weight: torch.Tensor, bias=None) -> PackedConv:
         pc.cp = cp
         pc.w_hi = torch.empty((cout, k * k * cp), device=w.device, dtype=torch.bfloat16)
         pc.w_lo = torch.empty_like(pc.w_hi)
-        _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(w), cout, cin, k, cp, 0, _ptr(pc.w_hi), _ptr(pc.w_lo), _stream()),
+        _C.check(_C.lib().rcn_pack_conv_weight_tc(_ptr(w), cout, cin, k, cp, 0, FMT_BF16, _ptr(pc.w_hi), _ptr(pc.w_lo), _stream()),
                  "rcn_pack_conv_weight_tc")
         pc.w_src = w
     return pc
@@ -178,10 +225,10 @@ def pack(module) -> PackedConv:
 class SplitOperand:
     """bf16 hi/lo planes of one activation tensor for the tcgen05 engine (shareable between the convs that read it).
     hi / lo are (N,H,W,Cp) bf16 tensors, possibly channel-slice views of a wider plane buffer (pixel stride = ld)."""
-    __slots__ = ("hi", "lo", "key")
+    __slots__ = ("hi", "lo", "key", "fmt")
 
-    def __init__(self, hi, lo, key):
-        self.hi, self.lo, self.key = hi, lo, key
+    def __init__(self, hi, lo, key, fmt=FMT_BF16):
+        self.hi, self.lo, self.key, self.fmt = hi, lo, key, fmt
 
     @property
     def ld(self):
@@ -196,7 +243,7 @@ class SplitOperand:
             raise ValueError(f"a {c1 - c0}-channel slice is not a valid plane width")
         k = self.key
         return SplitOperand(self.hi[..., c0:c1], None if self.lo is None else self.lo[..., c0:c1],
-                            (None, k[1], k[2], k[3], c1 - c0, None, cp, 1, False))
+                            (None, k[1], k[2], k[3], c1 - c0, None, cp, 1, False), self.fmt)
 
 
 def plane_ld(t):
@@ -210,40 +257,50 @@ def plane_ld(t):
     return ld
 
 
-def alloc_planes(N, H, W, C, device, passes=None, stride=1) -> SplitOperand:
+def alloc_planes(N, H, W, C, device, passes=None, stride=1, fmt=None) -> SplitOperand:
     """Uninitialised operand planes of an (N,H,W,C) tensor for producers to write (conv2d(split_out=...), layernorm / wmsa
-    emit); C must be a valid plane width.  stride=2: the polyphase layout a stride-2 consumer reads (4N, H/2, W/2, C)."""
+    emit); C must be a valid plane width.  stride=2: the polyphase layout a stride-2 consumer reads (4N, H/2, W/2, C).
+    passes / fmt default to what the CURRENT engine's consumers read."""
     if plane_channels(C) != C:
         raise ValueError(f"{C} channels is not a valid plane width")
     if passes is None:
-        passes = 3 if _ENGINE == "bf16x3" else 1
+        passes = _mode()[0]
+    if fmt is None:
+        fmt = _mode()[1]
     shape = (N, H, W, C) if stride == 1 else (4 * N, H // 2, W // 2, C)
-    hi = torch.empty(shape, device=device, dtype=torch.bfloat16)
+    hi = torch.empty(shape, device=device, dtype=_PLANE_DTYPE[fmt])
     lo = torch.empty_like(hi) if passes == 3 else None
-    return SplitOperand(hi, lo, (None, N, H, W, C, None, C, stride, False))
+    return SplitOperand(hi, lo, (None, N, H, W, C, None, C, stride, False), fmt)
 
 
 def planes_enabled() -> bool:
     return _ENGINE != "fp32"
 
 
-def split_operand(x, cp, stride=1, in_square=False, passes=None) -> SplitOperand:
-    """fp32 NHWC -> zero-padded bf16 planes; stride 2 -> the four polyphase planes stacked on the batch axis."""
+def bf16_planes_enabled() -> bool:
+    """LayerNorm / window-attention kernels emit bf16 planes only"""
+    return _ENGINE != "fp32" and _mode()[1] == FMT_BF16
+
+
+def split_operand(x, cp, stride=1, in_square=False, passes=None, fmt=None) -> SplitOperand:
+    """fp32 NHWC -> zero-padded 16-bit planes; stride 2 -> the four polyphase planes stacked on the batch axis."""
     N, H, W, C, ldx = geom(x, "split_operand.x")
     if passes is None:
-        passes = 3 if _ENGINE == "bf16x3" else 1
+        passes = _mode()[0] or 3
+    if fmt is None:
+        fmt = _mode()[1]
     if stride == 2:
-        hi = torch.empty((4 * N, H // 2, W // 2, cp), device=x.device, dtype=torch.bfloat16)
+        hi = torch.empty((4 * N, H // 2, W // 2, cp), device=x.device, dtype=_PLANE_DTYPE[fmt])
         lo = torch.empty_like(hi) if passes == 3 else None
         if in_square:
             raise ValueError("in_square is not used with stride 2")
-        _C.check(_C.lib().rcn_split_bf16_s2(_ptr(x), ldx, N, H, W, C, cp, _ptr(hi), _ptr(lo), _stream()), "rcn_split_bf16_s2")
+        _C.check(_C.lib().rcn_split_bf16_s2(_ptr(x), ldx, N, H, W, C, cp, fmt, _ptr(hi), _ptr(lo), _stream()), "rcn_split_bf16_s2")
     else:
-        hi = torch.empty((N, H, W, cp), device=x.device, dtype=torch.bfloat16)
+        hi = torch.empty((N, H, W, cp), device=x.device, dtype=_PLANE_DTYPE[fmt])
         lo = torch.empty_like(hi) if passes == 3 else None
-        _C.check(_C.lib().rcn_split_bf16(_ptr(x), ldx, N * H * W, C, cp, int(in_square), _ptr(hi), _ptr(lo), _stream()),
+        _C.check(_C.lib().rcn_split_bf16(_ptr(x), ldx, N * H * W, C, cp, int(in_square), fmt, _ptr(hi), _ptr(lo), _stream()),
                  "rcn_split_bf16")
-    return SplitOperand(hi, lo, (x.data_ptr(), N, H, W, C, ldx, cp, stride, bool(in_square)))
+    return SplitOperand(hi, lo, (x.data_ptr(), N, H, W, C, ldx, cp, stride, bool(in_square)), fmt)
 
 
 def shared_split(x, pcs, stride=1):
@@ -342,22 +399,26 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
             if tuple(sp_out.hi.shape) != want_shape or sp_out.key[7] != emit_stride:
                 raise ValueError("conv2d: split_out planes do not have the stored output geometry")
             d.planes_s2 = int(emit_stride == 2)
+            d.out_fmt = sp_out.fmt
             d.y_hi, d.y_lo, d.Cp_out = sp_out.hi.data_ptr(), (sp_out.lo.data_ptr() if sp_out.lo is not None else None), sp_out.ld
         elif out is None:
             raise ValueError("conv2d: cannot drop the fp32 output of a layer whose epilogue is not 16-byte aligned")
     if use_tc:
-        # tcgen05 path: bf16 hi/lo operand planes (from the producer's epilogue, a shared split, or a split pass here)
-        passes = 3 if eng == "bf16x3" else 1
-        sp = presplit if presplit is not None else split_operand(x, pc.cp, stride, in_square, passes)
+        # tcgen05 path: 16-bit operand planes (from the producer's epilogue, a shared split, or a split pass here)
+        passes, fmt = _mode(eng)
+        sp = presplit if presplit is not None else split_operand(x, pc.cp, stride, in_square, passes, fmt)
         k0 = sp.key
         same = (k0[1:5] == (N, H, W, Cin) and k0[6:] == (pc.cp, stride, bool(in_square)) and
                 (k0[0] is None or (x is not None and k0[0] == x.data_ptr() and k0[5] == ldx)))
+        if sp.fmt != fmt:
+            raise ValueError(f"conv2d: operand planes are in format {sp.fmt} but the {eng!r} engine reads format {fmt} "
+                             "(a producer outside the engine scope emitted them)")
         if not same or (passes == 3 and sp.lo is None):
             raise ValueError("conv2d: presplit operand does not belong to this input / layer geometry")
-        d.ldp_in = sp.ld
-        w_hi, w_lo = pc.w_hi, pc.w_lo
-        if store == STORE_PS2 and pc.cout % 64 == 0 and epi == EPI_NONE and cscale is None:
-            w_hi, w_lo = pc.ps_weights()          # rows grouped by sub-pixel: 64-byte contiguous pixel-shuffle stores
+        d.ldp_in, d.in_fmt = sp.ld, fmt
+        ps_perm = store == STORE_PS2 and pc.cout % 64 == 0 and epi == EPI_NONE and cscale is None
+        w_hi, w_lo = pc.tc_weights(fmt, ps_perm)  # ps_perm: rows grouped by sub-pixel -> 64-byte contiguous pixel-shuffle stores
+        if ps_perm:
             d.ps_perm = 1
         _C.check(_C.lib().rcn_conv2d_tc(ctypes.byref(d), _ptr(sp.hi), _ptr(sp.lo), _ptr(w_hi), _ptr(w_lo), pc.cp, passes,
                                         _stream()), "rcn_conv2d_tc")
@@ -371,7 +432,7 @@ def layernorm(x, weight, bias, eps=1e-5, out=None, act=ACT_NONE, emit_split=Fals
     tcgen05 engine is active and C is a valid plane width; (out, None) otherwise."""
     N, H, W, C, ldx = geom(x, "layernorm.x")
     sp = None
-    if emit_split and planes_enabled() and plane_channels(C) == C and out is None:
+    if emit_split and bf16_planes_enabled() and plane_channels(C) == C and out is None:
         sp = alloc_planes(N, H, W, C, x.device)
         _C.check(_C.lib().rcn_layernorm(_ptr(x), N * H * W, C, ldx, _ptr(weight), _ptr(bias), eps, _vp(0), 0, act,
                                         _ptr(sp.hi), _ptr(sp.lo), sp.ld, _stream()), "rcn_layernorm")
@@ -390,7 +451,7 @@ def wmsa(qkv, relpos, head_dim, ws, shifted, out=None, emit_split=False):
     C = C3 // 3
     _chk(relpos)
     assert relpos.is_contiguous() and tuple(relpos.shape) == (C // head_dim, 2 * ws - 1, 2 * ws - 1)
-    if emit_split and planes_enabled() and plane_channels(C) == C and out is None:
+    if emit_split and bf16_planes_enabled() and plane_channels(C) == C and out is None:
         sp = alloc_planes(N, H, W, C, qkv.device)
         _C.check(_C.lib().rcn_wmsa(_ptr(qkv), N, H, W, C, ldq, head_dim, ws, int(shifted), _ptr(relpos), _vp(0), 0,
                                    _ptr(sp.hi), _ptr(sp.lo), sp.ld, _stream()), "rcn_wmsa")

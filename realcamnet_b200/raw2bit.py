@@ -363,9 +363,11 @@ class raw_compression_tcm_final(SliceCodecModel):
         # tail at full resolution (raw2bit.py:1680-1682): subpel -> ResidualBlock -> subpel.  The 128-channel maps are 2.1 GB
         # each: the producers write the consumers' bf16 operand planes themselves, and the ResidualBlock output (read by the
         # last conv only) never exists in fp32.
-        h, hsp = mods[-3]._f(h, emit_split=True, keep_fp32=True)
-        h, rsp = mods[-2]._f(h, presplit=hsp, emit_split=True, keep_fp32=False)    # h is None when only the planes exist
-        return mods[-1]._f(h, presplit=rsp, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
+        # Precision policy (SliceCodecModel.tail_engine): these four convs run as one fp16 pass.
+        with self._tail_scope():
+            h, hsp = mods[-3]._f(h, emit_split=True, keep_fp32=True)
+            h, rsp = mods[-2]._f(h, presplit=hsp, emit_split=True, keep_fp32=False)    # h is None when only the planes exist
+            return mods[-1]._f(h, presplit=rsp, store=STORE_PS2_NCHW, act=ACT_CLAMP01 if clamp else ACT_NONE)
 
     # ------------------------------------------------------------------------------ public API
     @torch.no_grad()

@@ -9,6 +9,7 @@ All tensor math is dispatched to librcn_b200.so through ``ops``.
 from __future__ import annotations
 
 import math
+import os
 from types import SimpleNamespace
 
 import torch
@@ -196,6 +197,18 @@ class SliceCodecModel(CompressionModel):
     analysis transform: hyper-prior, the 5-slice channel-conditional entropy parameter loop, the Gaussian / factorised
     entropy kernels and the range coder hand-off.  Sub-classes provide the parameter-holding sub-modules under the reference
     names (h_a, h_mean_s, h_scale_s, atten_*, cc_*_transforms, lrp_transforms, entropy_bottleneck, gaussian_conditional)."""
+
+    # Per-stage precision policy.  Everything whose result feeds a quantisation decision (g_a, hyper-prior, slice loop: the symbols
+    # must match the reference's) runs on the parity engine (bf16 hi/lo split, 3 MMA passes).  The full-resolution synthesis TAIL
+    # (models/raw2bit.py:1680-1682; the last subpel conv of TCM, models/tcm.py:367) comes after quantisation, where only the
+    # 1e-3 bar on x_hat applies, and holds a third of the model's FLOPs: it runs as ONE fp16 pass (11 significand bits; measured
+    # x_hat error 4.7e-4 of max at T=256, profiles/r2_precision_policy.md).  decompress() shares _g_s, so decode == forward stays
+    # bit-exact.  tail_engine = None / "bf16x3" turns the policy off; it only applies when the global engine is "bf16x3".
+    tail_engine = os.environ.get("RCN_TAIL_ENGINE", "fp16") or None
+
+    def _tail_scope(self):
+        te = self.tail_engine
+        return ops.engine_scope(te if (te and te != "bf16x3" and ops.get_engine() == "bf16x3") else None)
 
     def _invalidate_graphs(self):
         """Captured graphs hold raw pointers to packed weights, GDN / entropy-bottleneck parameters and the CDF tables: whatever
@@ -420,7 +433,7 @@ class StageRunner:
         self.inputs = inputs
         self.entry = None
         if getattr(model, "_use_graphs", False):
-            full = (key, ops.get_engine()) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
+            full = (key, ops.get_engine(), getattr(model, "tail_engine", None)) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
             cache = model.__dict__.setdefault("_graph_cache", {})
             ver = model._state_version()
             if cache.get("_version") != ver:        # weights / tables were edited in place since the graphs were captured
@@ -531,7 +544,8 @@ class TCM(SliceCodecModel):
         mods = list(self.g_s)
         for m in mods[:-1]:
             h = m._f(h)
-        return mods[-1]._f(h, store=ops.STORE_PS2_NCHW, act=ops.ACT_CLAMP01 if clamp else ops.ACT_NONE)
+        with self._tail_scope():
+            return mods[-1]._f(h, store=ops.STORE_PS2_NCHW, act=ops.ACT_CLAMP01 if clamp else ops.ACT_NONE)
 
     @torch.no_grad()
     def forward(self, x, emit_strings=False):

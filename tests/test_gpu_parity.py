@@ -80,6 +80,50 @@ def test_conv2d_plain_and_activations(dev, engine, case):
         assert rel(y, F.pixel_shuffle(ref, 2).clamp(0, 1)) < CONV_TOL
 
 
+@pytest.mark.parametrize("case", [(1, 40, 48, 128, 128, 3, 1), (2, 24, 40, 64, 512, 3, 1), (1, 32, 32, 128, 12, 3, 1), (1, 16, 32, 20, 48, 1, 1),
+                                  (1, 32, 16, 16, 32, 3, 2)])
+def test_conv2d_fp16_single_pass_engine(dev, case):
+    """The precision policy's tail engine: ONE fp16 MMA pass (kind::f16 with f16 operand formats).  Checked against torch fp32 on
+    operands pre-rounded to fp16 (then the only difference is fp32 accumulation order: ~1e-6), and against the unrounded result
+    within the fp16 rounding budget; conv -> conv chains hand fp16 planes from epilogue to consumer."""
+    from realcamnet_b200 import ops
+
+    N, H, W, Cin, Cout, k, s = case
+    g = torch.Generator().manual_seed(sum(case) + 1)
+    x = torch.randn(N, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    pc = ops.pack_weight(w.to(dev), b.to(dev))
+    xn = ops.to_nhwc(x.to(dev))
+    ref = F.conv2d(x, w, b, stride=s, padding=k // 2)
+    ref16 = F.conv2d(x.half().float(), w.half().float(), b, stride=s, padding=k // 2)
+    with ops.engine_scope("fp16"):
+        y = ops.to_nchw(ops.conv2d(xn, pc, stride=s, act=ops.ACT_LRELU, slope=0.01))
+        assert rel(y, F.leaky_relu(ref16, 0.01)) < 2e-5, case
+        assert rel(y, F.leaky_relu(ref, 0.01)) < 3e-3, case
+        if Cout % 4 == 0 and s == 1:
+            y = ops.conv2d(xn, pc, store=ops.STORE_PS2_NCHW, act=ops.ACT_CLAMP01)
+            assert rel(y, F.pixel_shuffle(ref16, 2).clamp(0, 1)) < 2e-5
+        if Cout % 64 == 0 and s == 1:
+            # chain: this layer emits fp16 planes only (NHWC and pixel-shuffle stores); a second conv consumes them
+            for store, up in ((ops.STORE_NHWC, 1), (ops.STORE_PS2, 2)):
+                C2 = Cout if up == 1 else Cout // 4
+                if ops.plane_channels(C2) != C2:
+                    continue
+                w2 = torch.randn(32, C2, 3, 3, generator=g) / (C2 * 9) ** 0.5
+                pc2 = ops.pack_weight(w2.to(dev), None)
+                t, sp = ops.conv2d(xn, pc, store=store, act=ops.ACT_RELU, emit_split=True, keep_fp32=False)
+                assert t is None and sp.fmt == ops.FMT_F16 and sp.lo is None and sp.hi.dtype == torch.float16
+                y2 = ops.to_nchw(ops.conv2d(None, pc2, presplit=sp))
+                mid = F.relu(ref16)
+                mid = F.pixel_shuffle(mid, 2) if up == 2 else mid
+                assert rel(y2, F.conv2d(mid.half().float(), w2.half().float(), None, padding=1)) < 2e-5, (case, store)
+    # planes of one format cannot feed an engine that reads the other
+    sp = ops.split_operand(xn, pc.cp, stride=s, passes=1, fmt=ops.FMT_F16)
+    with pytest.raises(ValueError, match="format"):
+        ops.conv2d(xn, pc, stride=s, presplit=sp, engine="bf16x3")
+
+
 @pytest.mark.parametrize("case", [(1, 256, 256, 128, 128, 3, 1), (1, 512, 512, 128, 128, 3, 2), (1, 192, 320, 64, 64, 3, 1)])
 def test_conv2d_many_tiles_per_sm(dev, case):
     """Persistent-kernel regression: 3-4 tiles per SM with a 3-stage ring and two MMA-issuing warps (a parity-aliasing race between
@@ -645,7 +689,8 @@ def test_graphed_calls_follow_weight_and_table_updates(dev):
     y0, s0 = first["y"].clone(), first["strings"]
     m2 = raw2bit.raw_compression_tcm_final()
     weights.fill_(m2, seed=3)
-    m.load_state_dict(m2.state_dict())
+    new_sd = {k: v for k, v in m2.state_dict().items() if not any(s in k for s in ("_offset", "_quantized_cdf", "_cdf_length", "scale_table"))}
+    m.load_state_dict(new_sd, strict=False)
     m.update(force=True)
     g = m(xd, emit_strings=True)
     gy, gs, gx = g["y"].clone(), g["strings"], g["x_hat"].clone()
