@@ -161,6 +161,10 @@ int rcn_upsample_bilinear2x(const float* x, int N, int H, int W, int C, int ldx,
  * [LL,LH,HL,HH] per input channel: models/networks.py:224-249 */
 int rcn_dwt_forward(const float* x, int N, int H, int W, int C, int ldx, float* y, int ldy, void* stream);
 int rcn_dwt_inverse(const float* x, int N, int H, int W, int C4, int ldx, float* y, int ldy, void* stream);
+/* space-to-depth by 2: y[n, ho, wo, (i*2+j)*C + c] = x[n, 2ho+i, 2wo+j, c].  With weights re-ordered to (O, i, j, c) the learned
+ * nn.Conv2d(C, O, 2, 2) down-samplers of ISPUNet_GFM_LSC / ResUNet (models/LiteISP.py:1253,1265,1278,2056,2065,2075) become 1x1
+ * contractions on the conv engines. */
+int rcn_space_to_depth2(const float* x, int N, int H, int W, int C, int ldx, float* y, int ldy, void* stream);
 /* depthwise k x k conv (k odd, padding k//2), weights [k*k][C]; add_input: "+ feat" of ConvPosEnc
  * (models/groupmix.py:213-215); mul: "q * conv(v)" of ConvRelPosEnc (models/groupmix.py:146-154) */
 int rcn_depthwise_conv(const float* x, int N, int H, int W, int C, int ldx, const float* w, const float* bias, int k,

@@ -623,6 +623,79 @@ def liteisp_forward(sd, x):
     return conv(sd, "tail.2", F.pixel_shuffle(conv(sd, "tail.0", u1), 2))
 
 
+# ----------------------------------------------------------------------------- the other ISP variants
+def _down2x2(sd, p, x):
+    """nn.Conv2d(C, 2C, 2, 2): kernel 2, stride 2, no padding (LiteISP.py:1253,1265,1278 / 2056,2065,2075)."""
+    return F.conv2d(x, sd[p + ".weight"], sd.get(p + ".bias"), stride=2)
+
+
+def _unet_isp(sd, x, m_blocks):
+    """Shared body of ISPUNet_GFM_LSC.forward (LiteISP.py:1340-1381, m_blocks Res_GFM blocks per modulation stage) and
+    ResUNet.forward (LiteISP.py:2122-2146, m_blocks = 0: no condition, no lens shading)."""
+    raw = x[0]
+    fea_intro = conv(sd, "intro", raw)
+    vec = None
+    if m_blocks:
+        vec = color_condition_gfm(sd, "classifier", x[1])
+        fea_intro = fea_intro * (lens_shading(sd, "lsc", x[2]) + 1)
+
+    def mod(p, t):
+        if m_blocks == 1:
+            return res_gfm(sd, p, t, vec)
+        for i in range(m_blocks):
+            t = res_gfm(sd, f"{p}.{i}", t, vec)
+        return t
+
+    def enc(p, t, lead):
+        o = 0
+        if lead:
+            t = conv(sd, f"{p}.0", t)
+            o = 1
+        return F.leaky_relu(conv(sd, f"{p}.{o + 1}", rca_group(sd, f"{p}.{o}", t, nb=2)), 0.1)
+
+    d1 = _down2x2(sd, "down1", enc("encoder1", mod("encoder_modulation1", fea_intro), False))
+    d2 = _down2x2(sd, "down2", enc("encoder2", mod("encoder_modulation2", d1), False))
+    d3 = _down2x2(sd, "down3", enc("encoder3", mod("encoder_modulation3", d2), True))
+    mid = mod("middle_modulation", d3)
+    mid = conv(sd, "middle.2", rca_group(sd, "middle.1", conv(sd, "middle.0", mid), nb=4)) + d3
+    u = mid
+    for lvl, skip in ((3, d2), (2, d1), (1, fea_intro)):
+        u = F.pixel_shuffle(conv(sd, f"up{lvl}.0", u), 2)
+        u = conv(sd, f"decoder{lvl}.1", rca_group(sd, f"decoder{lvl}.0", u, nb=2))
+        u = mod(f"decoder_modulation{lvl}", u) + skip
+    return conv(sd, "tail.2", F.pixel_shuffle(conv(sd, "tail.0", u), 2))
+
+
+@torch.no_grad()
+def ispunet_gfm_lsc_forward(sd, x, m_blocks=2):
+    """ISPUNet_GFM_LSC.forward, LiteISP.py:1228-1381."""
+    return _unet_isp(sd, x, m_blocks)
+
+
+@torch.no_grad()
+def resunet_forward(sd, x):
+    """ResUNet.forward, LiteISP.py:2038-2146 (reads x[0] only)."""
+    return _unet_isp(sd, x, 0)
+
+
+@torch.no_grad()
+def mwisp_forward(sd, x):
+    """MWISP.forward, LiteISP.py:2149-2218: DWTForward_/DWTInverse_ (networks.py:10-48, the same Haar bank as DWTForward),
+    nn.PReLU() with one shared slope, RCAGroups of 20 blocks."""
+    def prelu(p, t):
+        return F.prelu(t, sd[p + ".weight"])
+
+    c1 = dwt_forward(x[0])
+    c2 = rca_group(sd, "down1.2", prelu("down1.1", conv(sd, "down1.0", c1)), nb=20)
+    c3 = rca_group(sd, "down2.3", prelu("down2.2", conv(sd, "down2.1", dwt_forward(c2))), nb=20)
+    c4 = prelu("down3.2", conv(sd, "down3.1", dwt_forward(c3)))
+    m = rca_group(sd, "middle.1", rca_group(sd, "middle.0", c4, nb=20), nb=20)
+    c5 = dwt_inverse(prelu("up1.1", conv(sd, "up1.0", m))) + c3
+    c6 = dwt_inverse(prelu("up2.2", conv(sd, "up2.1", rca_group(sd, "up2.0", c5, nb=20)))) + c2
+    c7 = conv(sd, "up3.1", rca_group(sd, "up3.0", c6, nb=20)) + c1
+    return F.pixel_shuffle(conv(sd, "tail.1", dwt_inverse(c7)), 2)
+
+
 # ----------------------------------------------------------------------------- GroupMix
 def _bn(sd, p, x):
     return F.batch_norm(x, sd[p + ".running_mean"], sd[p + ".running_var"], sd[p + ".weight"], sd[p + ".bias"],

@@ -1,7 +1,8 @@
 """Host-side mirror of the reference's ``models/LiteISP.py`` (hot-path classes).
 
   color_block 23-30, Color_Condition_GFM 345-361, Lens_Shading_Correction 363-378,
-  Res_GFM 537-559, LiteISPNet_GFM_LSC 1924-2035 (BASELINE config 1).
+  Res_GFM 537-559, LiteISPNet_GFM_LSC 1924-2035 (BASELINE config 1), LiteISPNet 2322-2412,
+  ISPUNet_GFM_LSC 1228-1381, ResUNet 2038-2146, MWISP 2149-2218 (the other ISP variants, same kernels re-wired).
 forward([raw, cond, coord]) -> (B,3,2H,2W), as in the reference.
 """
 from __future__ import annotations
@@ -195,3 +196,126 @@ class LiteISPNet(nn.Module):
         u1 = self.up1._f(u2, res=h)
         t = self.tail[0]._f(u1, store=ops.STORE_PS2)
         return self.tail[2]._f(t, store=ops.STORE_NCHW)
+
+
+# ----------------------------------------------------------------------------- the other ISP variants
+def _modulate(mods, x, vec):
+    """N.seq(*[Res_GFM ...]) called on the (fea, vec) tuple: one block (seq collapses it) or a Sequential of them."""
+    for m in ([mods] if isinstance(mods, Res_GFM) else list(mods)):
+        x = m._f(x, vec)
+    return x
+
+
+class _UNetISP(nn.Module):
+    """Shared wiring of ISPUNet_GFM_LSC and ResUNet: 3-level UNet of RCAGroups with learned 2x2 stride-2 down-samplers and
+    1x1 conv + PixelShuffle up-samplers, chan = 32 -> 64 -> 128 -> 256."""
+
+    def _build(self, chan, n_blocks, modulation):
+        cond_c, mb = modulation if modulation else (None, 0)
+
+        def mod(c):
+            return N.seq(*[Res_GFM(in_nc=c, chan=c, cond_c=cond_c, out_nc=c, nf=c * 2) for _ in range(mb)])
+
+        self.intro = N.seq(Conv2d(4, chan, 3, 1, 1))
+        if modulation:
+            self.lsc = Lens_Shading_Correction(in_channels=2, out_c=chan, nf=chan)
+            self.encoder_modulation1 = mod(chan)
+        self.encoder1 = N.seq(N.RCAGroup(in_channels=chan, out_channels=chan, nb=n_blocks), Conv2d(chan, chan, 3, 1, 1),
+                              nn.LeakyReLU(negative_slope=1e-1, inplace=True))
+        self.down1 = N.Down2x2(chan, chan * 2)
+        chan *= 2
+        if modulation:
+            self.encoder_modulation2 = mod(chan)
+        self.encoder2 = N.seq(N.RCAGroup(in_channels=chan, out_channels=chan, nb=n_blocks), Conv2d(chan, chan, 3, 1, 1),
+                              nn.LeakyReLU(negative_slope=1e-1, inplace=True))
+        self.down2 = N.Down2x2(chan, chan * 2)
+        chan *= 2
+        if modulation:
+            self.encoder_modulation3 = mod(chan)
+        self.encoder3 = N.seq(Conv2d(chan, chan, 3, 1, 1), N.RCAGroup(in_channels=chan, out_channels=chan, nb=n_blocks),
+                              Conv2d(chan, chan, 3, 1, 1), nn.LeakyReLU(negative_slope=1e-1, inplace=True))
+        self.down3 = N.Down2x2(chan, chan * 2)
+        chan *= 2
+        if modulation:
+            self.middle_modulation = mod(chan)
+        self.middle = N.seq(Conv2d(chan, chan, 3, 1, 1), N.RCAGroup(in_channels=chan, out_channels=chan, nb=n_blocks * 2),
+                            Conv2d(chan, chan, 3, 1, 1))
+        for lvl in (3, 2, 1):
+            setattr(self, f"up{lvl}", N.seq(Conv2d(chan, chan * 2, 1, bias=False), nn.PixelShuffle(2)))
+            chan //= 2
+            if modulation:
+                setattr(self, f"decoder_modulation{lvl}", mod(chan))
+            setattr(self, f"decoder{lvl}", N.seq(N.RCAGroup(in_channels=chan, out_channels=chan, nb=n_blocks), N.conv(chan, chan, mode='C')))
+        self.tail = N.seq(N.conv(chan, chan * 4, mode='C'), nn.PixelShuffle(upscale_factor=2), N.conv(chan, 3, mode='C'))
+        self._modulated = bool(modulation)
+
+    def forward(self, x):
+        raw = ops.to_nhwc(x[0])
+        vec = None
+        if self._modulated:
+            lsc_fea = self.lsc._f(ops.to_nhwc(x[2]))
+            fea_intro = self.intro._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea)          # intro(x) * (lsc + 1)
+            vec = self.classifier._f(ops.to_nhwc(x[1]))
+        else:
+            fea_intro = self.intro._f(raw)
+        m = (lambda name, t: _modulate(getattr(self, name), t, vec)) if self._modulated else (lambda name, t: t)
+        d1 = self.down1._f(self.encoder1._f(m("encoder_modulation1", fea_intro)))
+        d2 = self.down2._f(self.encoder2._f(m("encoder_modulation2", d1)))
+        d3 = self.down3._f(self.encoder3._f(m("encoder_modulation3", d2)))
+        mid = self.middle._f(m("middle_modulation", d3), res=d3)
+        u = mid
+        for lvl, skip in ((3, d2), (2, d1), (1, fea_intro)):
+            u = getattr(self, f"decoder{lvl}")._f(getattr(self, f"up{lvl}")._f(u))
+            if self._modulated:          # u = modulation(u) + skip: the block's own residual occupies the conv epilogue
+                u = ops.add(m(f"decoder_modulation{lvl}", u), skip)
+            else:
+                u = ops.add(u, skip)
+        t = self.tail[0]._f(u, store=ops.STORE_PS2)
+        return self.tail[2]._f(t, store=ops.STORE_NCHW)
+
+
+class ISPUNet_GFM_LSC(_UNetISP):
+    """models/LiteISP.py:1228-1381.  forward([raw, cond, coord]) -> (B,3,2H,2W)."""
+
+    def __init__(self, cond_c=32, chan=32, m_blocks=2):
+        super().__init__()
+        self.classifier = Color_Condition_GFM(in_channels=4, out_c=cond_c)
+        self._build(chan, 2, (cond_c, m_blocks))
+
+
+class ResUNet(_UNetISP):
+    """models/LiteISP.py:2038-2146: ISPUNet without colour condition, lens shading and modulation.  forward(x) reads x[0]."""
+
+    def __init__(self):
+        super().__init__()
+        self._build(32, 2, None)
+
+
+class MWISP(nn.Module):
+    """models/LiteISP.py:2149-2218 (multi-level wavelet ISP: Haar DWT / IDWT around RCAGroups of 20 blocks, PReLU activations).
+    forward(x, c=None) reads x[0] (N,4,H,W) and returns (N,3,2H,2W)."""
+
+    def __init__(self):
+        super().__init__()
+        c1, c2, c3, n_b = 64, 128, 128, 20
+        self.head = N.DWTForward_()
+        self.down1 = N.seq(Conv2d(4 * 4, c1, 3, 1, 1), nn.PReLU(), N.RCAGroup(in_channels=c1, out_channels=c1, nb=n_b))
+        self.down2 = N.seq(N.DWTForward_(), Conv2d(c1 * 4, c2, 3, 1, 1), nn.PReLU(), N.RCAGroup(in_channels=c2, out_channels=c2, nb=n_b))
+        self.down3 = N.seq(N.DWTForward_(), Conv2d(c2 * 4, c3, 3, 1, 1), nn.PReLU())
+        self.middle = N.seq(N.RCAGroup(in_channels=c3, out_channels=c3, nb=n_b), N.RCAGroup(in_channels=c3, out_channels=c3, nb=n_b))
+        self.up1 = N.seq(Conv2d(c3, c2 * 4, 3, 1, 1), nn.PReLU(), N.DWTInverse_())
+        self.up2 = N.seq(N.RCAGroup(in_channels=c2, out_channels=c2, nb=n_b), Conv2d(c2, c1 * 4, 3, 1, 1), nn.PReLU(), N.DWTInverse_())
+        self.up3 = N.seq(N.RCAGroup(in_channels=c1, out_channels=c1, nb=n_b), Conv2d(c1, 16, 3, 1, 1))
+        self.tail = N.seq(N.DWTInverse_(), Conv2d(4, 12, 3, 1, 1), nn.PixelShuffle(upscale_factor=2))
+
+    def forward(self, x, c=None):
+        c1 = self.head._f(ops.to_nhwc(x[0]))
+        c2 = self.down1._f(c1)
+        c3 = self.down2._f(c2)
+        c4 = self.down3._f(c3)
+        m = self.middle._f(c4)
+        c5 = ops.add(self.up1._f(m), c3)
+        c6 = ops.add(self.up2._f(c5), c2)
+        c7 = self.up3._f(c6, res=c1)
+        t = self.tail[0]._f(c7)
+        return self.tail[1]._f(t, store=ops.STORE_PS2_NCHW)

@@ -54,6 +54,7 @@ PROTOTYPES = {
     "rcn_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_dwt_forward": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_dwt_inverse": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "rcn_space_to_depth2": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_depthwise_conv": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _I, _P, _I, _P, _I, _P]),
     "rcn_eb_forward": (_I, [_P, _I, _I, _L, _I, _P, _P, _P, _I, _P, _I, _P, _F, _P]),
     "rcn_eb_dequantize": (_I, [_P, _I, _L, _I, _P, _P, _I, _P]),

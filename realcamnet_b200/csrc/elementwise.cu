@@ -214,6 +214,23 @@ __global__ void dwt_forward_kernel(const float* __restrict__ x, int H, int W, in
     }
 }
 
+// space-to-depth by 2: (N,H,W,C) -> (N,H/2,W/2,4C), channel (i*2+j)*C + c <- pixel (2y+i, 2x+j) -- turns a learned 2x2 stride-2
+// conv (the `down` layers of ISPUNet_GFM_LSC / ResUNet, models/LiteISP.py:1253,2056) into a 1x1 contraction
+__global__ void space_to_depth2_kernel(const float* __restrict__ x, int H, int W, int C, int ldx, long long total,
+                                       float* __restrict__ y, int ldy) {
+    const int Ho = H / 2, Wo = W / 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        long long t = i / C;
+        const int q = (int)(t & 3); t >>= 2;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        y[((long long)(n * Ho + ho) * Wo + wo) * ldy + q * C + c] =
+            x[((long long)(n * H + 2 * ho + (q >> 1)) * W + 2 * wo + (q & 1)) * ldx + c];
+    }
+}
+
 // Haar synthesis: (N,H,W,4C) -> (N,2H,2W,C)
 __global__ void dwt_inverse_kernel(const float* __restrict__ x, int H, int W, int C, int ldx, long long total,
                                    float* __restrict__ y, int ldy) {
@@ -456,6 +473,15 @@ extern "C" int rcn_dwt_forward(const float* x, int N, int H, int W, int C, int l
     dwt_forward_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, ldx, total, y, ldy);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_dwt_forward");
+    return RCN_OK;
+}
+
+extern "C" int rcn_space_to_depth2(const float* x, int N, int H, int W, int C, int ldx, float* y, int ldy, void* stream) {
+    RCN_CHECK_ARG(x && y && H % 2 == 0 && W % 2 == 0 && ldy >= 4 * C, "rcn_space_to_depth2: bad arguments");
+    const long long total = (long long)N * (H / 2) * (W / 2) * 4 * C;
+    space_to_depth2_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, ldx, total, y, ldy);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_space_to_depth2");
     return RCN_OK;
 }
 

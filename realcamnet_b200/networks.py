@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's ``models/networks.py`` block library (hot-path subset).
 
   seq            models/networks.py:117-128     conv (string-mode factory)  models/networks.py:146-221
-  DWTForward/DWTInverse  models/networks.py:224-249
+  DWTForward/DWTInverse  models/networks.py:224-249     DWTForward_/DWTInverse_  models/networks.py:10-48
   CALayer 255-270, RCABlock 296-311, RCAGroup 317-335
 Only the layer modes that occur on the RAW->sRGB path are accepted by ``conv``: 'C', 'R'/'r', 'L'/'l', '2'.
 """
@@ -43,12 +43,14 @@ class _Seq(nn.Sequential):
             last_conv = isinstance(m, Conv2d) and not any(isinstance(n, Conv2d) or hasattr(n, "_f") for n in mods[i + 1:])
             if isinstance(m, Conv2d):
                 act, slope, store, j = ACT_NONE, 0.0, STORE_NHWC, i + 1
-                while j < len(mods) and isinstance(mods[j], (nn.ReLU, nn.LeakyReLU, nn.PixelShuffle)):
+                while j < len(mods) and isinstance(mods[j], (nn.ReLU, nn.LeakyReLU, nn.PReLU, nn.PixelShuffle)):
                     n = mods[j]
                     if isinstance(n, nn.ReLU) and act == ACT_NONE:
                         act = ACT_RELU
                     elif isinstance(n, nn.LeakyReLU) and act == ACT_NONE:
                         act, slope = ACT_LRELU, n.negative_slope
+                    elif isinstance(n, nn.PReLU) and act == ACT_NONE and store == STORE_NHWC:
+                        act, slope = ACT_LRELU, prelu_slope(n)
                     elif isinstance(n, nn.PixelShuffle) and store == STORE_NHWC and n.upscale_factor == 2:
                         store = STORE_PS2
                     else:
@@ -66,6 +68,46 @@ class _Seq(nn.Sequential):
         if res is not None:
             raise RuntimeError("residual could not be fused")
         return x
+
+    def forward(self, x):
+        return ops.to_nchw(self._f(ops.to_nhwc(x)))
+
+
+_prelu_cache = {}
+
+
+def prelu_slope(m: nn.PReLU) -> float:
+    """nn.PReLU() with its single shared parameter (the only form on the path, models/LiteISP.py:2160-2193) is LeakyReLU with a
+    learned slope: read once per parameter version (a device->host read, outside any graph capture)."""
+    if m.weight.numel() != 1:
+        raise NotImplementedError("per-channel PReLU is not on the B200 path")
+    key = (m.weight._version, m.weight.data_ptr())
+    hit = _prelu_cache.get(id(m))
+    if hit is None or hit[0] != key or hit[2]() is not m.weight:
+        import weakref
+        hit = _prelu_cache[id(m)] = (key, float(m.weight.detach().reshape(-1)[0].item()), weakref.ref(m.weight))
+    return hit[1]
+
+
+class Down2x2(nn.Conv2d):
+    """nn.Conv2d(C, O, 2, 2): the learned down-sampler of ISPUNet_GFM_LSC / ResUNet (models/LiteISP.py:1253,2056).  Runs as
+    rcn_space_to_depth2 + a 1x1 contraction over the (i, j, c)-ordered weights."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__(in_channels, out_channels, 2, 2)
+        self._packed = None
+
+    def _pack(self):
+        w, b = self.weight, self.bias
+        key = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()))
+        if self._packed is None or self._packed[0] != key or self._packed[2] is not w:
+            O, C = w.shape[0], w.shape[1]
+            w2 = w.detach().permute(0, 2, 3, 1).reshape(O, 4 * C).contiguous()     # [o][(i*2+j)*C + c]
+            self._packed = (key, ops.pack_weight(w2, b), w)
+        return self._packed[1]
+
+    def _f(self, x, **kw):
+        return ops.conv2d(ops.space_to_depth2(x), self._pack(), **kw)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
@@ -120,6 +162,33 @@ class DWTInverse(_Haar):
         super().__init__()
         w = torch.tensor([[[[0.5, 0.5], [0.5, 0.5]]], [[[0.5, 0.5], [-0.5, -0.5]]],
                           [[[0.5, -0.5], [0.5, -0.5]]], [[[0.5, -0.5], [-0.5, 0.5]]]]).repeat(in_channels // 4, 1, 1, 1)
+        self.weight = nn.Parameter(w, requires_grad=False)
+
+    def _f(self, x):
+        return ops.dwt_inverse(x)
+
+
+class DWTForward_(_Haar):
+    """models/networks.py:10-27: the functional twin of DWTForward (the flipped filter bank it builds equals DWTForward's, one
+    (4,1,2,2) weight shared by all channels)."""
+
+    def __init__(self):
+        super().__init__()
+        w = torch.tensor([[[[0.5, 0.5], [0.5, 0.5]]], [[[0.5, 0.5], [-0.5, -0.5]]],
+                          [[[0.5, -0.5], [0.5, -0.5]]], [[[0.5, -0.5], [-0.5, 0.5]]]])
+        self.weight = nn.Parameter(w, requires_grad=False)
+
+    def _f(self, x):
+        return ops.dwt_forward(x)
+
+
+class DWTInverse_(_Haar):
+    """models/networks.py:30-48."""
+
+    def __init__(self):
+        super().__init__()
+        w = torch.tensor([[[[0.5, 0.5], [0.5, 0.5]]], [[[0.5, 0.5], [-0.5, -0.5]]],
+                          [[[0.5, -0.5], [0.5, -0.5]]], [[[0.5, -0.5], [-0.5, 0.5]]]])
         self.weight = nn.Parameter(w, requires_grad=False)
 
     def _f(self, x):

@@ -560,6 +560,28 @@ def dwt_inverse(x, out=None):
     return out
 
 
+def space_to_depth2(x, out=None):
+    """(N,H,W,C) -> (N,H/2,W/2,4C), channel (i*2+j)*C + c <- pixel (2y+i, 2x+j)"""
+    N, H, W, C, ldx = geom(x)
+    if out is None:
+        out = empty(N, H // 2, W // 2, 4 * C, like=x)
+    _C.check(_C.lib().rcn_space_to_depth2(_ptr(x), N, H, W, C, ldx, _ptr(out), geom(out)[4], _stream()), "rcn_space_to_depth2")
+    return out
+
+
+def add(x, y, out=None):
+    """x + y (scale_add with a unit gain)"""
+    C = x.shape[-1]
+    key = (C, str(x.device))
+    ones = _ones_cache.get(key)
+    if ones is None:
+        ones = _ones_cache[key] = torch.ones(C, device=x.device, dtype=torch.float32)
+    return scale_add(x, ones, per_n=False, res=y, out=out)
+
+
+_ones_cache = {}
+
+
 def depthwise_conv(x, w_taps, bias, k, add_input=False, mul=None, out=None):
     """w_taps: [k*k][C] (tap-major) device tensor."""
     N, H, W, C, ldx = geom(x)

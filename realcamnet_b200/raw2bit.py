@@ -358,8 +358,10 @@ class raw_compression_tcm_final(SliceCodecModel):
     def _g_s(self, y_hat, clamp=False):
         h = y_hat
         mods = list(self.g_s)
-        for m in mods[:-3]:
-            h = m._f(h)
+        ts = self.tail_start if self.tail_start is not None else len(mods) - 3
+        for i, m in enumerate(mods[:-3]):
+            with self._tail_scope(i >= ts):     # experiments only (profiles/r2_precision_policy.md): a tail starting earlier
+                h = m._f(h)
         # tail at full resolution (raw2bit.py:1680-1682): subpel -> ResidualBlock -> subpel.  The 128-channel maps are 2.1 GB
         # each: the producers write the consumers' bf16 operand planes themselves, and the ResidualBlock output (read by the
         # last conv only) never exists in fp32.

@@ -205,10 +205,11 @@ class SliceCodecModel(CompressionModel):
     # x_hat error 4.7e-4 of max at T=256, profiles/r2_precision_policy.md).  decompress() shares _g_s, so decode == forward stays
     # bit-exact.  tail_engine = None / "bf16x3" turns the policy off; it only applies when the global engine is "bf16x3".
     tail_engine = os.environ.get("RCN_TAIL_ENGINE", "fp16") or None
+    tail_start = int(os.environ["RCN_TAIL_START"]) if os.environ.get("RCN_TAIL_START") else None   # first g_s module of the tail (None = default)
 
-    def _tail_scope(self):
+    def _tail_scope(self, active=True):
         te = self.tail_engine
-        return ops.engine_scope(te if (te and te != "bf16x3" and ops.get_engine() == "bf16x3") else None)
+        return ops.engine_scope(te if (active and te and te != "bf16x3" and ops.get_engine() == "bf16x3") else None)
 
     def _invalidate_graphs(self):
         """Captured graphs hold raw pointers to packed weights, GDN / entropy-bottleneck parameters and the CDF tables: whatever
@@ -433,7 +434,7 @@ class StageRunner:
         self.inputs = inputs
         self.entry = None
         if getattr(model, "_use_graphs", False):
-            full = (key, ops.get_engine(), getattr(model, "tail_engine", None)) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
+            full = (key, ops.get_engine(), getattr(model, "tail_engine", None), getattr(model, "tail_start", None)) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
             cache = model.__dict__.setdefault("_graph_cache", {})
             ver = model._state_version()
             if cache.get("_version") != ver:        # weights / tables were edited in place since the graphs were captured
@@ -542,8 +543,10 @@ class TCM(SliceCodecModel):
     def _g_s(self, y_hat, clamp=False):
         h = y_hat
         mods = list(self.g_s)
-        for m in mods[:-1]:
-            h = m._f(h)
+        ts = self.tail_start if self.tail_start is not None else len(mods) - 1
+        for i, m in enumerate(mods[:-1]):
+            with self._tail_scope(i >= ts):
+                h = m._f(h)
         with self._tail_scope():
             return mods[-1]._f(h, store=ops.STORE_PS2_NCHW, act=ops.ACT_CLAMP01 if clamp else ops.ACT_NONE)
 

@@ -24,13 +24,32 @@ from oracle import inputs, ref_import, weights  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
-def main(only_new=False):
+def main(only_new=False, only_r2=False):
     ref = ref_import.import_reference()
     torch.set_grad_enabled(False)
-    if only_new:      # fixtures added later in the round: leave the committed earlier ones untouched
+    if only_r2:       # fixtures added in round 2: leave the committed earlier ones untouched
+        return isp_variants(ref)
+    if only_new:      # fixtures added later in round 1
         return extra(ref)
     base(ref)
     extra(ref)
+    isp_variants(ref)
+
+
+ISP_VARIANTS = (("ISPUNet_GFM_LSC", 1241, 128), ("ResUNet", 1242, 128), ("MWISP", 1243, 128))
+
+
+def isp_variants(ref):
+    """the remaining ISP variants (LiteISP.py:1228-1381, 2038-2146, 2149-2218), one 4x128x128 tile each."""
+    for name, seed, T in ISP_VARIANTS:
+        m = getattr(ref.LiteISP, name)().eval()
+        weights.fill_(m, seed=0)
+        x = inputs.make_inputs(T, seed=seed, cond_size=128)
+        o = m(x)
+        np.savez_compressed(os.path.join(OUT, f"isp_{name}_T{T}.npz"), out_sub=o[:, :, ::2, ::2].numpy(),
+                            out_abs_sum=np.float64(o.double().abs().sum()),
+                            weights_abs_sum=np.float64(weights.checksum(m.state_dict())["abs_sum"]))
+        print(name, tuple(o.shape), float(o.abs().max()))
 
 
 def base(ref):
@@ -122,4 +141,4 @@ def extra(ref):
 
 
 if __name__ == "__main__":
-    main(only_new="--extra" in sys.argv)
+    main(only_new="--extra" in sys.argv, only_r2="--r2" in sys.argv)

@@ -128,14 +128,17 @@ def test_update_builds_the_oracle_tables():
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference/models"), reason="reference only exists in the authoring container")
-@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200", "tcm", "convgma", "gmaatten", "gmablock", "liteisp_plain"])
+@pytest.mark.parametrize("which", ["final", "liteisp", "gma80", "gma200", "tcm", "convgma", "gmaatten", "gmablock", "liteisp_plain",
+                                   "ISPUNet_GFM_LSC", "ResUNet", "MWISP"])
 def test_state_dict_names_match_reference(which):
     from oracle import ref_import
 
     ref = ref_import.import_reference()
     from realcamnet_b200 import LiteISP, groupmix, raw2bit, tcm
 
-    if which == "liteisp_plain":
+    if which in ("ISPUNet_GFM_LSC", "ResUNet", "MWISP"):
+        a, b = getattr(ref.LiteISP, which)(), getattr(LiteISP, which)()
+    elif which == "liteisp_plain":
         a, b = ref.LiteISP.LiteISPNet(), LiteISP.LiteISPNet()
     elif which == "tcm":
         a, b = ref.tcm.TCM(), tcm.TCM()

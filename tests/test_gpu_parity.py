@@ -117,7 +117,9 @@ def test_conv2d_fp16_single_pass_engine(dev, case):
                 y2 = ops.to_nchw(ops.conv2d(None, pc2, presplit=sp))
                 mid = F.relu(ref16)
                 mid = F.pixel_shuffle(mid, 2) if up == 2 else mid
-                assert rel(y2, F.conv2d(mid.half().float(), w2.half().float(), None, padding=1)) < 2e-5, (case, store)
+                # the hand-over rounds the first layer's fp32 result to fp16: a 1e-7 accumulation-order difference flips the
+                # rounding of a few elements by one fp16 ulp (2^-11), hence the looser bar on the chained result
+                assert rel(y2, F.conv2d(mid.half().float(), w2.half().float(), None, padding=1)) < 1e-3, (case, store)
     # planes of one format cannot feed an engine that reads the other
     sp = ops.split_operand(xn, pc.cp, stride=s, passes=1, fmt=ops.FMT_F16)
     with pytest.raises(ValueError, match="format"):
@@ -442,6 +444,26 @@ def test_liteisp_plain_matches_fixture(dev, engine, golden_dir):
     x = inputs.make_inputs(256, seed=1237)
     out = m.to(dev).eval()([t.to(dev) for t in x])
     assert tuple(out.shape) == (1, 3, 512, 512)
+    assert rel(out[:, :, ::2, ::2], torch.from_numpy(gold["out_sub"])) < TOL
+    assert abs(float(out.double().abs().sum()) - float(gold["out_abs_sum"])) / float(gold["out_abs_sum"]) < 1e-4
+
+
+@pytest.mark.parametrize("name,seed,fn", [("ISPUNet_GFM_LSC", 1241, "ispunet_gfm_lsc_forward"), ("ResUNet", 1242, "resunet_forward"),
+                                          ("MWISP", 1243, "mwisp_forward")])
+def test_isp_variants_match_oracle_and_fixture(dev, engine, golden_dir, name, seed, fn):
+    """ISPUNet_GFM_LSC / ResUNet / MWISP (LiteISP.py:1228-1381, 2038-2146, 2149-2218) against the oracle on the same
+    input and against the fixture the unmodified reference produced (learned 2x2 stride-2 down-samplers = rcn_space_to_depth2 +
+    1x1 contraction; PReLU = LeakyReLU with the learned slope; DWTForward_/DWTInverse_ = the Haar kernels)."""
+    from realcamnet_b200 import LiteISP
+
+    gold = np.load(os.path.join(golden_dir, f"isp_{name}_T128.npz"))
+    m = getattr(LiteISP, name)()
+    weights.fill_(m, seed=0)
+    sd = cpu_sd(m)
+    x = inputs.make_inputs(128, seed=seed, cond_size=128)
+    out = m.to(dev).eval()([t.to(dev) for t in x])
+    assert tuple(out.shape) == (1, 3, 256, 256)
+    assert rel(out, getattr(refpath, fn)(sd, x)) < TOL
     assert rel(out[:, :, ::2, ::2], torch.from_numpy(gold["out_sub"])) < TOL
     assert abs(float(out.double().abs().sum()) - float(gold["out_abs_sum"])) / float(gold["out_abs_sum"]) < 1e-4
 

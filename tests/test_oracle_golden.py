@@ -147,3 +147,18 @@ def test_liteisp_plain_matches_reference_fixture(golden_dir):
     assert abs(weights.checksum(sd)["abs_sum"] - float(g["weights_abs_sum"])) < 1e-3
     o = refpath.liteisp_forward(sd, inputs.make_inputs(256, seed=1237))
     np.testing.assert_array_equal(o[:, :, ::2, ::2].numpy(), g["out_sub"])
+
+
+@pytest.mark.parametrize("name,seed,fn", [("ISPUNet_GFM_LSC", 1241, "ispunet_gfm_lsc_forward"), ("ResUNet", 1242, "resunet_forward"),
+                                          ("MWISP", 1243, "mwisp_forward")])
+def test_isp_variants_match_reference_fixtures(golden_dir, name, seed, fn):
+    """SURVEY 8f-4 (LiteISP.py:1228-1381, 2038-2146, 2149-2218): the oracle restatement == the unmodified reference, bit for bit."""
+    from realcamnet_b200 import LiteISP
+
+    g = np.load(os.path.join(golden_dir, f"isp_{name}_T128.npz"))
+    m = getattr(LiteISP, name)()
+    weights.fill_(m, seed=0)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    assert abs(weights.checksum(sd)["abs_sum"] - float(g["weights_abs_sum"])) < 1e-3
+    o = getattr(refpath, fn)(sd, inputs.make_inputs(128, seed=seed, cond_size=128))
+    np.testing.assert_array_equal(o[:, :, ::2, ::2].numpy(), g["out_sub"])
