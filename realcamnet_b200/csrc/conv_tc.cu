@@ -37,6 +37,12 @@ constexpr uint32_t SPIN_LIMIT = 1u << 24;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+template <typename T>
+__device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
+__device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
+__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
+
 // operand-plane element formats (rcn_conv_desc.in_fmt / out_fmt): both are 16-bit, so planes, tensor maps and smem tiles are
 // format-agnostic; only the conversions and the MMA instruction descriptor differ
 __device__ __forceinline__ uint16_t to_plane(float v, int f16) {
@@ -71,6 +77,36 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// shared-space-address variants (the issue loops keep barrier addresses as 32-bit uniform values)
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_try_wait_a(bar, parity)) {
+        if (++spins > SPIN_LIMIT) __trap();
+    }
+}
+// one lane of a CONVERGED warp: ptxas issues the uniform-datapath instructions (UTCHMMA, UTCBAR, UTMALDG) of an elect.sync
+// region directly; from an `if (lane == 0)` region it wraps every one of them in an ELECT / 7 x R2UR.BROADCAST / BRA.U.ANY loop
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
     asm volatile(
         "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
@@ -96,6 +132,9 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_a(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // the MMAs of one pipeline stage: KSTEPS k16 steps x (3 split passes | 1 pass), fully unrolled with constant descriptor advances
 template <int PASSES, int KSTEPS>
@@ -257,11 +296,6 @@ struct EpiRegs {
 };
 enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512,
        EF_DUAL = 1024, EF_F16OUT = 2048 };
-template <typename T>
-__device__ __forceinline__ void opaque_ptr(T*& v) { asm volatile("" : "+l"(v)); }
-__device__ __forceinline__ void opaque(int& v) { asm volatile("" : "+r"(v)); }
-__device__ __forceinline__ void opaque(uint32_t& v) { asm volatile("" : "+r"(v)); }
-__device__ __forceinline__ void opaque(float& v) { asm volatile("" : "+f"(v)); }
 __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg, bool dual) {
     EpiRegs r;
     r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
@@ -508,6 +542,54 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, in
     }
 }
 
+// The MMA issue loop of one issuing warp, run by the whole (converged) warp with the tcgen05 instructions behind elect.sync.
+// Everything it needs is hoisted into registers first: reading kernel parameters from the constant bank inside the loop cost an
+// LDC / LDCU round trip per use (~100 of the ~830 cycles per stage the old `if (lane == 0)` loop took at 4 MMAs per stage).
+// Descriptors are advanced arithmetically: the start-address field (bits 0-13, 16-byte units) of the stage-0 descriptor plus
+// stage * (stage_bytes / 16) never carries out of the field (shared memory is < 256 KB).
+struct MmaLoopArgs {
+    uint32_t total_tiles, tiles_n, grid, first_tile;
+    int Ntile, Cout, kiters, stages, mw, owner_mode;   // owner_mode 0: every stage (all of it, or this warp's half of its k16 steps); 1: stages with gstage % 2 == mw
+    uint32_t sb16, oB, oAlo, oBlo, koff;                // descriptor offsets in 16-byte units
+    uint32_t full_bar, empty_bar, tmem_full, tmem_empty;   // shared-space addresses of the barrier arrays
+    uint32_t tmem_base, idesc_fmt;
+    uint64_t desc0;                                      // A_hi descriptor of stage 0
+    int skip_mma;
+};
+template <int PASSES, int SPW>
+__device__ __forceinline__ void mma_issue_loop(const MmaLoopArgs& A) {
+    uint32_t stage = 0, phase = 0, local = 0, gstage = 0;
+    for (uint32_t t = A.first_tile; t < A.total_tiles; t += A.grid, ++local) {
+        const int n0 = (int)(t % A.tiles_n) * A.Ntile;
+        int nact = A.Cout - n0;
+        if (nact > A.Ntile) nact = A.Ntile;
+        nact = (nact + 15) & ~15;
+        // instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), N >> 3 at 17, M >> 4 at 24
+        const uint32_t idesc = (1u << 4) | A.idesc_fmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t ab = local & 1;
+        mbar_wait_a(A.tmem_empty + 8u * ab, ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator pair
+        tc_fence_after();
+        const uint32_t tmem_d = A.tmem_base + ab * 256 + (uint32_t)A.mw * 128;
+        uint32_t acc = 0;
+        for (int it = 0; it < A.kiters; ++it, ++gstage) {
+            if (A.owner_mode == 0 || (int)(gstage & 1u) == A.mw) {
+                mbar_wait_a(A.full_bar + 8u * stage, phase);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a_hi = A.desc0 + (uint64_t)(stage * A.sb16 + A.koff);
+                    if (!A.skip_mma) issue_stage<PASSES, SPW>(tmem_d, a_hi, a_hi + A.oB, a_hi + A.oAlo, a_hi + A.oBlo, idesc, acc);
+                    umma_commit_a(A.empty_bar + 8u * stage);  // frees the smem slot once this warp's MMAs on it have retired
+                }
+                __syncwarp();
+                acc = 1;
+            }
+            if (++stage == (uint32_t)A.stages) { stage = 0; phase ^= 1; }
+        }
+        if (elect_one()) umma_commit_a(A.tmem_full + 8u * ab);
+        __syncwarp();
+    }
+}
+
 // Persistent kernel: one CTA per SM walks tiles t = blockIdx.x, +gridDim.x, ...; tile t -> (m-tile, n-tile).
 // TMEM holds two 128-column accumulators so the epilogue of tile i overlaps the MMAs of tile i+1.
 // One instantiation per (activation, combinator, store path): the epilogue of a single variant is ~3k SASS instructions; with all
@@ -620,55 +702,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // TMEM accumulator (the epilogue adds the two in a fixed order).  Everything read from memory is first made warp-uniform
         // (REDUX results live in uniform registers) so that descriptors and addresses stay in the uniform datapath.
         const int mw = warp - 1;
-        const uint32_t tmem_u = __reduce_or_sync(0xffffffffu, tmem_base);
-        const uint32_t smem0 = __reduce_or_sync(0xffffffffu, smem_u32(smem));
-        int stage = 0;
-        uint32_t phase = 0;
-        uint32_t local = 0;
-        uint32_t gstage = 0;       // stages consumed by this CTA so far (all tiles)
-        if (lane == 0 && mw < nmma)
-        for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {
-            const int n0 = (int)(t % (uint32_t)P.tiles_n) * P.Ntile;
-            int nact = p.Cout - n0;
-            if (nact > P.Ntile) nact = P.Ntile;
-            nact = (nact + 15) & ~15;
-            // instruction descriptor: D = f32 (bit 4), A / B format at bits 7 / 10 (0 = f16, 1 = bf16), N >> 3 at 17, M >> 4 at 24
-            const uint32_t abfmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
-            const uint32_t idesc = (1u << 4) | abfmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t ab = local & 1;
-            mbar_wait(&tmem_empty[ab], ((local >> 1) & 1) ^ 1);  // epilogue has drained this accumulator pair
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_u + ab * 256 + (uint32_t)mw * 128;
-            uint32_t acc = 0;
-            for (int it = 0; it < kiters; ++it, ++gstage) {
-                if (nmma == 1 || splitk || (int)(gstage & 1u) == mw) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sa = smem0 + (uint32_t)stage * (uint32_t)stage_bytes;
-                    const uint32_t koff = splitk ? (uint32_t)(mw * (ksteps >> 1)) * 2u : 0u;   // this warp's k16 steps (32 B each)
-                    const uint64_t a_hi = make_kmajor_desc(sa, BLOCK_K) + koff, b_hi = make_kmajor_desc(sa + A_BYTES, BLOCK_K) + koff;
-                    const uint64_t a_lo = make_kmajor_desc(sa + A_BYTES + B_BYTES, BLOCK_K) + koff,
-                                   b_lo = make_kmajor_desc(sa + 2 * A_BYTES + B_BYTES, BLOCK_K) + koff;
-                    const int spw = splitk ? (ksteps >> 1) : ksteps;
-                    if (!(P.dbg & 2)) {
-                        if (P.passes == 3) {
-                            if (spw == 4) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else if (spw == 2) issue_stage<3, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else issue_stage<3, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        } else {
-                            if (spw == 4) issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else if (spw == 2) issue_stage<1, 2>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else issue_stage<1, 1>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                        }
-                    }
-                    acc = 1;
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once this warp's MMAs on it have retired
-                }
-                if (++stage == P.stages) { stage = 0; phase ^= 1; }
+        if (mw < nmma) {
+            MmaLoopArgs A;
+            A.total_tiles = (uint32_t)P.total_tiles; A.tiles_n = (uint32_t)P.tiles_n; A.grid = gridDim.x; A.first_tile = blockIdx.x;
+            A.Ntile = P.Ntile; A.Cout = p.Cout; A.kiters = kiters; A.stages = P.stages; A.mw = mw;
+            A.owner_mode = (nmma == 1 || splitk) ? 0 : 1;
+            A.sb16 = (uint32_t)stage_bytes >> 4;
+            A.oB = (uint32_t)A_BYTES >> 4; A.oAlo = (uint32_t)(A_BYTES + B_BYTES) >> 4; A.oBlo = (uint32_t)(2 * A_BYTES + B_BYTES) >> 4;
+            A.koff = splitk ? (uint32_t)(mw * (ksteps >> 1)) * 2u : 0u;   // this warp's k16 steps (32 B each)
+            A.full_bar = smem_u32(full_bar); A.empty_bar = smem_u32(empty_bar);
+            A.tmem_full = smem_u32(tmem_full); A.tmem_empty = smem_u32(tmem_empty);
+            A.tmem_base = tmem_base;
+            A.idesc_fmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
+            A.desc0 = make_kmajor_desc(smem_u32(smem), BLOCK_K);
+            A.skip_mma = (P.dbg & 2) != 0;
+            // opaque: keep the loop invariants in registers instead of re-reading the constant bank at every use
+            opaque(A.total_tiles); opaque(A.tiles_n); opaque(A.Ntile); opaque(A.Cout); opaque(A.kiters); opaque(A.stages);
+            opaque(A.owner_mode); opaque(A.sb16); opaque(A.oB); opaque(A.oAlo); opaque(A.oBlo); opaque(A.koff); opaque(A.idesc_fmt);
+            opaque(A.skip_mma); asm volatile("" : "+l"(A.desc0));
+            const int spw = splitk ? (ksteps >> 1) : ksteps;
+            if (P.passes == 3) {
+                if (spw == 4) mma_issue_loop<3, 4>(A);
+                else if (spw == 2) mma_issue_loop<3, 2>(A);
+                else mma_issue_loop<3, 1>(A);
+            } else {
+                if (spw == 4) mma_issue_loop<1, 4>(A);
+                else if (spw == 2) mma_issue_loop<1, 2>(A);
+                else mma_issue_loop<1, 1>(A);
             }
-            umma_commit(&tmem_full[ab]);
         }
-        __syncwarp();
     } else {
         // ================= epilogue: TMEM -> registers -> (warp-private transposition slab) -> fused element-wise -> global
         const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp_id % 4)

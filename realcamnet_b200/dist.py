@@ -13,6 +13,13 @@ import torch
 import torch.distributed as dist
 
 
+def _rank_world():
+    """(rank, world) of the default process group; (0, 1) when torch.distributed is not initialised (single GPU)."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def my_tiles(num_tiles: int, rank: int, world: int) -> List[int]:
     """Round-robin ownership: tile t -> rank t mod world."""
     return list(range(rank, num_tiles, world))
@@ -21,7 +28,7 @@ def my_tiles(num_tiles: int, rank: int, world: int) -> List[int]:
 def scatter_tiles(tiles: torch.Tensor | None, num_tiles: int, tile_shape: Sequence[int], src: int = 0, device=None,
                   dtype=torch.float32) -> torch.Tensor:
     """Rank `src` holds tiles (T,C,h,w); every rank receives the (len(my_tiles),C,h,w) stack it owns."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     mine = my_tiles(num_tiles, rank, world)
     out = torch.empty((len(mine), *tile_shape), device=device, dtype=dtype)
     if world == 1:
@@ -47,7 +54,7 @@ def scatter_tiles(tiles: torch.Tensor | None, num_tiles: int, tile_shape: Sequen
 def gather_bitstreams(local: List[bytes], num_tiles: int, dst: int = 0, device=None) -> List[bytes] | None:
     """Variable-length gather: each rank contributes the byte strings of its tiles (in my_tiles order);
     rank `dst` returns the list for all tiles in tile order, the others return None."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     if world == 1:
         return list(local)
     device = device or torch.device("cpu")
@@ -80,7 +87,40 @@ def gather_bitstreams(local: List[bytes], num_tiles: int, dst: int = 0, device=N
 def compress_frame_sharded(tiles_on_src: torch.Tensor | None, num_tiles: int, tile_shape: Sequence[int],
                            codec: Callable[[torch.Tensor, int], bytes], device=None) -> List[bytes] | None:
     """scatter -> per-rank codec(tile, tile_index) -> gather; `codec` is the per-tile RAW->bitstream function."""
-    rank, world = dist.get_rank(), dist.get_world_size()
+    rank, world = _rank_world()
     mine = scatter_tiles(tiles_on_src, num_tiles, tile_shape, device=device)
     streams = [codec(mine[i:i + 1], t) for i, t in enumerate(my_tiles(num_tiles, rank, world))]
     return gather_bitstreams(streams, num_tiles, device=device)
+
+
+def compress_frame_distributed(model, frame: torch.Tensor | None, height: int, width: int, tile: int, device, model_id: int = 0,
+                               max_batch: int = 8) -> bytes | None:
+    """BASELINE config 4: one packed-Bayer frame (4,height,width), held by rank 0, -> RCNB container bytes on rank 0.
+
+    Rank 0 uploads the frame, tiles it on the device and scatters tile t to rank t mod G (point-to-point); the frame-level colour
+    condition is broadcast once; every rank pushes ITS tiles through frame.compress_tiles (equal batches, host coder overlapped
+    with the next batch); the variable-length streams are gathered on rank 0 and packed.  The container does not depend on G."""
+    from . import container, tiler
+    from . import frame as rframe
+
+    rank, world = _rank_world()
+    ny, nx = tiler.tile_grid(height, width, tile)
+    meta, ntiles = (height, width, ny, nx), ny * nx
+    if rank == 0:
+        fdev = frame.to(device, non_blocking=True)
+        tiles = tiler.split_frame(fdev, tile)[0]
+        cond = rframe.frame_condition(fdev)
+    else:
+        tiles, cond = None, torch.empty((1, 4, 256, 256), device=device)
+    if world > 1:
+        dist.broadcast(cond, 0)
+    mine = my_tiles(ntiles, rank, world)
+    local = scatter_tiles(tiles, ntiles, (4, tile, tile), device=device)
+    out = rframe.compress_tiles(model, local, cond, tiler.tiles_coords(meta, tile, mine, device=device), max_batch=max_batch)
+    all_y = gather_bitstreams([o[0] for o in out], ntiles, device=device)
+    all_z = gather_bitstreams([o[1] for o in out], ntiles, device=device)
+    if rank != 0:
+        return None
+    shape = out[0][2]
+    recs = [container.TileStreams(t, shape, all_y[t], all_z[t]) for t in range(ntiles)]
+    return container.pack(container.FrameHeader(model_id, height, width, tile, ny, nx, ntiles), recs)

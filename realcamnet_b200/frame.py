@@ -10,8 +10,11 @@ codec's CUDA kernels.  Multi-GPU: tiles are independent, tile t belongs to rank 
 """
 from __future__ import annotations
 
-from typing import List, Optional
+import os
+from concurrent.futures import ThreadPoolExecutor
+from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 
 from . import container, tiler
@@ -42,6 +45,79 @@ def frame_condition(frame: torch.Tensor, size: int = 256) -> torch.Tensor:
                                            align_corners=False)
 
 
+# ----------------------------------------------------------------------------- batched, pipelined tile compression
+_pool = None
+
+
+def _coder_pool() -> ThreadPoolExecutor:
+    """Host range-coder workers.  The coder is a C call through ctypes (the GIL is released while it runs), one independent
+    stream per tile: the streams of a batch are encoded in parallel, and while the GPU already runs the next batch."""
+    global _pool
+    if _pool is None:
+        _pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) - 1)), thread_name_prefix="rcn-coder")
+    return _pool
+
+
+def batch_size_for(n_tiles: int, max_batch: int = 8) -> int:
+    """Largest divisor of n_tiles that is <= max_batch: equal batches, one captured graph per rank."""
+    for b in range(min(max_batch, n_tiles), 0, -1):
+        if n_tiles % b == 0:
+            return b
+    return 1
+
+
+def _encode_tile(model, pending, n: int, B: int) -> Tuple[bytes, bytes]:
+    """Host side of one tile of a batch: its y stream from the GPU-prepared coder input (slice-major, then this tile's (c,h,w)
+    block of every slice -- exactly the order compress() of the single tile produces) and its z stream."""
+    from .entropy_models import rans_encode_packed
+
+    done, host, _keep = pending
+    done.synchronize()
+    h_packed, h_raw, h_flags, h_zsym = host
+    S = model.num_slices
+    pk = np.ascontiguousarray(h_packed.numpy().reshape(S, B, -1)[:, n]).reshape(-1)
+    rw = np.ascontiguousarray(h_raw.numpy().reshape(S, B, -1)[:, n]).reshape(-1)
+    fl = np.ascontiguousarray(h_flags.numpy().reshape(S, B, -1)[:, n]).reshape(-1)
+    y = rans_encode_packed(pk, rw, fl)
+    z = model.entropy_bottleneck.compress_symbols(h_zsym[n:n + 1])[0]
+    return y, z
+
+
+@torch.no_grad()
+def compress_tiles(model, tiles: torch.Tensor, cond: torch.Tensor, coords: torch.Tensor, max_batch: int = 8):
+    """tiles (n,4,T,T), cond (1,4,h,w), coords (n,2,T,T) on the model's device -> [(y_bytes, z_bytes, (zh, zw))] * n.
+
+    Tiles are independent images, so they are pushed through the compress stage in equal batches of up to `max_batch` (one CUDA
+    graph replay per batch: at 512-tiles the ~600 launches of a single tile are launch-latency bound), and the host range coder
+    of batch k runs on worker threads while the GPU computes batch k+1 (double-buffered pinned staging).  Every tile's streams are
+    byte-identical to model.compress() of that tile alone (tests/test_gpu_parity.py::test_tile_pipeline_equals_per_tile_compress)."""
+    from .tcm import StageRunner
+
+    n = tiles.shape[0]
+    if n == 0:
+        return []
+    if model.gaussian_conditional._offset.numel() == 0:
+        raise RuntimeError("call update() before compressing")
+    B = batch_size_for(n, max_batch)
+    pool = _coder_pool()
+    jobs, copy_done = [], None
+    model.entropy_bottleneck.host_tables()       # build the host tables on this thread, not racily on the workers
+    for k in range(n // B):
+        sl = slice(k * B, (k + 1) * B)
+        xs = [tiles[sl], cond.expand(B, -1, -1, -1), coords[sl]]
+        if k >= 2:                               # the staging slot about to be refilled must have been consumed
+            for f in jobs[(k - 2) * B:(k - 1) * B]:
+                f.result()
+        if copy_done is not None:                # the stage's outputs live in the graph pool: finish the previous copy first
+            torch.cuda.current_stream().wait_event(copy_done)
+        E = StageRunner(model, ("compress",), xs, model._compress_stage, None).a()
+        pending = model._begin_host_copy(E.coder.packed, E.coder.raw, E.coder.flags, E.z_sym, slot=k % 2)
+        copy_done = pending[0]
+        shape = (int(E.z.shape[1]), int(E.z.shape[2]))
+        jobs.extend(pool.submit(_encode_tile, model, pending, i, B) for i in range(B))
+    return [f.result() + (shape,) for f in jobs]
+
+
 def compress_frame(model, frame: torch.Tensor, tile: int, cond: Optional[torch.Tensor] = None, model_id: int = 0,
                    tile_indices: Optional[List[int]] = None) -> bytes:
     """frame (4,H,W) packed Bayer in [0,1] -> RCNB container bytes.  tile must be a multiple of 128 and at least 256 (window /
@@ -57,10 +133,14 @@ def compress_frame(model, frame: torch.Tensor, tile: int, cond: Optional[torch.T
     cond = cond.to(dev)
     todo = list(range(ny * nx)) if tile_indices is None else list(tile_indices)
     recs = []
-    for t in todo:
-        x = [tiles[t:t + 1].to(dev), cond, tiler.tile_coords(meta, tile, t, device=dev)]
-        c = model.compress(x)
-        recs.append(container.TileStreams(t, tuple(int(v) for v in c["shape"]), c["strings"][0][0], c["strings"][1][0]))
+    if hasattr(model, "_compress_stage") and dev.type == "cuda":      # the codec models: batched + pipelined
+        out = compress_tiles(model, tiles[todo].to(dev), cond, tiler.tiles_coords(meta, tile, todo, device=dev))
+        recs = [container.TileStreams(t, shp, y, z) for t, (y, z, shp) in zip(todo, out)]
+    else:                                                             # any object with the reference's compress() signature
+        for t in todo:
+            x = [tiles[t:t + 1].to(dev), cond, tiler.tile_coords(meta, tile, t, device=dev)]
+            c = model.compress(x)
+            recs.append(container.TileStreams(t, tuple(int(v) for v in c["shape"]), c["strings"][0][0], c["strings"][1][0]))
     return container.pack(container.FrameHeader(model_id, H, W, tile, ny, nx, len(recs)), recs)
 
 

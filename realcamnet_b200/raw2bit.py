@@ -400,13 +400,15 @@ class raw_compression_tcm_final(SliceCodecModel):
             out["shape"] = torch.Size(E.z.shape[1:3])
         return out
 
+    def _compress_stage(self, xs):
+        return self._entropy_stage(self._analysis(xs)[0], True, want_lik=False)
+
     @torch.no_grad()
     def compress(self, x):
         """models/raw2bit.py:1876-1960."""
         if self.gaussian_conditional._offset.numel() == 0:
             raise RuntimeError("call update() before compress()")
-        run = StageRunner(self, ("compress",), list(x), lambda xs: self._entropy_stage(self._analysis(xs)[0], True, want_lik=False),
-                          None)
+        run = StageRunner(self, ("compress",), list(x), self._compress_stage, None)
         E = run.a()
         pending = self._begin_host_copy(E.coder.packed, E.coder.raw, E.coder.flags, E.z_sym)
         return {"strings": self._strings(E, pending), "shape": torch.Size(E.z.shape[1:3])}

@@ -223,7 +223,9 @@ class SliceCodecModel(CompressionModel):
         ts = self.__dict__.get("_graph_tensors")
         if ts is None:
             ts = self.__dict__["_graph_tensors"] = [t for t in list(self.parameters()) + list(self.buffers())]
-        return sum(t._version for t in ts)
+        gc, eb = self.gaussian_conditional, self.entropy_bottleneck
+        # entropy-model updates REBIND their table buffers (new tensors at version 0), also when called on the sub-module directly
+        return (sum(t._version for t in ts), id(gc._quantized_cdf), id(gc._offset), id(gc.scale_table), id(eb._quantized_cdf))
 
     def _apply(self, fn, *args, **kwargs):
         self._invalidate_graphs()
@@ -316,8 +318,9 @@ class SliceCodecModel(CompressionModel):
         h_packed, h_raw, h_flags = self._end_host_copy(pending)[:3]
         return rans_encode_packed(h_packed.numpy(), h_raw.numpy(), h_flags.numpy())
 
-    def _begin_host_copy(self, *tensors):
-        """Async device->pinned-host copies on a side stream, ordered after the work already queued."""
+    def _begin_host_copy(self, *tensors, slot=0):
+        """Async device->pinned-host copies on a side stream, ordered after the work already queued.  `slot` selects one of
+        several pinned staging sets (the tile pipeline double-buffers: the host coder reads one while the next copy fills the other)."""
         dev = tensors[0].device
         if getattr(self, "_side", None) is None or self._side.device != dev:
             self._side = torch.cuda.Stream(device=dev)
@@ -328,7 +331,7 @@ class SliceCodecModel(CompressionModel):
         host = []
         with torch.cuda.stream(self._side):
             for j, t in enumerate(tensors):
-                key = (j, tuple(t.shape), t.dtype)
+                key = (slot, j, tuple(t.shape), t.dtype)
                 h = self._pinned.get(key)
                 if h is None:
                     h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
@@ -576,12 +579,15 @@ class TCM(SliceCodecModel):
             out["shape"] = torch.Size(E.z.shape[1:3])
         return out
 
+    def _compress_stage(self, xs):
+        return self._entropy_stage(self._g_a(xs[0]), True, want_lik=False)
+
     @torch.no_grad()
     def compress(self, x):
         """models/tcm.py:511-570."""
         if self.gaussian_conditional._offset.numel() == 0:
             raise RuntimeError("call update() before compress()")
-        run = StageRunner(self, ("compress",), [x], lambda xs: self._entropy_stage(self._g_a(xs[0]), True, want_lik=False), None)
+        run = StageRunner(self, ("compress",), [x], self._compress_stage, None)
         E = run.a()
         pending = self._begin_host_copy(E.coder.packed, E.coder.raw, E.coder.flags, E.z_sym)
         return {"strings": self._strings(E, pending), "shape": torch.Size(E.z.shape[1:3])}

@@ -40,6 +40,18 @@ def tile_coords(meta: Tuple[int, int, int, int], tile: int, index: int, device=N
     return torch.stack([xx, yy])[None].contiguous()
 
 
+def tiles_coords(meta: Tuple[int, int, int, int], tile: int, indices, device=None) -> torch.Tensor:
+    """(len(indices),2,tile,tile): tile_coords of several tiles in one tensor (same values, bit for bit)."""
+    H, W, ny, nx = meta
+    idx = torch.as_tensor(list(indices), dtype=torch.int64, device=device)
+    ty, tx = idx // nx, idx % nx
+    ar = torch.arange(tile, device=device, dtype=torch.float32)
+    ys = (ar[None, :] + (ty * tile).to(torch.float32)[:, None]) / max(H - 1, 1) * 2 - 1        # (n, tile)
+    xs = (ar[None, :] + (tx * tile).to(torch.float32)[:, None]) / max(W - 1, 1) * 2 - 1
+    n = idx.numel()
+    return torch.stack([xs[:, None, :].expand(n, tile, tile), ys[:, :, None].expand(n, tile, tile)], dim=1).contiguous()
+
+
 def stitch(tiles: List[torch.Tensor], meta: Tuple[int, int, int, int], tile: int, scale: int = 2) -> torch.Tensor:
     """tiles: list of (1,C,scale*tile,scale*tile) outputs in grid order -> (1,C,scale*H,scale*W) with the padding removed."""
     H, W, ny, nx = meta

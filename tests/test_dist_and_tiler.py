@@ -68,3 +68,52 @@ def test_two_rank_scatter_and_bitstream_gather():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(res)
+
+
+def _fake_compress_tiles(model, tiles, cond, coords, max_batch=8):
+    """Stand-in for frame.compress_tiles (the CUDA codec): streams are hashes of the tile, its coordinates and the condition."""
+    out = []
+    for i in range(tiles.shape[0]):
+        h = hashlib.sha256(tiles[i].numpy().tobytes() + coords[i].numpy().tobytes() + cond.numpy().tobytes()).digest()
+        out.append((h * (1 + h[0] % 3), h[:7], (tiles.shape[2] // 64, tiles.shape[3] // 64)))
+    return out
+
+
+def _frame_worker(rank, world, port, q):
+    import realcamnet_b200.frame as rframe
+
+    rframe.compress_tiles = _fake_compress_tiles
+    if world > 1:
+        os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        fr = torch.rand(4, 300, 600, generator=torch.Generator().manual_seed(21)) if rank == 0 else None
+        blob = rdist.compress_frame_distributed(None, fr, 300, 600, 128, torch.device("cpu"))
+        q.put((rank, blob))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+def test_frame_container_is_identical_for_one_and_two_ranks():
+    """BASELINE config 4 host logic on CPU (gloo): scatter, condition broadcast, per-rank tile codec, variable-length gather and
+    container packing give the same bytes whatever the number of ranks."""
+    from realcamnet_b200 import container
+
+    ctx = mp.get_context("spawn")
+    blobs = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = 31500 + (os.getpid() % 2000) + world
+        procs = [ctx.Process(target=_frame_worker, args=(r, world, port, q)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = dict(q.get(timeout=180) for _ in procs)
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+        assert all(res[r] is None for r in range(1, world))
+        blobs[world] = res[0]
+    assert blobs[1] == blobs[2]
+    hdr, recs = container.unpack(blobs[1])
+    assert (hdr.H, hdr.W, hdr.tile, hdr.ny, hdr.nx, hdr.n_tiles) == (300, 600, 128, 3, 5, 15) and len(recs) == 15

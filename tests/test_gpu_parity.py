@@ -723,7 +723,9 @@ def test_graphed_calls_follow_weight_and_table_updates(dev):
     # tables only: a different scale table changes indexes / bytes, and compress must stay decodable by the eager decompress
     m.enable_cuda_graphs(True)
     c0 = m.compress(xd)
-    m.update(scale_table=torch.exp(torch.linspace(np.log(0.2), np.log(200.0), 48)), force=True)
+    # (model.update(scale_table, force=True) re-applies the default table through CompressionModel.update, exactly like the
+    #  reference, raw2bit.py:1756-1764 -- so the custom table goes in through the entropy model itself)
+    m.gaussian_conditional.update_scale_table(torch.exp(torch.linspace(np.log(0.2), np.log(200.0), 48)), force=True)
     c1 = m.compress(xd)
     assert c1["strings"][0][0] != c0["strings"][0][0]
     d = m.decompress(c1["strings"], c1["shape"])

@@ -1,6 +1,6 @@
 """Runs one conv launch shape alone for `ncu --set full`.  Default: the full-resolution 128->128 3x3 convolution of the
 g_s tail at T=2048 (the launch bench.py times for `roofline`).
-usage: prof_conv.py [T] [fp32|bf16x3|bf16] [Cin] [Cout] [k] [act] [emit_planes 0|1] [res 0|1]"""
+usage: prof_conv.py [T] [fp32|bf16x3|bf16|fp16] [Cin] [Cout] [k] [act] [emit_planes 0|1] [res 0|1]"""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -22,7 +22,7 @@ b = torch.randn(Cout, generator=g).to(dev)
 pc = ops.pack_weight(w, b)
 a = torch.randn(1, T, T, Cin, device=dev)
 r = torch.randn(1, T, T, Cout, device=dev) if res else None
-sp = ops.split_operand(a, pc.cp, passes=3) if eng != "fp32" else None
+sp = ops.split_operand(a, pc.cp) if eng != "fp32" else None
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(5):
     if i == 2:
