@@ -169,6 +169,50 @@ def run_cpu_reference(T, steps, warmup, budget_s=150.0):
     return {"value": mp / dt, "dt": dt, "threads": best, "steps_timed": done, "kind": kind, "note": note, "sym": sym}
 
 
+# --------------------------------------------------------------------------------------------- BASELINE config 4
+def measure_frame4k(model, dev, rank, world, height=2160, width=3840, tile=512, reps=2):
+    """Frames/s of the tiled-frame path on the ranks of this run (wall time incl. all host work, max over ranks)."""
+    import hashlib
+
+    import torch
+    import torch.distributed as dist
+
+    from realcamnet_b200 import dist as rdist
+    from realcamnet_b200 import tiler
+
+    model.enable_cuda_graphs(True)
+    fr = torch.rand(4, height, width, generator=torch.Generator().manual_seed(99)).pin_memory() if rank == 0 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    blob = rdist.compress_frame_distributed(model, fr, height, width, tile, dev)      # warm-up: graph capture of the batch shape
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        blob2 = rdist.compress_frame_distributed(model, fr, height, width, tile, dev)
+    barrier()
+    ms = (time.perf_counter() - t0) * 1e3 / reps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    if rank != 0:
+        return None
+    ny, nx = tiler.tile_grid(height, width, tile)
+    mp = 4.0 * height * width / 1e6
+    from realcamnet_b200 import frame as rframe
+    return {"workload": f"BASELINE configs[3]: packed 4x{height}x{width} RAW frame -> {ny * nx} tiles of 4x{tile}x{tile}, tile t -> rank t mod {world}, "
+                        "compress() per tile (batched, host coder overlapped), NCCL scatter / bitstream gather, RCNB container on rank 0",
+            "value": mp / (ms / 1e3), "unit": "MP/s", "ms_per_frame": ms, "frames_per_s": 1e3 / ms, "n_gpus": world, "tiles": ny * nx,
+            "tiles_per_rank": len(rdist.my_tiles(ny * nx, 0, world)), "batch": rframe.batch_size_for(len(rdist.my_tiles(ny * nx, 0, world))),
+            "container_bytes": len(blob), "container_sha256": hashlib.sha256(blob).hexdigest()[:16], "deterministic": blob2 == blob,
+            "timing": "wall clock around whole frames incl. H2D of the frame, tiling, scatter, host range coder and gather; max over ranks"}
+
+
 # --------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -185,6 +229,7 @@ def main():
                     help="per-stage precision policy: engine of the post-quantisation full-resolution synthesis tail when --engine is "
                          "bf16x3 (fp16 = one fp16 MMA pass, within the 1e-3 bar on x_hat; bf16x3 = policy off)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-frame", action="store_true", help="skip the secondary frame workload (BASELINE config 4)")
     ap.add_argument("--no-graphs", action="store_true", help="launch every kernel eagerly instead of replaying CUDA graphs")
     ap.add_argument("--engine", default=os.environ.get("RCN_CONV_ENGINE", "bf16x3"), choices=["fp32", "bf16x3", "bf16", "fp16"],
                     help="conv engine: fp32 = CUDA-core exact; bf16x3 = tcgen05 with hi/lo split operands (parity grade); "
@@ -298,6 +343,15 @@ def main():
         model.decompress(strings, shape)
     torch.cuda.synchronize()
     decode_ms = (time.perf_counter() - t0) * 1e3 / ndec
+
+    # ---- BASELINE config 4 on the same ranks: one 3840x2160 (packed 4 x 2160 x 3840) frame, 40 tiles of 4x512x512, tile t -> rank
+    # t mod N, compress() per tile in equal batches with the host coder overlapped, scatter / gather over NCCL, one RCNB container
+    frame4k = None
+    if not args.no_frame:
+        try:
+            frame4k = measure_frame4k(model, dev, rank, world)
+        except Exception as e:      # a secondary workload must never cost the bench line
+            frame4k = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
 
     # ---- roofline of the dominant kernel: the full-resolution 128->128 3x3 conv + LeakyReLU of the g_s tail (ResidualBlock.conv1,
     # raw2bit.py:1681), launched exactly as the step launches it: the engine the precision policy gives the tail, operand planes
@@ -416,7 +470,7 @@ def main():
                 "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
                 "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
-                "symbols_mismatch_vs_oracle": mismatch,
+                "symbols_mismatch_vs_oracle": mismatch, "frame4k": frame4k,
                 "decode": {"value": mp_tile / (decode_ms / 1e3), "unit": "MP/s", "ms_per_tile": decode_ms,
                            "what": "decompress(strings, shape) -> x_hat of the same tile (eager launches; host range decoder per slice)"},
                 "packed_positions_per_s": value * 0.25e6, "tiles_per_s": value / mp_tile}

@@ -150,35 +150,52 @@ __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, 
     for (int d = 0; d < HD; ++d) q[d] *= qscale;
     const bool rq = shifted && (wy == nwh - 1) && (py >= WS - sh);
     const bool cq = shifted && (wx == nww - 1) && (px >= WS - sh);
+    const bool edge_y = shifted && (wy == nwh - 1), edge_x = shifted && (wx == nww - 1);
     const float* rp = rps + hl * RP + (py + WS - 1) * (2 * WS - 1) + (px + WS - 1);
-    float s[P];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const int jy = j / WS, jx = j - jy * WS;
-        float a = rp[-(jy * (2 * WS - 1) + jx)];
-#pragma unroll
-        for (int d = 0; d < HD; ++d) a = fmaf(q[d], ks[j * HD + d], a);
-        if (shifted) {
-            const bool rk = (wy == nwh - 1) && (jy >= WS - sh);
-            const bool ck = (wx == nww - 1) && (jx >= WS - sh);
-            if (rk != rq || ck != cq) a = -INFINITY;
-        }
-        s[j] = a;
-        mx = fmaxf(mx, a);
-    }
-    float den = 0.f;
-#pragma unroll
-    for (int j = 0; j < P; ++j) { s[j] = exp2f(s[j] - mx); den += s[j]; }
-    const float inv = 1.f / den;
+    // Online softmax over the P keys (log2 domain): running maximum mx, denominator den and the un-normalised output o[] --
+    // no score array.  The first kernel kept all P scores in registers (s[64] + q + o: ~130 registers, 16 warps per SM, every
+    // dependent FMA chain exposed); this one needs ~2 HD + 20 registers and runs at full occupancy.  A new maximum rescales
+    // den and o[] (a handful of times per query); masked keys (shifted windows on the last row / column) are skipped.
+    float mx = -INFINITY, den = 0.f;
     float o[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
-#pragma unroll
+#pragma unroll 4
     for (int j = 0; j < P; ++j) {
+        const int jy = j / WS, jx = j - jy * WS;
+        if (edge_y || edge_x) {   // block-uniform
+            const bool rk = edge_y && (jy >= WS - sh);
+            const bool ck = edge_x && (jx >= WS - sh);
+            if (rk != rq || ck != cq) continue;
+        }
+        float a = rp[-(jy * (2 * WS - 1) + jx)];
+        const float4* kr = reinterpret_cast<const float4*>(ks + j * HD);
 #pragma unroll
-        for (int d = 0; d < HD; ++d) o[d] = fmaf(s[j], vs[j * HD + d], o[d]);
+        for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 kk = kr[d4];
+            a = fmaf(q[4 * d4], kk.x, a); a = fmaf(q[4 * d4 + 1], kk.y, a); a = fmaf(q[4 * d4 + 2], kk.z, a); a = fmaf(q[4 * d4 + 3], kk.w, a);
+        }
+        float pj;
+        if (a > mx) {
+            const float sc = exp2f(mx - a);   // mx = -inf on the first key: sc = 0
+            den *= sc;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) o[d] *= sc;
+            mx = a;
+            pj = 1.f;
+        } else {
+            pj = exp2f(a - mx);
+        }
+        den += pj;
+        const float4* vr = reinterpret_cast<const float4*>(vs + j * HD);
+#pragma unroll
+        for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 vv = vr[d4];
+            o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+            o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+        }
     }
+    const float inv = 1.f / den;
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] *= inv;
     const long long opix = (long long)(n * H + gy) * W + gx;
@@ -236,7 +253,9 @@ extern "C" int rcn_layernorm(const float* x, long long npix, int C, int ldx, con
     const bool al = (ldx % 4 == 0) && ((uintptr_t)x % 16 == 0) && ((uintptr_t)gamma % 16 == 0) && ((uintptr_t)beta % 16 == 0) &&
                     (!y || (ldy % 4 == 0 && (uintptr_t)y % 16 == 0)) &&
                     (!y_hi || (ldp % 4 == 0 && (uintptr_t)y_hi % 8 == 0 && (!y_lo || (uintptr_t)y_lo % 8 == 0)));
-    if (al && (C == 64 || C == 128) && npix >= 512) {
+    // NOT conditioned on npix: the two kernels sum in different orders, and a result that depended on how many pixels a call
+    // happens to carry would make a tile's bitstream depend on the batch it was compressed in
+    if (al && (C == 64 || C == 128)) {
         constexpr int PIX_IT = 4;
         if (C == 64) {
             const int g2 = cdiv(npix, (long long)wpb * 2 * PIX_IT);

@@ -119,6 +119,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
                  : "memory");
 }
 
+__device__ __forceinline__ void tma_load_4d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_a(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+                 "l"(map), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -177,6 +189,9 @@ struct TcParams {
     int s2;       // stride-2 conv: A planes are the 4 polyphase components stacked on the batch axis ((py*2+px)*N + n)
     int nmma;     // MMA-issuing warps: 2 for long K loops (3x3 layers), 1 otherwise
     int wcw;      // accumulator columns per epilogue warp: 64, or Ntile / 2 when that keeps all 8 warps busy (Ntile = 64, 96)
+    int halo;     // halo-tile kernel (3x3 stride-1 layers with 64-channel K chunks): A operand = one (16+2) x (8+2)-pixel box per chunk
+    int na;       // halo kernel: number of A (halo box) buffers in the ring
+    int rv;       // epilogue: row-vector (256-bit, no transposition) instead of the transposing one (VEC kernels only)
     int in_f16;   // operand planes and packed weights are fp16 (kind::f16 with f16 A/B formats) instead of bf16
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math, 16 centre-tap A loads only
 };
@@ -325,16 +340,20 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
 //                channels cb/4 ..+15 of that pixel -- the same 64-byte-contiguous store pattern as the NHWC case.
 // The residual (or aux) operand of all 16 items is requested BEFORE the wait on the accumulator barrier, so its HBM latency
 // hides behind the MMAs of this tile; the TMEM load of quarter hh+1 is in flight while quarter hh is finished.
-template <int ACT, int EPI, bool DUAL>
+template <int ACT, int EPI, bool DUAL, int TW>
 __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int epi, uint32_t slab, uint32_t sbias, uint32_t taddr,
                                                   uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0,
                                                   int cb, int wcols, int q, int lane) {
     const bool ps = (r.flags & EF_PS) != 0;
     const int chunk = lane & 3, r0 = lane >> 2;
-    const int hy = y0 + 2 * q, wx = x0 + r0;
+    // tile geometry TW x (128 / TW): accumulator row m = pixel (m / TW, m % TW).  Item `it` of a lane is row 32q + r0 + 8 it:
+    // TW = 16 -> pixel (2q + (it >> 1), r0 + 8 (it & 1));  TW = 8 (halo-tile kernel) -> pixel (4q + it, r0)
+#define RCN_DY(it) (TW == 16 ? ((it) >> 1) : (it))
+#define RCN_DX8(it) (TW == 16 ? ((it) & 1) : 0)
+    const int hy = y0 + (TW == 16 ? 2 : 4) * q, wx = x0 + r0;
     bool okp[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) okp[it] = (hy + (it >> 1) < r.H) && (wx + 8 * (it & 1) < r.W);
+    for (int it = 0; it < 4; ++it) okp[it] = (hy + RCN_DY(it) < r.H) && (wx + 8 * RCN_DX8(it) < r.W);
     // stored-tensor geometry of the lane's items
     long long pix0;
     int sx, sy, chb, chs, Wst;      // pixel steps for x + 8 / y + 1; first stored channel of quarter 0 and its step per quarter
@@ -351,7 +370,7 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
 #define RCN_QOFF(hh) (ps ? (long long)((hh) >> 1) * Wst + ((hh) & 1) : 0ll)
     long long ip[4];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) ip[it] = pix0 + (it & 1) * sx + (long long)(it >> 1) * sy;
+    for (int it = 0; it < 4; ++it) ip[it] = pix0 + RCN_DX8(it) * sx + (long long)RCN_DY(it) * sy;
     const bool has_res = (r.flags & EF_RES) != 0;
     constexpr bool has_aux = (EPI != 0);
     // operand prefetched ahead of the accumulator: the residual when there is one, else aux
@@ -454,7 +473,7 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                 long long po = (ip[it] + qoff) * r.cpo + ch;
                 if (r.flags & EF_S2OUT) {
                     // polyphase layout of a stride-2 consumer: pixel (h, w) -> plane (h&1)*2 + (w&1), position (h>>1, w>>1)
-                    const int h = hy + (it >> 1), w = wx + 8 * (it & 1);
+                    const int h = hy + RCN_DY(it), w = wx + 8 * RCN_DX8(it);
                     const long long plane = (long long)(((h & 1) * 2 + (w & 1)) * r.N + n);
                     po = ((plane * (r.H >> 1) + (h >> 1)) * (r.W >> 1) + (w >> 1)) * r.cpo + ch;
                 }
@@ -464,6 +483,150 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
         }
     }
     if (prof) atomicAdd(&g_tcprof[1], (unsigned long long)(clock64() - tp1));
+#undef RCN_QOFF
+#undef RCN_DY
+#undef RCN_DX8
+}
+
+// 256-bit global accesses (sm_100: LDG / STG .E.ENL2.256): one full 32-byte sector per lane and instruction
+__device__ __forceinline__ void ldg256(const float* p, float* v) {
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7])
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]),
+                 "f"(v[5]), "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void stg256u(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+
+// Row-vector epilogue of one tile for one warp: NO transposition.  A lane keeps the accumulator row it gets from TMEM (lane =
+// pixel) and handles 16 columns = 16 consecutive stored channels of its pixel at a time: 64 contiguous bytes of the fp32 map
+// (two 256-bit stores), 32 contiguous bytes of each 16-bit operand plane (one 256-bit store) -- every access a full sector, no
+// shared-memory slab, no warp barriers, and ~4x fewer instructions than the transposing epilogue below (measured with ncu on the
+// 128 -> 128 layers: 2077 warp instructions per warp and tile, 29 of them local-memory spills waiting on L2).  The pixel-shuffle
+// store has the same shape: with sub-pixel-grouped weights, block hh of a warp's 64 columns is sub-pixel hh and holds 16
+// consecutive shuffled channels of OUTPUT pixel (2y + (hh >> 1), 2x + (hh & 1)).
+// Requirements (host-checked, else the transposing epilogue runs): Cout % 16 == 0, pixel strides % 8 == 0 (fp32) / % 16 == 0
+// (planes), 32-byte aligned bases.
+template <int ACT, int EPI, bool DUAL, int TW>
+__device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int epi, uint32_t sbias, uint32_t taddr, uint64_t* full_bar,
+                                                 uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0, int cb, int wcols, int q,
+                                                 int lane) {
+    const bool ps = (r.flags & EF_PS) != 0;
+    const int m = q * 32 + lane;
+    const int ho = y0 + m / TW, wo = x0 + (m % TW);
+    const bool ok = ho < r.H && wo < r.W;
+    const bool has_res = (r.flags & EF_RES) != 0;
+    constexpr bool has_aux = (EPI != 0);
+    long long pix0;        // stored pixel of block 0
+    int Wst = 0, chb, chs;
+    if (!ps) { pix0 = ((long long)n * r.H + ho) * r.W + wo; chb = cb; chs = 16; }
+    else { Wst = 2 * r.W; pix0 = ((long long)n * 2 * r.H + 2 * ho) * Wst + 2 * wo; chb = cb >> 2; chs = 0; }
+#define RCN_QOFF(hh) (ps ? (long long)((hh) >> 1) * Wst + ((hh) & 1) : 0ll)
+    // residual (else aux) of every block, requested BEFORE the wait on the accumulator barrier: its HBM latency hides behind the MMAs
+    const float* pre_ptr = has_res ? r.res : (has_aux ? r.aux : nullptr);
+    const int pre_ld = has_res ? r.ldres : r.ldaux;
+    float pre[QN][16];
+#pragma unroll
+    for (int hh = 0; hh < QN; ++hh) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pre[hh][j] = 0.f;
+        if (pre_ptr && 16 * hh < wcols && ok) {
+            const float* pp = pre_ptr + (pix0 + RCN_QOFF(hh)) * pre_ld + chb + chs * hh;
+            ldg256(pp, &pre[hh][0]);
+            ldg256(pp + 8, &pre[hh][8]);
+        }
+    }
+    mbar_wait(full_bar, parity);
+    tc_fence_after();
+    if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
+    uint32_t v[16], w2[16];
+    tmem_ld16x2_async(taddr, v, w2, DUAL);
+#pragma unroll
+    for (int hh = 0; hh < QN; ++hh) {
+        if (16 * hh >= wcols) break;   // warp-uniform
+        const long long spix = pix0 + RCN_QOFF(hh);
+        const int ch = chb + chs * hh;                    // first stored channel of this block
+        // conv channel of column j: plain store cb + 16 hh + j; pixel shuffle (sub-pixel-grouped rows) cb + 4 j + hh
+        const int c0 = ps ? cb + hh : cb + 16 * hh, ce = ps ? 4 : 1;
+        float sec[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) sec[j] = 0.f;
+        if (has_aux && has_res && ok) {
+            const float* ap = r.aux + spix * r.ldaux + ch;
+            ldg256(ap, &sec[0]);
+            ldg256(ap + 8, &sec[8]);
+        }
+        tmem_wait_sum16(v, w2, DUAL);
+        float val[16];
+        if (sbias) {
+            if (!ps) {
+#pragma unroll
+                for (int k4 = 0; k4 < 4; ++k4) {
+                    const float4 b4 = lds4(sbias + 4u * (uint32_t)(c0 + 4 * k4));   // same address in every lane: broadcast
+                    val[4 * k4] = __uint_as_float(v[4 * k4]) + b4.x; val[4 * k4 + 1] = __uint_as_float(v[4 * k4 + 1]) + b4.y;
+                    val[4 * k4 + 2] = __uint_as_float(v[4 * k4 + 2]) + b4.z; val[4 * k4 + 3] = __uint_as_float(v[4 * k4 + 3]) + b4.w;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(v[j]) + lds1(sbias + 4u * (uint32_t)(c0 + 4 * j));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(v[j]);
+        }
+        if (16 * (hh + 1) < wcols) tmem_ld16x2_async(taddr + 16 * (hh + 1), v, w2, DUAL);   // next block in flight
+        else epi_release(empty_bar, lane);                                                  // last TMEM read of this tile by this warp
+        if (!ok) continue;
+        if (r.flags & EF_CS) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+                val[j] = fmaf(val[j], 1.f + __ldg(r.cscale + n * r.Cout + c0 + ce * j), __ldg(r.cshift + n * r.Cout + c0 + ce * j));
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float rv = has_res ? pre[hh][j] : 0.f;
+            const float ax = has_res ? sec[j] : pre[hh][j];
+            if (EPI != 0) val[j] = epi_ct<EPI>(val[j], ax, epi);
+            val[j] = fmaf(r.rpre, rv, val[j]);                       // residual before / after the activation
+            val[j] = act_ct<ACT>(val[j], act, r.slope);
+            val[j] = fmaf(r.rpost, rv, val[j]);
+        }
+        if (r.flags & EF_NOSTORE) continue;
+        if (r.flags & EF_Y) {
+            float* yp = r.y + spix * r.ldy + ch;
+            stg256(yp, &val[0]);
+            stg256(yp + 8, &val[8]);
+        }
+        if (r.flags & EF_HI) {
+            // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16)
+            const int f16 = (r.flags & EF_F16OUT) ? 1 : 0;
+            uint32_t hp[8], lp[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint16_t h0 = to_plane(val[2 * j], f16), h1 = to_plane(val[2 * j + 1], f16);
+                hp[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+                if (r.flags & EF_LO) {
+                    const uint16_t l0 = to_plane(val[2 * j] - from_plane(h0, f16), f16), l1 = to_plane(val[2 * j + 1] - from_plane(h1, f16), f16);
+                    lp[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                }
+            }
+            long long po = spix * r.cpo + ch;
+            if (r.flags & EF_S2OUT) {
+                // polyphase layout of a stride-2 consumer: pixel (h, w) -> plane (h&1)*2 + (w&1), position (h>>1, w>>1)
+                const long long plane = (long long)(((ho & 1) * 2 + (wo & 1)) * r.N + n);
+                po = ((plane * (r.H >> 1) + (ho >> 1)) * (r.W >> 1) + (wo >> 1)) * r.cpo + ch;
+            }
+            stg256u(r.y_hi + po, hp);
+            if (r.flags & EF_LO) stg256u(r.y_lo + po, lp);
+        }
+    }
 #undef RCN_QOFF
 }
 
@@ -521,7 +684,7 @@ __device__ __forceinline__ void rows_block(const EpiRegs& r, int act, int epi, i
         }
     }
 }
-template <int ACT, int EPI, bool DUAL>
+template <int ACT, int EPI, bool DUAL, int TW>
 __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, int epi, int store, uint32_t sbias, uint32_t taddr,
                                                    uint64_t* full_bar, uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0, int cb,
                                                    int wcols, int q, int lane) {
@@ -529,7 +692,7 @@ __device__ __forceinline__ void epilogue_tile_rows(const EpiRegs& r, int act, in
     tc_fence_after();
     if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
     const int m = q * 32 + lane;
-    const int ho = y0 + m / TILE_W, wo = x0 + (m % TILE_W);
+    const int ho = y0 + m / TW, wo = x0 + (m % TW);
     const bool ok = ho < r.H && wo < r.W;
 #pragma unroll 1
     for (int c0 = 0; c0 < wcols; c0 += 16) {
@@ -650,46 +813,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
-            const bool loadA_all = !(P.dbg & 4);
-            const uint32_t b_tx = (uint32_t)(P.Ntile * BLOCK_K * 2), a_tx = (uint32_t)(128 * BLOCK_K * 2);   // bytes the boxes really carry
-            int stage = 0;
-            uint32_t phase = 0;
-            const uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
-            for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x) {
+        // Same shape as the MMA issue loops: the whole warp walks the loop (uniform control flow), one elected lane issues the
+        // TMA instructions; loop invariants live in registers; (tap, chunk) advance incrementally instead of by division.
+        {
+            int dbg = P.dbg, k = p.k, chunks_ = chunks, kit = kiters, stages = P.stages, s2 = P.s2, Nimg = p.N, Cp = P.Cp, Ntile = P.Ntile;
+            int three = (P.passes == 3);
+            uint32_t sbytes = (uint32_t)stage_bytes, abytes = (uint32_t)A_BYTES, bbytes = (uint32_t)B_BYTES, bk = (uint32_t)BLOCK_K;
+            uint32_t total_tiles = (uint32_t)P.total_tiles, tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+            opaque(dbg); opaque(k); opaque(chunks_); opaque(kit); opaque(stages); opaque(s2); opaque(Nimg); opaque(Cp); opaque(Ntile);
+            opaque(three); opaque(sbytes); opaque(abytes); opaque(bbytes); opaque(bk); opaque(total_tiles); opaque(tiles_n);
+            opaque(tiles_x); opaque(tiles_y);
+            const bool loadA_all = !(dbg & 4);
+            const uint32_t b_tx = (uint32_t)Ntile * bk * 2u, a_tx = 128u * bk * 2u;   // bytes the boxes really carry
+            const uint32_t smem0 = smem_u32(smem), fullb = smem_u32(full_bar), emptyb = smem_u32(empty_bar);
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
                 const int nt = (int)(t % tiles_n);
                 uint32_t mt = t / tiles_n;
                 const int tx = (int)(mt % tiles_x); mt /= tiles_x;
                 const int ty = (int)(mt % tiles_y);
                 const int n = (int)(mt / tiles_y);
-                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * P.Ntile;
-                for (int it = 0; it < kiters; ++it) {
-                    const int tap = it / chunks, ch = it - tap * chunks;
-                    const int ky = tap / p.k, kx = tap - ky * p.k;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + (size_t)stage * stage_bytes;
-                    // perf triage: dbg & 16 fetches the A boxes of the centre tap only (what a halo-tile load would cost in L2 -> smem
-                    // traffic); the other taps multiply stale but finite shared-memory contents
-                    const bool loadA = loadA_all && (!(P.dbg & 16) || tap == (p.k * p.k) / 2);
-                    const uint32_t tx_bytes = (P.passes == 3 ? 2u : 1u) * (b_tx + (loadA ? a_tx : 0u));
-                    mbar_expect_tx(&full_bar[stage], tx_bytes);
-                    // input box origin for this tap.  stride 1: shifted box of the same plane.  stride 2 (pad k/2):
-                    // input row 2y+ky-pad lives in polyphase plane py = (ky-pad)&1 at row y + floor((ky-pad)/2).
-                    int ax = x0 + kx - pad, ay = y0 + ky - pad, an = n;
-                    if (P.s2) {
-                        const int oy = ky - pad, ox = kx - pad;
-                        const int py = oy & 1, px = ox & 1;
-                        ay = y0 + ((oy - py) >> 1);
-                        ax = x0 + ((ox - px) >> 1);
-                        an = (py * 2 + px) * p.N + n;
+                const int x0 = tx * TILE_W, y0 = ty * TILE_H, n0 = nt * Ntile;
+                int tap = 0, ky = 0, kx = 0, ch = 0;
+                for (int it = 0; it < kit; ++it) {
+                    mbar_wait_a(emptyb + 8u * stage, phase ^ 1);
+                    if (elect_one()) {
+                        const uint32_t sa = smem0 + stage * sbytes, fb = fullb + 8u * stage;
+                        // perf triage: dbg & 16 fetches the A boxes of the centre tap only; the other taps multiply stale but finite
+                        // shared-memory contents
+                        const bool loadA = loadA_all && (!(dbg & 16) || tap == (k * k) / 2);
+                        const uint32_t tx_bytes = (three ? 2u : 1u) * (b_tx + (loadA ? a_tx : 0u));
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(tx_bytes) : "memory");
+                        // input box origin for this tap.  stride 1: shifted box of the same plane.  stride 2 (pad k/2):
+                        // input row 2y+ky-pad lives in polyphase plane py = (ky-pad)&1 at row y + floor((ky-pad)/2).
+                        int ax = x0 + kx - pad, ay = y0 + ky - pad, an = n;
+                        if (s2) {
+                            const int oy = ky - pad, ox = kx - pad;
+                            const int py = oy & 1, px = ox & 1;
+                            ay = y0 + ((oy - py) >> 1);
+                            ax = x0 + ((ox - px) >> 1);
+                            an = (py * 2 + px) * Nimg + n;
+                        }
+                        const int c0 = ch * (int)bk, w0 = tap * Cp + c0;
+                        if (loadA) tma_load_4d_a(sa, &map_a_hi, fb, c0, ax, ay, an);
+                        tma_load_2d_a(sa + abytes, &map_w_hi, fb, w0, n0);
+                        if (three) {
+                            if (loadA) tma_load_4d_a(sa + abytes + bbytes, &map_a_lo, fb, c0, ax, ay, an);
+                            tma_load_2d_a(sa + 2u * abytes + bbytes, &map_w_lo, fb, w0, n0);
+                        }
                     }
-                    if (loadA) tma_load_4d(sa, &map_a_hi, &full_bar[stage], ch * BLOCK_K, ax, ay, an);
-                    tma_load_2d(sa + A_BYTES, &map_w_hi, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
-                    if (P.passes == 3) {
-                        if (loadA) tma_load_4d(sa + A_BYTES + B_BYTES, &map_a_lo, &full_bar[stage], ch * BLOCK_K, ax, ay, an);
-                        tma_load_2d(sa + 2 * A_BYTES + B_BYTES, &map_w_lo, &full_bar[stage], tap * P.Cp + ch * BLOCK_K, n0);
+                    __syncwarp();
+                    if (++ch == chunks_) {
+                        ch = 0; ++tap;
+                        if (++kx == k) { kx = 0; ++ky; }
                     }
-                    if (++stage == P.stages) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -741,8 +919,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         opaque(act); opaque(epi); opaque(store);
         uint32_t tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
         opaque(tiles_n); opaque(tiles_x); opaque(tiles_y);
-        int Ntile = P.Ntile, wcw = P.wcw;
-        opaque(Ntile); opaque(wcw);
+        int Ntile = P.Ntile, wcw = P.wcw, rvflag = P.rv;
+        opaque(Ntile); opaque(wcw); opaque(rvflag);
         uint32_t local = 0;
         for (uint32_t t = blockIdx.x; t < (uint32_t)P.total_tiles; t += gridDim.x, ++local) {   // total_tiles < 2^31 (host-checked)
             const int nt = (int)(t % tiles_n);
@@ -757,12 +935,226 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             if (wcols > wcw) wcols = wcw;
             const uint32_t ab = local & 1;
             const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(wcw * jsub);
-            if constexpr (VEC)
-                epilogue_tile_vec<ACT, EPI, DUAL>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
-                                            n0 + wcw * jsub, wcols, q, lane);
+            if constexpr (VEC) {
+                if (rvflag)
+                    epilogue_tile_rv<ACT, EPI, DUAL, TILE_W>(er, act, epi, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                                                             n0 + wcw * jsub, wcols, q, lane);
+                else
+                    epilogue_tile_vec<ACT, EPI, DUAL, TILE_W>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n,
+                                                              x0, y0, n0 + wcw * jsub, wcols, q, lane);
+            }
             else
-                epilogue_tile_rows<ACT, EPI, DUAL>(er, act, epi, store, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
+                epilogue_tile_rows<ACT, EPI, DUAL, TILE_W>(er, act, epi, store, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
                                              n0 + wcw * jsub, wcols, q, lane);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
+    }
+}
+
+
+// ---------------------------------------------------------------- halo-tile kernel for 3x3 stride-1 layers
+// The tap-by-tap kernel above re-fetches a shifted 128-pixel box for each of the 9 taps: per 128 x 128 tile of a 128 -> 128 layer
+// it moves 1152 KB (bf16x3) from L2 into shared memory for 4.2 MFLOP-equivalents of tensor work, and ncu shows BOTH engines pinned
+// at the same 13.7 TB/s of L2 -> SM traffic (l1tex__m_xbar2l1tex_read_bytes: 39.1 GB / 2.86 ms at 3 passes, 19.8 GB / 1.45 ms at
+// 1 pass) -- the layer is bound by the L2 fabric, not by the tensor pipe or the issuing threads.  Here the A operand of a tile is
+// fetched ONCE per 64-channel chunk as a (16+2) x (8+2)-pixel halo box (180 rows of 128 B; out-of-image rows zero-filled by TMA =
+// the conv padding), and each tap's A tile is a VIEW of it: the tile is 16 image rows x 8 pixels, so the 8 rows of every UMMA
+// core-matrix group are the 8 pixels of one image row (consecutive 128-byte rows of the box) and groups are one box row apart
+// (stride-byte-offset = 10 * 128 B); the tap (ky, kx) only moves the descriptor's start address by (ky * 10 + kx) * 128 B.  The
+// 128B swizzle XORs address bits [4,7) with bits [7,10) of the ABSOLUTE shared-memory address on both the TMA write and the UMMA
+// read (the box buffer is 1024-byte aligned), so a start address that is not a multiple of 1024 stays consistent with a ZERO
+// base-offset field (measured: every conv parity test passes with base offset 0 and fails with (start >> 7) & 7 in the field).
+// A traffic drops 6.4x; B (weights) is unchanged.
+// Loop order is chunk-major (A box outermost), one issuing warp, one 128-column accumulator per tile (double-buffered).
+constexpr int HT_H = 16, HT_W = 8;                          // tile: 16 image rows x 8 pixels
+constexpr int HB_H = HT_H + 2, HB_W = HT_W + 2;             // halo box
+constexpr int HALO_TX = HB_H * HB_W * 128;                  // bytes one box carries (23040)
+constexpr int HALO_BYTES = (HALO_TX + 1023) & ~1023;        // 23552: box buffers stay 1024-byte aligned
+
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr, uint32_t row_shift, int base_off_mode) {
+    const uint32_t start = smem_addr + row_shift * 128u;
+    uint64_t d = 0;
+    d |= (uint64_t)((start & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((uint32_t)(HB_W * 128) >> 4) << 32;     // 8-row groups are one box row (10 pixels) apart
+    d |= (uint64_t)1 << 46;
+    if (base_off_mode) d |= (uint64_t)((start >> 7) & 7u) << 49;
+    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    return d;
+}
+
+template <int ACT, int EPI, bool VEC>
+__global__ void RCN_TC_BOUNDS
+conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const rcn_conv_desc& p = P.d;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int planes = P.passes == 3 ? 2 : 1;
+    const int abuf_bytes = planes * HALO_BYTES, bstage_bytes = planes * P.b_bytes;
+    uint8_t* bsm = smem + (size_t)P.na * abuf_bytes;
+    uint8_t* tail = bsm + (size_t)P.stages * bstage_bytes;
+    float* stg = reinterpret_cast<float*>(tail);
+    float* sbias_mem = reinterpret_cast<float*>(tail + STG_BYTES);
+    uint64_t* afull = reinterpret_cast<uint64_t*>(tail + STG_BYTES + BIAS_BYTES);
+    uint64_t* aempty = afull + P.na;
+    uint64_t* bfull = aempty + P.na;
+    uint64_t* bempty = bfull + P.stages;
+    uint64_t* tmem_full = bempty + P.stages;   // [2]
+    uint64_t* tmem_empty = tmem_full + 2;      // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    const int chunks = P.Cp / 64;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < P.na; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
+        for (int i = 0; i < P.stages; ++i) { mbar_init(&bfull[i], 1); mbar_init(&bempty[i], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (p.bias) {
+        for (int i = threadIdx.x; i < p.Cout; i += TC_THREADS) sbias_mem[i] = __ldg(p.bias + i);
+    }
+    const uint32_t sbias = p.bias ? smem_u32(sbias_mem) : 0u;
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // loop invariants shared by the producer and the issuer, held in registers
+    uint32_t total_tiles = (uint32_t)P.total_tiles, tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+    int Ntile = P.Ntile, Cp = P.Cp, nch = chunks, stages = P.stages, na = P.na, three = (P.passes == 3), dbg = P.dbg, Cout = p.Cout;
+    uint32_t abytes = (uint32_t)abuf_bytes, bsbytes = (uint32_t)bstage_bytes, bbytes = (uint32_t)P.b_bytes;
+    opaque(total_tiles); opaque(tiles_n); opaque(tiles_x); opaque(tiles_y); opaque(Ntile); opaque(Cp); opaque(nch); opaque(stages);
+    opaque(na); opaque(three); opaque(dbg); opaque(Cout); opaque(abytes); opaque(bsbytes); opaque(bbytes);
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(bsm);
+    const uint32_t afull_a = smem_u32(afull), aempty_a = smem_u32(aempty), bfull_a = smem_u32(bfull), bempty_a = smem_u32(bempty);
+
+    if (warp == 0) {
+        // ================= TMA producer: per tile and chunk one halo box (hi [+ lo]), then the 9 weight tiles of that chunk
+        const uint32_t a_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)HALO_TX, b_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)Ntile * 128u;
+        uint32_t ab = 0, aph = 0, st = 0, bph = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+            const int nt = (int)(t % tiles_n);
+            uint32_t mt = t / tiles_n;
+            const int tx = (int)(mt % tiles_x); mt /= tiles_x;
+            const int ty = (int)(mt % tiles_y);
+            const int n = (int)(mt / tiles_y);
+            const int x0 = tx * HT_W, y0 = ty * HT_H, n0 = nt * Ntile;
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait_a(aempty_a + 8u * ab, aph ^ 1);
+                if (elect_one()) {
+                    const uint32_t fb = afull_a + 8u * ab, dst = a0 + ab * abytes;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(a_tx) : "memory");
+                    tma_load_4d_a(dst, &map_a_hi, fb, c * 64, x0 - 1, y0 - 1, n);
+                    if (three) tma_load_4d_a(dst + (uint32_t)HALO_BYTES, &map_a_lo, fb, c * 64, x0 - 1, y0 - 1, n);
+                }
+                __syncwarp();
+                if (++ab == (uint32_t)na) { ab = 0; aph ^= 1; }
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_a(bempty_a + 8u * st, bph ^ 1);
+                    if (elect_one()) {
+                        const uint32_t fb = bfull_a + 8u * st, dst = b0 + st * bsbytes;
+                        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(b_tx) : "memory");
+                        tma_load_2d_a(dst, &map_w_hi, fb, tap * Cp + c * 64, n0);
+                        if (three) tma_load_2d_a(dst + bbytes, &map_w_lo, fb, tap * Cp + c * 64, n0);
+                    }
+                    __syncwarp();
+                    if (++st == (uint32_t)stages) { st = 0; bph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (one warp, converged, tcgen05 instructions behind elect.sync)
+        const uint32_t tfull_a = smem_u32(tmem_full), tempty_a = smem_u32(tmem_empty);
+        const uint32_t idesc_fmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
+        const int bo_mode = (dbg & 64) ? 1 : 0;   // triage only: 1 sets the descriptor's base-offset field (WRONG on B200, see above)
+        const uint64_t bdesc0 = make_kmajor_desc(b0, 64);
+        uint32_t ab = 0, aph = 0, st = 0, bph = 0, local = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            const int n0 = (int)(t % tiles_n) * Ntile;
+            int nact = Cout - n0;
+            if (nact > Ntile) nact = Ntile;
+            nact = (nact + 15) & ~15;
+            const uint32_t idesc = (1u << 4) | idesc_fmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            const uint32_t acb = local & 1;
+            mbar_wait_a(tempty_a + 8u * acb, ((local >> 1) & 1) ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acb * 256;
+            uint32_t acc = 0;
+            for (int c = 0; c < nch; ++c) {
+                mbar_wait_a(afull_a + 8u * ab, aph);
+                const uint32_t abase = a0 + ab * abytes;
+                for (int tap = 0; tap < 9; ++tap) {
+                    mbar_wait_a(bfull_a + 8u * st, bph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t shift = (uint32_t)((tap / 3) * HB_W + (tap % 3));
+                        const uint64_t a_hi = make_halo_desc(abase, shift, bo_mode);
+                        const uint64_t a_lo = make_halo_desc(abase + (uint32_t)HALO_BYTES, shift, bo_mode);
+                        const uint64_t b_hi = bdesc0 + (uint64_t)((st * bsbytes) >> 4);
+                        const uint64_t b_lo = b_hi + (uint64_t)(bbytes >> 4);
+                        if (!(dbg & 2)) {
+                            if (three) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                            else issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_hi, b_hi, idesc, acc);
+                        }
+                        umma_commit_a(bempty_a + 8u * st);
+                    }
+                    __syncwarp();
+                    acc = 1;
+                    if (++st == (uint32_t)stages) { st = 0; bph ^= 1; }
+                }
+                if (elect_one()) umma_commit_a(aempty_a + 8u * ab);     // the box is free once every MMA reading it has retired
+                __syncwarp();
+                if (++ab == (uint32_t)na) { ab = 0; aph ^= 1; }
+            }
+            if (elect_one()) umma_commit_a(tfull_a + 8u * acb);
+            __syncwarp();
+        }
+    } else if (warp >= EPI_WARP0) {
+        // ================= epilogue (same code as the tap-by-tap kernel, tile geometry 16 x 8)
+        const int q = warp & 3;
+        const int jsub = (warp - EPI_WARP0) >> 2;
+        const uint32_t slab = smem_u32(stg + (warp - EPI_WARP0) * SLAB_FLOATS);
+        const EpiRegs er = make_epi_regs(p, P.dbg, false);
+        int act = p.act, epi = p.epi, store = p.store;
+        opaque(act); opaque(epi); opaque(store);
+        int wcw = P.wcw, rvflag = P.rv;
+        opaque(wcw); opaque(rvflag);
+        uint32_t local = 0;
+        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
+            const int nt = (int)(t % tiles_n);
+            uint32_t mt = t / tiles_n;
+            const int tx = (int)(mt % tiles_x); mt /= tiles_x;
+            const int ty = (int)(mt % tiles_y);
+            const int n = (int)(mt / tiles_y);
+            const int x0 = tx * HT_W, y0 = ty * HT_H, n0 = nt * Ntile;
+            int ncols = er.Cout - n0;
+            if (ncols > Ntile) ncols = Ntile;
+            int wcols = ncols - wcw * jsub;
+            if (wcols > wcw) wcols = wcw;
+            const uint32_t acb = local & 1;
+            const uint32_t taddr = tmem_base + acb * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(wcw * jsub);
+            if constexpr (VEC) {
+                if (rvflag)
+                    epilogue_tile_rv<ACT, EPI, false, HT_W>(er, act, epi, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb], n,
+                                                            x0, y0, n0 + wcw * jsub, wcols, q, lane);
+                else
+                    epilogue_tile_vec<ACT, EPI, false, HT_W>(er, act, epi, slab, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb], n,
+                                                             x0, y0, n0 + wcw * jsub, wcols, q, lane);
+            }
+            else
+                epilogue_tile_rows<ACT, EPI, false, HT_W>(er, act, epi, store, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb],
+                                                          n, x0, y0, n0 + wcw * jsub, wcols, q, lane);
         }
     }
     tc_fence_before();
@@ -868,10 +1260,10 @@ CUtensorMapSwizzle swizzle_of(int bk) {
 }
 
 // planes (N,H,W,Cp) with pixel stride ldp >= Cp elements (a channel slice of a wider plane buffer when ldp > Cp)
-bool make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cp, int ldp, int bk) {
+bool make_act_map(CUtensorMap* m, const void* base, int N, int H, int W, int Cp, int ldp, int bk, int box_w = TILE_W, int box_h = TILE_H) {
     cuuint64_t dims[4] = {(cuuint64_t)Cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)ldp * 2, (cuuint64_t)W * ldp * 2, (cuuint64_t)H * W * ldp * 2};
-    cuuint32_t box[4] = {(cuuint32_t)bk, TILE_W, TILE_H, 1};
+    cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
     cuuint32_t es[4] = {1, 1, 1, 1};
     return get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_of(bk), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -912,8 +1304,12 @@ TcKernel tc_variant_d() {
 
 // perf / fault triage knobs, read from the environment ONCE per process (not on every launch)
 struct TcDebugEnv {
-    int dbg = 0, nmma = 0, stages = 0;
+    int dbg = 0, nmma = 0, stages = 0, halo = 1, rv = 1;
     TcDebugEnv() {
+        const char* h = getenv("RCN_TC_HALO");       // 0: keep 3x3 stride-1 layers on the tap-by-tap kernel
+        if (h) halo = atoi(h) != 0;
+        const char* rvs = getenv("RCN_TC_RV");       // 0: transposing epilogue everywhere
+        if (rvs) rv = atoi(rvs) != 0;
         const char* e = getenv("RCN_TC_DEBUG");
         dbg = e ? atoi(e) : 0;
         const char* nm = getenv("RCN_TC_NMMA");      // force the number of MMA-issuing warps
@@ -939,12 +1335,26 @@ int sm_count() {
 }
 
 template <int ACT, int EPI, bool VEC>
-TcKernel tc_variant(bool dual) {
-    return dual ? tc_variant_d<ACT, EPI, VEC, true>() : tc_variant_d<ACT, EPI, VEC, false>();
+TcKernel tc_variant_h() {
+    static bool attr_set[MAX_DEVICES] = {};
+    TcKernel k = conv_tc_halo_kernel<ACT, EPI, VEC>;
+    const int dev = current_device();
+    if (!attr_set[dev]) {
+        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        attr_set[dev] = true;
+    }
+    return k;
+}
+
+// mode: 0 = tap-by-tap kernel, one issuing warp; 1 = tap-by-tap, two issuing warps; 2 = halo-tile kernel
+template <int ACT, int EPI, bool VEC>
+TcKernel tc_variant(int mode) {
+    if (mode == 2) return tc_variant_h<ACT, EPI, VEC>();
+    return mode == 1 ? tc_variant_d<ACT, EPI, VEC, true>() : tc_variant_d<ACT, EPI, VEC, false>();
 }
 
 // (act, epi, 16-byte path?, two MMA warps?) -> instantiation; combinations the path never uses share the generic (-1, -1) variant
-TcKernel select_kernel(int act, int epi, bool vec, bool dual) {
+TcKernel select_kernel(int act, int epi, bool vec, int dual) {
     if (vec) {
         if (epi == RCN_EPI_NONE) {
             switch (act) {
@@ -1068,30 +1478,48 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.tiles_y = (P.d.H + TILE_H - 1) / TILE_H;
     const int bk = Cp >= 64 ? 64 : Cp;
     P.bk = bk;
-    // two issuing warps pay off when the K loop is long (3x3: 9+ stages per tile); short loops (1x1) are bound by the epilogue,
-    // which the second accumulator makes more expensive
-    P.nmma = (d->k == 3) ? MMA_WARPS : 1;   // 9+ stages per tile
+    const TcDebugEnv& env = tc_debug_env();
+    P.dbg = env.dbg;
+    // One issuing warp: with the lean issue loops (converged warp + elect.sync) a second issuer never helped any layer and cost
+    // the epilogue a second accumulator to add; RCN_TC_NMMA=2 keeps the dual-issuer variant reachable for triage.
+    P.nmma = env.nmma == 2 ? MMA_WARPS : 1;
     P.wcw = (!ps && nt >= 64 && nt % 32 == 0) ? nt / 2 : WCOLS;
     P.a_bytes = 128 * bk * 2;                          // 16 / 8 / 4 KB
     P.b_bytes = (nt * bk * 2 + 1023) & ~1023;
-    const int stage_bytes = (passes == 3 ? 2 : 1) * (P.a_bytes + P.b_bytes);
-    int stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 512) / stage_bytes;
-    if (stages > 12) stages = 12;
-    if (stages < 2) stages = 2;
-    if (P.nmma == 2 && bk == 16 && stages > 2) stages &= ~1;   // single-step stages alternate between the issuers: fixed slot owners need an even ring
-    P.stages = stages;
-    {
-        const TcDebugEnv& env = tc_debug_env();
-        P.dbg = env.dbg;
-        if (env.nmma) P.nmma = env.nmma;
-        if (env.stages && env.stages <= stages) P.stages = stages = env.stages;
+    // halo-tile kernel: 3x3, stride 1, 64-channel K chunks
+    P.halo = (env.halo && d->k == 3 && d->stride == 1 && bk == 64) ? 1 : 0;
+    P.na = 0;
+    const int planes_n = passes == 3 ? 2 : 1;
+    int stages;
+    size_t smem;
+    if (P.halo) {
+        P.nmma = 1;
+        P.tiles_x = (P.d.W + HT_W - 1) / HT_W;
+        P.tiles_y = (P.d.H + HT_H - 1) / HT_H;
+        P.na = planes_n == 2 ? 2 : 3;
+        const int fixed = P.na * planes_n * HALO_BYTES + STG_BYTES + BIAS_BYTES + 1024 + 512;
+        stages = (226 * 1024 - fixed) / (planes_n * P.b_bytes);
+        if (stages > 12) stages = 12;
+        RCN_CHECK_ARG(stages >= 2, "rcn_conv2d_tc: halo kernel does not fit in shared memory");
+        if (env.stages && env.stages <= stages) stages = env.stages;
+        P.stages = stages;
+        smem = (size_t)fixed + (size_t)stages * planes_n * P.b_bytes;
+    } else {
+        const int stage_bytes = planes_n * (P.a_bytes + P.b_bytes);
+        stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 512) / stage_bytes;
+        if (stages > 12) stages = 12;
+        if (stages < 2) stages = 2;
+        if (P.nmma == 2 && bk == 16 && stages > 2) stages &= ~1;   // single-step stages alternate between the issuers: fixed slot owners need an even ring
+        if (env.stages && env.stages <= stages) stages = env.stages;
+        P.stages = stages;
+        smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 512;
     }
-    const size_t smem = (size_t)stages * stage_bytes + STG_BYTES + BIAS_BYTES + 1024 + 512;
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     const long long Ktot = (long long)d->k * d->k * Cp;
     const int planes = P.s2 ? 4 * d->N : d->N;
-    bool ok = make_act_map(&ma_hi, x_hi, planes, P.d.H, P.d.W, Cp, ldp, bk) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt, bk);
-    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp, ldp, bk) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt, bk);
+    const int box_w = P.halo ? HB_W : TILE_W, box_h = P.halo ? HB_H : TILE_H;
+    bool ok = make_act_map(&ma_hi, x_hi, planes, P.d.H, P.d.W, Cp, ldp, bk, box_w, box_h) && make_w_map(&mw_hi, w_hi, d->Cout, Ktot, nt, bk);
+    if (passes == 3) ok = ok && make_act_map(&ma_lo, x_lo, planes, P.d.H, P.d.W, Cp, ldp, bk, box_w, box_h) && make_w_map(&mw_lo, w_lo, d->Cout, Ktot, nt, bk);
     else { ma_lo = ma_hi; mw_lo = mw_hi; }
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
     // epilogue variant (mirrors the alignment rules of the 16-byte path)
@@ -1101,7 +1529,15 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
                      (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
                      (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
     RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
-    const TcKernel kern = select_kernel(d->act, d->epi, vec, P.nmma == 2);
+    // row-vector epilogue: 16-column blocks and 32-byte accesses
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    const int cs_store = (d->store == RCN_STORE_PS2) ? d->Cout / 4 : d->Cout;
+    P.rv = (vec && env.rv && (d->Cout % 16) == 0 && (cs_store % 16) == 0 && (!d->y || ((d->ldy & 7) == 0 && al32(d->y))) &&
+            (!d->res || ((d->ldres & 7) == 0 && al32(d->res))) && (d->epi == RCN_EPI_NONE || ((d->ldaux & 7) == 0 && al32(d->aux))) &&
+            (!d->y_hi || ((d->Cp_out & 15) == 0 && al32(d->y_hi) && (!d->y_lo || al32(d->y_lo)))) &&
+            (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0))
+               ? 1 : 0;
+    const TcKernel kern = select_kernel(d->act, d->epi, vec, P.halo ? 2 : (P.nmma == 2 ? 1 : 0));
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
     RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");

@@ -632,6 +632,36 @@ def test_frame_pipeline_roundtrip_ragged_frame(final_pair):
     assert torch.equal(out[:, :, 512:, 1024:], fwd["x_hat"].clamp(0, 1)[:, :, :600 - 512, :1200 - 1024])
 
 
+def test_tile_pipeline_equals_per_tile_compress(final_pair):
+    """frame.compress_tiles (equal batches through one graph replay each, host coder on worker threads overlapped with the next
+    batch, double-buffered staging) returns, for every tile, exactly the bytes of model.compress() on that tile alone."""
+    from realcamnet_b200 import frame, tiler
+
+    gold, m, sd, x, xd = final_pair
+    dev = xd[0].device
+    g = torch.Generator().manual_seed(23)
+    fr = torch.rand(4, 700, 520, generator=g)                 # 3 x 3 grid of 256-tiles -> 9 tiles: batches of 3 (max_batch 4)
+    tiles, meta = tiler.split_frame(fr, 256)
+    cond = frame.frame_condition(fr).to(dev)
+    coords = tiler.tiles_coords(meta, 256, range(9), device=dev)
+    single = []
+    for t in range(9):
+        assert torch.equal(coords[t:t + 1], tiler.tile_coords(meta, 256, t, device=dev)), t
+        c = m.compress([tiles[t:t + 1].to(dev), cond, tiler.tile_coords(meta, 256, t, device=dev)])
+        single.append((c["strings"][0][0], c["strings"][1][0], tuple(int(v) for v in c["shape"])))
+    for graphs in (False, True):
+        m.enable_cuda_graphs(graphs)
+        try:
+            for rep in range(2):
+                out = frame.compress_tiles(m, tiles.to(dev), cond, coords, max_batch=4)
+                assert frame.batch_size_for(9, 4) == 3 and len(out) == 9
+                bad = [(t, out[t][0] == single[t][0], out[t][1] == single[t][1], out[t][2] == single[t][2]) for t in range(9)
+                       if out[t] != single[t]]
+                assert not bad, (graphs, rep, bad)
+        finally:
+            m.enable_cuda_graphs(False)
+
+
 def test_batch_and_nonsquare_tiles(dev, engine):
     """Edge cases: batch 2 and a 256x384 tile give the same result as the oracle."""
     from realcamnet_b200 import raw2bit
