@@ -1,6 +1,8 @@
 // LayerNorm over channels and Swin window attention (W-MSA / SW-MSA), NHWC fp32.
 #include <cuda_bf16.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace rcn {
@@ -220,6 +222,273 @@ __global__ void wmsa_kernel(const float* __restrict__ qkv, int H, int W, int C, 
     }
 }
 
+// ---------------------------------------------------------------- window attention on tensor cores (8x8 windows)
+// One warp per (window, head, 16-query m-tile); S = Q K^T and O = P V run as mma.sync m16n8k8 TF32 tiles with 3xTF32 split
+// operands (x = hi + lo, hi*hi + lo*hi + hi*lo accumulated in fp32: ~2^-21 relative, the parity bar of the Swin blocks is 1e-4).
+// The FFMA kernels above need 2*64*HD FMAs + ~6 element-wise instructions per (query, head, key); here the contractions are
+// 48*HD/8 warp-level MMAs per 16 queries and only the softmax stays element-wise.
+//   fragments (PTX m16n8k8 .tf32, g = lane / 4, t = lane % 4):
+//     A (16x8, row): a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);   B (8x8, col): b0 (k=t, n=g) b1 (k=t+4, n=g)
+//     C (16x8):      c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+//   The probabilities never leave registers: for P V the k index of A is re-labelled (k=t <-> key 2t, k=t+4 <-> key 2t+1 inside
+//   each 8-key block), which makes the C fragment of S exactly the A fragment of P V (a0=c0, a1=c2, a2=c1, a3=c3); the B
+//   fragment of V uses the same labelling (rows 2t and 2t+1 of the block).
+//   Shared memory per head: Q (pre-scaled by hd^-1/2 * log2 e) and K, V pre-split into hi / lo, rows padded to HD + 4 floats
+//   (conflict-free fragment loads: (HD+4) g + t and 2 (HD+4) t + g hit 32 distinct banks for HD = 8, 16, 32).
+// hi part of the 3xTF32 split by TRUNCATION (one LOP3 on the ALU pipe; cvt.rna.tf32 runs on the 16-lane XU pipe, which the
+// exponentials already load): x = hi + lo exactly, |lo| < 2^-10 |x|, and the tensor core's own truncation of lo costs 2^-20 |x|
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return __float_as_uint(x) & 0xFFFFE000u; }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ void mma_tf32(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+
+// Persistent blocks: a block walks windows w = blockIdx.x, += gridDim.x for its HPB heads; the q / k / v rows of the NEXT window
+// stream into the second shared-memory buffer with cp.async while the current one is computed (the first version of this
+// kernel staged, synchronised and computed one window per block: 16 K cycles per block for ~2 K cycles of issue, i.e. bound by
+// the exposed global-load latency at 32 warps per SM).  The hi / lo split happens at fragment-load time.
+template <int HD, int HPB>
+__global__ void __launch_bounds__(HPB * 128) wmsa_mma_kernel(const float* __restrict__ qkv, int H, int W, int C, int ldq, int shifted,
+                                                             const float* __restrict__ relpos, float* __restrict__ out, int ldo, int nheads,
+                                                             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int ldp,
+                                                             int nwin) {
+    constexpr int WS = 8, P = 64, LD = HD + 4, RP = (2 * WS - 1) * (2 * WS - 1);
+    constexpr float LOG2E = 1.4426950408889634f;
+    extern __shared__ __align__(16) float sm[];
+    // [2 buffers][HPB heads][q | k | v][P][LD] fp32, then [HPB][RP] bias
+    constexpr int HEAD_FLOATS = 3 * P * LD, BUF_FLOATS = HPB * HEAD_FLOATS;
+    float* bias_all = sm + 2 * BUF_FLOATS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int hl = warp >> 2, mt = warp & 3;            // head within the block, 16-query tile
+    const int head0 = blockIdx.y * HPB;
+    const int nww = W / WS, nwh = H / WS;
+    const int sh = shifted ? WS / 2 : 0;
+    const float qscale = rsqrtf((float)HD) * LOG2E;
+    constexpr int V4_PER_TOK = 3 * HPB * HD / 4;
+
+    // thread -> (token, 16-byte chunk of the block's HPB*HD contiguous floats), the same for q, k and v: three cp.async per token
+    constexpr int F4 = HPB * HD / 4, TOK_STEP = HPB * 128 / F4;
+    const int pf_c = tid % F4, pf_t0 = tid / F4;
+    const int pf_h = (4 * pf_c) / HD, pf_d = (4 * pf_c) % HD;
+    const bool pf_live = head0 + pf_h < nheads;
+    auto prefetch = [&](int win, int buf) {
+        const int n = win / (nwh * nww);
+        const int wrem = win - n * nwh * nww;
+        const int wy = wrem / nww, wx = wrem - wy * nww;
+        float* dstb = sm + buf * BUF_FLOATS + pf_h * HEAD_FLOATS + pf_d;
+        if (pf_live) {
+#pragma unroll
+            for (int tok = pf_t0; tok < P; tok += TOK_STEP) {
+                const int py = tok >> 3, px = tok & 7;
+                int gy = wy * WS + py + sh, gx = wx * WS + px + sh;
+                if (gy >= H) gy -= H;
+                if (gx >= W) gx -= W;
+                const float* src = qkv + ((long long)(n * H + gy) * W + gx) * ldq + head0 * HD + 4 * pf_c;
+                float* dst = dstb + tok * LD;
+                cp_async16(dst, src);
+                cp_async16(dst + P * LD, src + C);
+                cp_async16(dst + 2 * P * LD, src + 2 * C);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    for (int i = tid; i < HPB * RP; i += HPB * 128) {
+        const int h = i / RP, r = i - h * RP;
+        bias_all[i] = (head0 + h < nheads) ? relpos[(size_t)(head0 + h) * RP + r] * LOG2E : 0.f;
+    }
+    const int head = head0 + hl;
+    const bool live = head < nheads;
+    const float* bias = bias_all + hl * RP;
+    const int g = lane >> 2, t = lane & 3;
+
+    int buf = 0;
+    if ((int)blockIdx.x < nwin) prefetch(blockIdx.x, 0);
+    for (int win = blockIdx.x; win < nwin; win += gridDim.x, buf ^= 1) {
+        const int next = win + gridDim.x;
+        if (next < nwin) {
+            prefetch(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        if (live) {
+            const int n = win / (nwh * nww);
+            const int wrem = win - n * nwh * nww;
+            const int wy = wrem / nww, wx = wrem - wy * nww;
+            const float* Qs = sm + buf * BUF_FLOATS + hl * HEAD_FLOATS;
+            const float* Ks = Qs + P * LD;
+            const float* Vs = Ks + P * LD;
+            // ---- Q fragments of this warp's 16 queries (rows 16 mt + g and + 8), scaled and split hi / lo
+            uint32_t qh[HD / 8][4], ql[HD / 8][4];
+#pragma unroll
+            for (int ks = 0; ks < HD / 8; ++ks) {
+                const float f[4] = {Qs[(16 * mt + g) * LD + 8 * ks + t], Qs[(16 * mt + g + 8) * LD + 8 * ks + t],
+                                    Qs[(16 * mt + g) * LD + 8 * ks + t + 4], Qs[(16 * mt + g + 8) * LD + 8 * ks + t + 4]};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float fs = f[j] * qscale;
+                    qh[ks][j] = tf32_hi(fs);
+                    ql[ks][j] = __float_as_uint(fs - __uint_as_float(qh[ks][j]));
+                }
+            }
+            // ---- S = bias (+ mask) + Q K^T: query rows i0 = 16 mt + g -> (py, px) = (2 mt, g) and i1 = i0 + 8 -> (2 mt + 1, g);
+            //      key 8 nt + 2 t (+1) -> (jy, jx) = (nt, 2 t (+1))
+            const bool edge_y = shifted && (wy == nwh - 1), edge_x = shifted && (wx == nww - 1);
+            const bool cq = edge_x && (g >= WS - sh);
+            const bool rq0 = edge_y && (2 * mt >= WS - sh), rq1 = edge_y && (2 * mt + 1 >= WS - sh);
+            float s[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                const int b0i = (2 * mt - nt + WS - 1) * (2 * WS - 1) + (g - 2 * t + WS - 1);    // (i0, key 2t); key 2t+1 is one entry to the left
+                s[nt][0] = bias[b0i];
+                s[nt][1] = bias[b0i - 1];
+                s[nt][2] = bias[b0i + (2 * WS - 1)];
+                s[nt][3] = bias[b0i + (2 * WS - 1) - 1];
+            }
+            if (edge_y || edge_x) {   // block-uniform: only the last window row / column of a shifted map pays for the mask
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    const bool rk = edge_y && (nt >= WS - sh);
+                    const bool ck0 = edge_x && (2 * t >= WS - sh), ck1 = edge_x && (2 * t + 1 >= WS - sh);
+                    if (rk != rq0 || ck0 != cq) s[nt][0] = -INFINITY;
+                    if (rk != rq0 || ck1 != cq) s[nt][1] = -INFINITY;
+                    if (rk != rq1 || ck0 != cq) s[nt][2] = -INFINITY;
+                    if (rk != rq1 || ck1 != cq) s[nt][3] = -INFINITY;
+                }
+            }
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int ks = 0; ks < HD / 8; ++ks) {
+                    const int o0 = (8 * nt + g) * LD + 8 * ks + t;
+                    const float k0 = Ks[o0], k1 = Ks[o0 + 4];
+                    const uint32_t kh0 = tf32_hi(k0), kh1 = tf32_hi(k1);
+                    const uint32_t kl0 = __float_as_uint(k0 - __uint_as_float(kh0)), kl1 = __float_as_uint(k1 - __uint_as_float(kh1));
+                    mma_tf32(s[nt], ql[ks], kh0, kh1);
+                    mma_tf32(s[nt], qh[ks], kl0, kl1);
+                    mma_tf32(s[nt], qh[ks], kh0, kh1);
+                }
+            }
+            // ---- softmax over the 64 keys of rows i0 (elements 0, 1) and i1 (elements 2, 3): quad-wide reductions
+            float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
+                m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
+            }
+            m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+            float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = ex2_approx(s[nt][0] - m0); s[nt][1] = ex2_approx(s[nt][1] - m0);
+                s[nt][2] = ex2_approx(s[nt][2] - m1); s[nt][3] = ex2_approx(s[nt][3] - m1);
+                d0 += s[nt][0] + s[nt][1];
+                d1 += s[nt][2] + s[nt][3];
+            }
+            d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+            d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+            // ---- O = P V (un-normalised), keys in blocks of 8 with the re-labelled k index
+            float o[HD / 8][4];
+#pragma unroll
+            for (int dt = 0; dt < HD / 8; ++dt) { o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f; }
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+                const float pf[4] = {s[kk][0], s[kk][2], s[kk][1], s[kk][3]};     // a0 = c0, a1 = c2, a2 = c1, a3 = c3
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    ph[j] = tf32_hi(pf[j]);
+                    pl[j] = __float_as_uint(pf[j] - __uint_as_float(ph[j]));
+                }
+#pragma unroll
+                for (int dt = 0; dt < HD / 8; ++dt) {
+                    const int o0 = (8 * kk + 2 * t) * LD + 8 * dt + g;
+                    const float v0 = Vs[o0], v1 = Vs[o0 + LD];
+                    const uint32_t vh0 = tf32_hi(v0), vh1 = tf32_hi(v1);
+                    const uint32_t vl0 = __float_as_uint(v0 - __uint_as_float(vh0)), vl1 = __float_as_uint(v1 - __uint_as_float(vh1));
+                    mma_tf32(o[dt], pl, vh0, vh1);
+                    mma_tf32(o[dt], ph, vl0, vl1);
+                    mma_tf32(o[dt], ph, vh0, vh1);
+                }
+            }
+            const float inv0 = 1.f / d0, inv1 = 1.f / d1;
+            // ---- store: rows i0, i1 -> pixels of the (shifted) window; each lane holds channels head*HD + 8 dt + 2 t, +1
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int py = 2 * mt + r, px = g;
+                int gy = wy * WS + py + sh, gx = wx * WS + px + sh;
+                if (gy >= H) gy -= H;
+                if (gx >= W) gx -= W;
+                const long long opix = (long long)(n * H + gy) * W + gx;
+                const float inv = r ? inv1 : inv0;
+#pragma unroll
+                for (int dt = 0; dt < HD / 8; ++dt) {
+                    const float v0 = o[dt][2 * r] * inv, v1 = o[dt][2 * r + 1] * inv;
+                    const int ch = head * HD + 8 * dt + 2 * t;
+                    if (out) *reinterpret_cast<float2*>(out + opix * ldo + ch) = make_float2(v0, v1);
+                    if (out_hi) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+                        __nv_bfloat162 hp; hp.x = h0; hp.y = h1;
+                        *reinterpret_cast<__nv_bfloat162*>(out_hi + opix * ldp + ch) = hp;
+                        if (out_lo) {
+                            __nv_bfloat162 lp;
+                            lp.x = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+                            lp.y = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+                            *reinterpret_cast<__nv_bfloat162*>(out_lo + opix * ldp + ch) = lp;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();   // every warp is done with this buffer before the next iteration's prefetch overwrites it
+    }
+}
+
+template <int HD>
+int launch_wmsa_mma(const float* qkv, int N, int H, int W, int C, int ldq, int shifted, const float* relpos, float* out, int ldo,
+                    __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldp, cudaStream_t s) {
+    constexpr int HPB = (HD == 32) ? 1 : 2;           // heads per block (4 warps each)
+    constexpr int P = 64, LD = HD + 4, RP = 225;
+    const int nheads = C / HD;
+    const int nwin = N * (H / 8) * (W / 8);
+    const int groups = (nheads + HPB - 1) / HPB;
+    const size_t smem = ((size_t)2 * HPB * 3 * P * LD + (size_t)HPB * RP) * sizeof(float);
+    auto kern = wmsa_mma_kernel<HD, HPB>;
+    static bool attr[64] = {};
+    static int resident[64] = {};      // blocks of this instantiation that fit on the device at once
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!attr[dev]) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, HPB * 128, smem);
+        resident[dev] = (sms > 0 ? sms : 148) * (per_sm > 0 ? per_sm : 1);
+        attr[dev] = true;
+    }
+    // persistent: exactly one wave of resident blocks, shared by the head groups
+    int gx = resident[dev] / groups;
+    if (gx > nwin) gx = nwin;
+    if (gx < 1) gx = 1;
+    dim3 grid((unsigned)gx, (unsigned)groups);
+    kern<<<grid, HPB * 128, smem, s>>>(qkv, H, W, C, ldq, shifted, relpos, out, ldo, nheads, out_hi, out_lo, ldp, nwin);
+    return 0;
+}
+
 template <int WS, int HD>
 int launch_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, int shifted, const float* relpos,
                 float* out, int ldo, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int ldp, cudaStream_t s) {
@@ -292,7 +561,13 @@ extern "C" int rcn_wmsa(const float* qkv, int N, int H, int W, int C, int ldq, i
     RCN_CHECK_ARG(((uintptr_t)qkv & 15) == 0 && ((uintptr_t)out & 15) == 0, "rcn_wmsa: pointers must be 16-byte aligned");
     cudaStream_t s = (cudaStream_t)stream;
     int rc = -1;
-    if (ws == 8 && head_dim == 8) rc = launch_wmsa<8, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    static const bool use_mma = !(getenv("RCN_WMSA_FFMA") && atoi(getenv("RCN_WMSA_FFMA")));   // triage: 1 = CUDA-core kernel for 8x8 windows too
+    const bool mma_ok = use_mma && ws == 8 && (!out_hi || ((uintptr_t)out_hi % 4 == 0 && (!out_lo || (uintptr_t)out_lo % 4 == 0) && ldp % 2 == 0)) &&
+                        (!out || ((uintptr_t)out % 8 == 0 && ldo % 2 == 0));
+    if (mma_ok && head_dim == 8) rc = launch_wmsa_mma<8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (mma_ok && head_dim == 16) rc = launch_wmsa_mma<16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (mma_ok && head_dim == 32) rc = launch_wmsa_mma<32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
+    else if (ws == 8 && head_dim == 8) rc = launch_wmsa<8, 8>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
     else if (ws == 8 && head_dim == 16) rc = launch_wmsa<8, 16>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
     else if (ws == 8 && head_dim == 32) rc = launch_wmsa<8, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);
     else if (ws == 4 && head_dim == 32) rc = launch_wmsa<4, 32>(qkv, N, H, W, C, ldq, shifted, relpos, out, ldo, out_hi, out_lo, ldp, s);

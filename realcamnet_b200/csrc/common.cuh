@@ -47,11 +47,28 @@ __device__ __forceinline__ float erf_as(float x) {
     return copysignf(r, x);
 }
 
+// GELU (erf form) with the same A&S 7.1.26 erf, rearranged so that the sign handling and the 0.5 factors disappear:
+//   0.5 v (1 + erf(v / sqrt 2)) = max(v, 0) - |v| exp(-v^2 / 2) * q(t),  t = 1 / (1 + p |v| / sqrt 2),  q = 0.5 t (a1 + t (a2 + ...))
+// 6 FFMA + 4 FMUL + FMNMX + 2 MUFU per element (the direct form costs 8 FFMA + 8 FMUL + 3 FADD + selects: the GELU epilogues of
+// the Swin MLPs are bound by exactly this instruction count, profiles/r2_conv_epilogue_ncu.md).
+__device__ __forceinline__ float gelu_as(float v) {
+    const float av = fabsf(v);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, av, 1.f)));
+    float q = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+    q = fmaf(q, t, 0.5f * 1.421413741f);
+    q = fmaf(q, t, 0.5f * -0.284496736f);
+    q = fmaf(q, t, 0.5f * 0.254829592f);
+    q *= t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * v * (-0.5f * 1.4426950408889634f)));
+    return fmaf(-(av * e), q, fmaxf(v, 0.f));
+}
+
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
     switch (act) {
         case RCN_ACT_RELU: return v > 0.f ? v : 0.f;
         case RCN_ACT_LRELU: return v > 0.f ? v : v * slope;
-        case RCN_ACT_GELU: return 0.5f * v * (1.f + erf_as(v * 0.70710678118654752440f));
+        case RCN_ACT_GELU: return gelu_as(v);
         case RCN_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
         case RCN_ACT_HALF_TANH: return 0.5f * tanhf(v);
         case RCN_ACT_CLAMP01: return fminf(fmaxf(v, 0.f), 1.f);

@@ -204,8 +204,27 @@ constexpr int WCOLS = 128 / (EPI_WARPS / 4);  // 64 (8 warps) or 32 (16 warps)
 constexpr int QN = WCOLS / 16;                // 16-column quarters per warp and tile
 constexpr int EPI_THREADS = EPI_WARPS * 32;
 constexpr int MMA_WARPS = 2;             // warps 1, 2: each issues half of a stage's k16 steps into its own TMEM accumulator
-constexpr int EPI_WARP0 = 1 + MMA_WARPS; // first epilogue warp
+// Warp groups: warps 0-3 = TMA producer, MMA issuer(s), one idle warp; warps 4-11 = epilogue.  The roles are aligned to warp
+// groups so that the register file can be re-split after the prologue (setmaxnreg): the three single-lane warps need ~40
+// registers, the epilogue (64 accumulator columns, prefetched residual / aux operands, 256-bit stores) wants > 168 -- with one
+// budget for all 12 warps ptxas spilled loop counters of the epilogue to local memory (ncu: LDL round trips through L2 on every
+// tile, ~4 % of the launch).  384 threads x 168 = 64512 registers at launch; 128 x 96 + 256 x 200 afterwards (40 for the light warps made ptxas spill inside the halo kernel's MMA issue loop: 3x slower).
+constexpr int EPI_WARP0 = 4;             // first epilogue warp
 constexpr int TC_THREADS = 32 * EPI_WARP0 + EPI_THREADS;
+constexpr int REGS_LIGHT = 96, REGS_EPI = 200;
+// Called at the top of each role's branch (every warp of a warp group executes the same one), so that ptxas knows the budget
+// of the code that follows: issued once before the role dispatch, the epilogue of the halo kernel was still compiled against
+// the smaller budget and spilled 2 KB per thread.
+__device__ __forceinline__ void regs_light() {
+#if RCN_TC_EPI_WARPS == 8
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_LIGHT));
+#endif
+}
+__device__ __forceinline__ void regs_epilogue() {
+#if RCN_TC_EPI_WARPS == 8
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
+#endif
+}
 constexpr int SLAB_FLOATS = 32 * 16;     // warp-private transposition slab: 32 pixel rows x 16 floats, 16-byte chunks XOR-swizzled
 constexpr int STG_BYTES = EPI_WARPS * SLAB_FLOATS * 4;   // 16 KB
 // The bias vector is staged in shared memory once per CTA: with ~220 KB of the SM's 228 KB carved out as shared memory there
@@ -543,14 +562,28 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
             ldg256(pp + 8, &pre[hh][8]);
         }
     }
+    static_assert(!DUAL, "the row-vector epilogue reads one accumulator per tile");
     mbar_wait(full_bar, parity);
     tc_fence_after();
     if (wcols <= 0 || (r.flags & EF_SKIP)) { epi_release(empty_bar, lane); return; }
-    uint32_t v[16], w2[16];
-    tmem_ld16x2_async(taddr, v, w2, DUAL);
+    // TMEM -> registers two 16-column blocks at a time: tcgen05.wait::ld waits for EVERY outstanding load, so with one block in
+    // flight each of the four waits of a tile exposed the load latency (ncu: ~12 % of the epilogue's samples on the instruction
+    // after the wait).  Blocks (0,1) are requested together; while they are processed, (2,3) are in flight.
+    uint32_t va[16], vb[16];
+    tmem_ld16_async(taddr, va);
+    if (16 < wcols) tmem_ld16_async(taddr + 16, vb);
+    tmem_wait_ld16(va);
+    tmem_wait_ld16(vb);
+    if (wcols <= 32) epi_release(empty_bar, lane);      // every TMEM read of this tile by this warp has landed
 #pragma unroll
     for (int hh = 0; hh < QN; ++hh) {
         if (16 * hh >= wcols) break;   // warp-uniform
+        uint32_t* v = (hh & 1) ? vb : va;
+        if (hh == 2) {                 // second pair: requested while blocks 0 and 1 were processed
+            tmem_wait_ld16(va);
+            tmem_wait_ld16(vb);
+            epi_release(empty_bar, lane);
+        }
         const long long spix = pix0 + RCN_QOFF(hh);
         const int ch = chb + chs * hh;                    // first stored channel of this block
         // conv channel of column j: plain store cb + 16 hh + j; pixel shuffle (sub-pixel-grouped rows) cb + 4 j + hh
@@ -563,7 +596,6 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
             ldg256(ap, &sec[0]);
             ldg256(ap + 8, &sec[8]);
         }
-        tmem_wait_sum16(v, w2, DUAL);
         float val[16];
         if (sbias) {
             if (!ps) {
@@ -581,8 +613,8 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
 #pragma unroll
             for (int j = 0; j < 16; ++j) val[j] = __uint_as_float(v[j]);
         }
-        if (16 * (hh + 1) < wcols) tmem_ld16x2_async(taddr + 16 * (hh + 1), v, w2, DUAL);   // next block in flight
-        else epi_release(empty_bar, lane);                                                  // last TMEM read of this tile by this warp
+        // this buffer's registers are consumed: request block hh + 2 into it; after the last request the accumulator is free
+        if (16 * (hh + 2) < wcols) tmem_ld16_async(taddr + 16 * (hh + 2), v);
         if (!ok) continue;
         if (r.flags & EF_CS) {
 #pragma unroll
@@ -605,16 +637,31 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
             stg256(yp + 8, &val[8]);
         }
         if (r.flags & EF_HI) {
-            // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16)
-            const int f16 = (r.flags & EF_F16OUT) ? 1 : 0;
+            // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16), converted two
+            // elements per instruction (F2FP pack); the format branch is warp-uniform and sits outside the element loop
             uint32_t hp[8], lp[8];
+            if (r.flags & EF_F16OUT) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint16_t h0 = to_plane(val[2 * j], f16), h1 = to_plane(val[2 * j + 1], f16);
-                hp[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-                if (r.flags & EF_LO) {
-                    const uint16_t l0 = to_plane(val[2 * j] - from_plane(h0, f16), f16), l1 = to_plane(val[2 * j + 1] - from_plane(h1, f16), f16);
-                    lp[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+                for (int j = 0; j < 8; ++j) {
+                    const __half2 h2 = __floats2half2_rn(val[2 * j], val[2 * j + 1]);
+                    hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                    if (r.flags & EF_LO) {
+                        const float2 hf = __half22float2(h2);
+                        const __half2 l2 = __floats2half2_rn(val[2 * j] - hf.x, val[2 * j + 1] - hf.y);
+                        lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const __nv_bfloat162 h2 = __floats2bfloat162_rn(val[2 * j], val[2 * j + 1]);
+                    hp[j] = *reinterpret_cast<const uint32_t*>(&h2);
+                    if (r.flags & EF_LO) {
+                        // bf16 -> fp32 is a 16-bit shift: low half << 16, high half masked
+                        const float f0 = __uint_as_float(hp[j] << 16), f1 = __uint_as_float(hp[j] & 0xFFFF0000u);
+                        const __nv_bfloat162 l2 = __floats2bfloat162_rn(val[2 * j] - f0, val[2 * j + 1] - f1);
+                        lp[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                    }
                 }
             }
             long long po = spix * r.cpo + ch;
@@ -812,6 +859,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
+        regs_light();
         // ================= TMA producer =================
         // Same shape as the MMA issue loops: the whole warp walks the loop (uniform control flow), one elected lane issues the
         // TMA instructions; loop invariants live in registers; (tap, chunk) advance incrementally instead of by division.
@@ -872,7 +920,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
         }
     } else if (warp < EPI_WARP0) {
-        // ================= MMA issuers (warps 1 and 2) =================
+        regs_light();
+        // ================= MMA issuers (warps 1 and 2; warp 3 idles) =================
         // The single thread that issues tcgen05.mma is the bottleneck of every layer with a long K loop: ptxas wraps each UTCHMMA
         // issued from divergent code in an ELECT / PLOP3 / BRA.U.ANY sequence, ~120 cycles per MMA against the 64-90 the tensor
         // pipe needs for M128 x N128 x K16 (ncu: producer waiting on free stages, MMA warp never waiting on data, tensor pipe 56 %
@@ -910,6 +959,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
         }
     } else {
+        regs_epilogue();
         // ================= epilogue: TMEM -> registers -> (warp-private transposition slab) -> fused element-wise -> global
         const int q = warp & 3;            // TMEM lane quarter this warp may access (hardware: warp_id % 4)
         const int jsub = (warp - EPI_WARP0) >> 2;  // which WCOLS-column slice of the accumulator this warp drains
@@ -936,10 +986,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             const uint32_t ab = local & 1;
             const uint32_t taddr = tmem_base + ab * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(wcw * jsub);
             if constexpr (VEC) {
-                if (rvflag)
-                    epilogue_tile_rv<ACT, EPI, DUAL, TILE_W>(er, act, epi, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0, y0,
-                                                             n0 + wcw * jsub, wcols, q, lane);
-                else
+                bool done = false;
+                if constexpr (!DUAL) {
+                    if (rvflag) {
+                        epilogue_tile_rv<ACT, EPI, false, TILE_W>(er, act, epi, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0,
+                                                                  y0, n0 + wcw * jsub, wcols, q, lane);
+                        done = true;
+                    }
+                }
+                if (!done)
                     epilogue_tile_vec<ACT, EPI, DUAL, TILE_W>(er, act, epi, slab, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n,
                                                               x0, y0, n0 + wcw * jsub, wcols, q, lane);
             }
@@ -1030,17 +1085,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // loop invariants shared by the producer and the issuer, held in registers
-    uint32_t total_tiles = (uint32_t)P.total_tiles, tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
-    int Ntile = P.Ntile, Cp = P.Cp, nch = chunks, stages = P.stages, na = P.na, three = (P.passes == 3), dbg = P.dbg, Cout = p.Cout;
-    uint32_t abytes = (uint32_t)abuf_bytes, bsbytes = (uint32_t)bstage_bytes, bbytes = (uint32_t)P.b_bytes;
-    opaque(total_tiles); opaque(tiles_n); opaque(tiles_x); opaque(tiles_y); opaque(Ntile); opaque(Cp); opaque(nch); opaque(stages);
-    opaque(na); opaque(three); opaque(dbg); opaque(Cout); opaque(abytes); opaque(bsbytes); opaque(bbytes);
-    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(bsm);
-    const uint32_t afull_a = smem_u32(afull), aempty_a = smem_u32(aempty), bfull_a = smem_u32(bfull), bempty_a = smem_u32(bempty);
+    // loop invariants of the producer / issuer loops, held in registers (declared inside each role's branch: values hoisted
+    // above the role dispatch stay live in the epilogue warps too and pushed their code into local-memory spills)
+#define RCN_HALO_INVARIANTS                                                                                                              \
+    uint32_t total_tiles = (uint32_t)P.total_tiles, tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x,                         \
+             tiles_y = (uint32_t)P.tiles_y;                                                                                              \
+    int Ntile = P.Ntile, Cp = P.Cp, nch = chunks, stages = P.stages, na = P.na, three = (P.passes == 3), dbg = P.dbg, Cout = p.Cout;     \
+    uint32_t abytes = (uint32_t)abuf_bytes, bsbytes = (uint32_t)bstage_bytes, bbytes = (uint32_t)P.b_bytes;                               \
+    opaque(total_tiles); opaque(tiles_n); opaque(tiles_x); opaque(tiles_y); opaque(Ntile); opaque(Cp); opaque(nch); opaque(stages);      \
+    opaque(na); opaque(three); opaque(dbg); opaque(Cout); opaque(abytes); opaque(bsbytes); opaque(bbytes);                               \
+    const uint32_t a0 = smem_u32(smem), b0 = smem_u32(bsm);                                                                              \
+    const uint32_t afull_a = smem_u32(afull), aempty_a = smem_u32(aempty), bfull_a = smem_u32(bfull), bempty_a = smem_u32(bempty);       \
+    (void)tiles_x; (void)tiles_y; (void)Cp; (void)Cout; (void)dbg; (void)a0; (void)b0; (void)afull_a; (void)aempty_a; (void)bfull_a;     \
+    (void)bempty_a; (void)abytes; (void)bsbytes; (void)bbytes; (void)na; (void)stages; (void)nch; (void)three; (void)Ntile; (void)tiles_n
 
     if (warp == 0) {
+        regs_light();
         // ================= TMA producer: per tile and chunk one halo box (hi [+ lo]), then the 9 weight tiles of that chunk
+        RCN_HALO_INVARIANTS;
         const uint32_t a_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)HALO_TX, b_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)Ntile * 128u;
         uint32_t ab = 0, aph = 0, st = 0, bph = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -1074,7 +1136,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             }
         }
     } else if (warp == 1) {
+        regs_light();
         // ================= MMA issuer (one warp, converged, tcgen05 instructions behind elect.sync)
+        RCN_HALO_INVARIANTS;
         const uint32_t tfull_a = smem_u32(tmem_full), tempty_a = smem_u32(tmem_empty);
         const uint32_t idesc_fmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
         const int bo_mode = (dbg & 64) ? 1 : 0;   // triage only: 1 sets the descriptor's base-offset field (WRONG on B200, see above)
@@ -1120,7 +1184,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             if (elect_one()) umma_commit_a(tfull_a + 8u * acb);
             __syncwarp();
         }
-    } else if (warp >= EPI_WARP0) {
+    } else if (warp < EPI_WARP0) {
+        regs_light();      // idle warps of the first warp group
+    } else {
+        regs_epilogue();
         // ================= epilogue (same code as the tap-by-tap kernel, tile geometry 16 x 8)
         const int q = warp & 3;
         const int jsub = (warp - EPI_WARP0) >> 2;
@@ -1128,8 +1195,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         const EpiRegs er = make_epi_regs(p, P.dbg, false);
         int act = p.act, epi = p.epi, store = p.store;
         opaque(act); opaque(epi); opaque(store);
-        int wcw = P.wcw, rvflag = P.rv;
-        opaque(wcw); opaque(rvflag);
+        int wcw = P.wcw, rvflag = P.rv, Ntile = P.Ntile;
+        uint32_t total_tiles = (uint32_t)P.total_tiles, tiles_n = (uint32_t)P.tiles_n, tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+        opaque(wcw); opaque(rvflag); opaque(Ntile); opaque(total_tiles); opaque(tiles_n); opaque(tiles_x); opaque(tiles_y);
         uint32_t local = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
             const int nt = (int)(t % tiles_n);
@@ -1157,6 +1225,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                                                           n, x0, y0, n0 + wcw * jsub, wcols, q, lane);
         }
     }
+#undef RCN_HALO_INVARIANTS
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -1532,7 +1601,7 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     // row-vector epilogue: 16-column blocks and 32-byte accesses
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
     const int cs_store = (d->store == RCN_STORE_PS2) ? d->Cout / 4 : d->Cout;
-    P.rv = (vec && env.rv && (d->Cout % 16) == 0 && (cs_store % 16) == 0 && (!d->y || ((d->ldy & 7) == 0 && al32(d->y))) &&
+    P.rv = (vec && env.rv && P.nmma == 1 && (d->Cout % 16) == 0 && (cs_store % 16) == 0 && (!d->y || ((d->ldy & 7) == 0 && al32(d->y))) &&
             (!d->res || ((d->ldres & 7) == 0 && al32(d->res))) && (d->epi == RCN_EPI_NONE || ((d->ldaux & 7) == 0 && al32(d->aux))) &&
             (!d->y_hi || ((d->Cp_out & 15) == 0 && al32(d->y_hi) && (!d->y_lo || al32(d->y_lo)))) &&
             (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0))

@@ -103,24 +103,63 @@ def compress_frame_distributed(model, frame: torch.Tensor | None, height: int, w
     from . import container, tiler
     from . import frame as rframe
 
+    import os
+    import time
+
+    timing = bool(os.environ.get("RCN_FRAME_TIMING"))
+    marks = []
+
+    def mark(name):
+        if timing:
+            torch.cuda.synchronize()
+            marks.append((name, time.perf_counter()))
+
     rank, world = _rank_world()
     ny, nx = tiler.tile_grid(height, width, tile)
     meta, ntiles = (height, width, ny, nx), ny * nx
+    mark("start")
     if rank == 0:
         fdev = frame.to(device, non_blocking=True)
         tiles = tiler.split_frame(fdev, tile)[0]
         cond = rframe.frame_condition(fdev)
     else:
         tiles, cond = None, torch.empty((1, 4, 256, 256), device=device)
+    mark("upload+tile+cond")
     if world > 1:
         dist.broadcast(cond, 0)
     mine = my_tiles(ntiles, rank, world)
     local = scatter_tiles(tiles, ntiles, (4, tile, tile), device=device)
-    out = rframe.compress_tiles(model, local, cond, tiler.tiles_coords(meta, tile, mine, device=device), max_batch=max_batch)
+    mark("scatter")
+    coords = _coords_cached(meta, tile, tuple(mine), device)
+    mark("coords")
+    out = rframe.compress_tiles(model, local, cond, coords, max_batch=max_batch)
+    mark("compress_tiles")
     all_y = gather_bitstreams([o[0] for o in out], ntiles, device=device)
     all_z = gather_bitstreams([o[1] for o in out], ntiles, device=device)
+    mark("gather")
     if rank != 0:
         return None
     shape = out[0][2]
     recs = [container.TileStreams(t, shape, all_y[t], all_z[t]) for t in range(ntiles)]
-    return container.pack(container.FrameHeader(model_id, height, width, tile, ny, nx, ntiles), recs)
+    blob = container.pack(container.FrameHeader(model_id, height, width, tile, ny, nx, ntiles), recs)
+    mark("pack")
+    if timing:
+        import sys
+        print("frame timing (ms): " + ", ".join(f"{b[0]} {1e3 * (b[1] - a[1]):.1f}" for a, b in zip(marks, marks[1:])), file=sys.stderr)
+    return blob
+
+
+_coords_cache: dict = {}
+
+
+def _coords_cached(meta, tile, mine, device):
+    """Per-tile coordinate maps depend on the frame geometry only: built once per (geometry, tile share, device)."""
+    from . import tiler
+
+    key = (meta, tile, mine, str(device))
+    c = _coords_cache.get(key)
+    if c is None:
+        if len(_coords_cache) > 8:
+            _coords_cache.clear()
+        c = _coords_cache[key] = tiler.tiles_coords(meta, tile, mine, device=device)
+    return c
