@@ -101,13 +101,13 @@ class Res_GFM(nn.Module):
         self.out_nc = chan
         self.act = nn.LeakyReLU(inplace=True)
 
-    def _f(self, x, vec):
-        """x NHWC, vec (N,1,1,cond_c)"""
+    def _f(self, x, vec, presplit=None, emit_split=False):
+        """x NHWC, vec (N,1,1,cond_c); presplit: operand planes of x from its producer; emit_split: returns (out, planes of out)"""
         scale = self.GFM_scale_conv1._f(self.GFM_scale_conv0._f(vec, act=ACT_LRELU, slope=0.1))
         shift = self.GFM_shift_conv1._f(self.GFM_shift_conv0._f(vec, act=ACT_LRELU, slope=0.1))
         fea, sp = self.conv0._f(x, cscale=scale.reshape(-1), cshift=shift.reshape(-1), act=ACT_LRELU, slope=0.01,
-                                emit_split=True, keep_fp32=False)
-        return self.conv1._f(fea, res=x, presplit=sp)
+                                emit_split=True, keep_fp32=False, presplit=presplit)
+        return self.conv1._f(fea, res=x, presplit=sp, emit_split=emit_split)
 
     def forward(self, x):
         fea = self._f(ops.to_nhwc(x[0]), x[1].reshape(x[1].shape[0], 1, 1, -1).contiguous())

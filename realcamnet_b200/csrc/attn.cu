@@ -101,6 +101,74 @@ __global__ void layernorm_vec_kernel(const float* __restrict__ x, long long npix
     }
 }
 
+// Any C % 4 == 0 up to 128 * NV (GroupMix: C = 80, 200, 16): one warp per pixel and step, NV float4 per lane (lanes past C / 4
+// idle), PIX_IT pixels in flight per warp.  The scalar kernel above issues one 4-byte load per lane and channel.
+template <int NV, int PIX_IT>
+__global__ void layernorm_vecg_kernel(const float* __restrict__ x, long long npix, int C, int ldx, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, float eps, float* __restrict__ y, int ldy, int act,
+                                      __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int ldp) {
+    const int lane = threadIdx.x & 31;
+    const long long wg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long base = wg * PIX_IT;
+    if (base >= npix) return;
+    float4 v[PIX_IT][NV], g[NV], b[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        const int c = 4 * lane + 128 * k;
+        g[k] = c < C ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b[k] = c < C ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int it = 0; it < PIX_IT; ++it) {
+        const long long pix = base + it;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = 4 * lane + 128 * k;
+            v[it][k] = (pix < npix && c < C) ? *reinterpret_cast<const float4*>(x + pix * ldx + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+#pragma unroll
+    for (int it = 0; it < PIX_IT; ++it) {
+        const long long pix = base + it;
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) s += (v[it][k].x + v[it][k].y) + (v[it][k].z + v[it][k].w);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            if (4 * lane + 128 * k < C) {
+                const float dx = v[it][k].x - mean, dy = v[it][k].y - mean, dz = v[it][k].z - mean, dw = v[it][k].w - mean;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q / (float)C + eps);
+        if (pix >= npix) continue;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            const int c = 4 * lane + 128 * k;
+            if (c >= C) continue;
+            float r[4] = {act_apply((v[it][k].x - mean) * rstd * g[k].x + b[k].x, act, 0.f), act_apply((v[it][k].y - mean) * rstd * g[k].y + b[k].y, act, 0.f),
+                          act_apply((v[it][k].z - mean) * rstd * g[k].z + b[k].z, act, 0.f), act_apply((v[it][k].w - mean) * rstd * g[k].w + b[k].w, act, 0.f)};
+            if (y) *reinterpret_cast<float4*>(y + pix * ldy + c) = make_float4(r[0], r[1], r[2], r[3]);
+            if (y_hi) {
+                __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    hb[e] = __float2bfloat16_rn(r[e]);
+                    lb[e] = __float2bfloat16_rn(r[e] - __bfloat162float(hb[e]));
+                }
+                *reinterpret_cast<uint2*>(y_hi + pix * ldp + c) = *reinterpret_cast<uint2*>(hb);
+                if (y_lo) *reinterpret_cast<uint2*>(y_lo + pix * ldp + c) = *reinterpret_cast<uint2*>(lb);
+            }
+        }
+    }
+}
+
 // Window attention. One thread per (query token, head); blockDim = (P, HPB) with P = WS*WS tokens.
 // K and V of the head are staged in shared memory (broadcast reads), scores live in registers.
 template <int WS, int HD>
@@ -533,6 +601,15 @@ extern "C" int rcn_layernorm(const float* x, long long npix, int C, int ldx, con
             const int g2 = cdiv(npix, (long long)wpb * 1 * PIX_IT);
             layernorm_vec_kernel<32, PIX_IT><<<g2, wpb * 32, 0, s>>>(x, npix, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
         }
+        count_launch();
+        RCN_CHECK_LAUNCH("rcn_layernorm");
+        return RCN_OK;
+    }
+    if (al && C % 4 == 0 && C <= 256) {   // (C = 64 / 128 took the fixed-width kernel above)
+        constexpr int PIX_IT = 4;
+        const int g3 = cdiv(npix, (long long)wpb * PIX_IT);
+        if (C <= 128) layernorm_vecg_kernel<1, PIX_IT><<<g3, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
+        else layernorm_vecg_kernel<2, PIX_IT><<<g3, wpb * 32, 0, s>>>(x, npix, C, ldx, gamma, beta, eps, y, ldy, act, y_hi, y_lo, ldp);
         count_launch();
         RCN_CHECK_LAUNCH("rcn_layernorm");
         return RCN_OK;

@@ -329,7 +329,7 @@ struct EpiRegs {
     uint32_t flags;
 };
 enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512,
-       EF_DUAL = 1024, EF_F16OUT = 2048 };
+       EF_DUAL = 1024, EF_F16OUT = 2048, EF_SQOUT = 4096 };
 __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg, bool dual) {
     EpiRegs r;
     r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
@@ -340,7 +340,7 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
     r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
     r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
               (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
-              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0) | (p.out_fmt ? EF_F16OUT : 0);
+              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0) | (p.out_fmt ? EF_F16OUT : 0) | (p.planes_square ? EF_SQOUT : 0);
     opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
     opaque(r.H); opaque(r.W); opaque(r.N); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
     opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
@@ -486,8 +486,9 @@ __device__ __forceinline__ void epilogue_tile_vec(const EpiRegs& r, int act, int
                 uint16_t hb[4], lb[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    hb[e] = to_plane(val[e], f16);
-                    lb[e] = to_plane(val[e] - from_plane(hb[e], f16), f16);
+                    const float pv = (r.flags & EF_SQOUT) ? val[e] * val[e] : val[e];
+                    hb[e] = to_plane(pv, f16);
+                    lb[e] = to_plane(pv - from_plane(hb[e], f16), f16);
                 }
                 long long po = (ip[it] + qoff) * r.cpo + ch;
                 if (r.flags & EF_S2OUT) {
@@ -640,6 +641,10 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
             // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16), converted two
             // elements per instruction (F2FP pack); the format branch is warp-uniform and sits outside the element loop
             uint32_t hp[8], lp[8];
+            if (r.flags & EF_SQOUT) {   // the consumer is a GDN norm pool: its operand is x^2 (rcn_split_bf16 with square = 1)
+#pragma unroll
+                for (int j = 0; j < 16; ++j) val[j] *= val[j];
+            }
             if (r.flags & EF_F16OUT) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {

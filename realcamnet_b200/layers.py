@@ -113,9 +113,11 @@ class GDN(nn.Module):
             self._packed = (key, ops.pack_weight(gamma, beta))
         return self._packed[1]
 
-    def _f(self, x, res=None, out=None):
+    def _f(self, x, res=None, out=None, presplit=None, emit_split=False):
+        """presplit: planes of x*x emitted by the producer of x (conv2d(..., emit_square=True)); emit_split: also write the result
+        as the next layer's operand planes -> returns (out, planes)."""
         return ops.conv2d(x, self._pack(), in_square=True, epi=EPI_IGDN if self.inverse else EPI_GDN, aux=x, res=res,
-                          out=out)
+                          out=out, presplit=presplit, emit_split=emit_split)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
@@ -135,16 +137,17 @@ class ResidualBlockWithStride(_Block):
         self.gdn = GDN(out_ch)
         self.skip = conv1x1(in_ch, out_ch, stride=stride) if (stride != 1 or in_ch != out_ch) else None
 
-    def _f(self, x, out=None, presplit=None):
-        """presplit: operand planes of x emitted by its producer for this stride (x may then be None when a skip conv exists)."""
+    def _f(self, x, out=None, presplit=None, emit_split=False):
+        """presplit: operand planes of x emitted by its producer for this stride (x may then be None when a skip conv exists).
+        emit_split: returns (out, planes of out) for the layer that reads the block's result."""
         # conv1 and the 1x1 skip read the same tensor with the same stride: one bf16 split serves both
         sp = presplit
         if sp is None and self.skip is not None:
             sp = ops.shared_split(x, [ops.pack(self.conv1), ops.pack(self.skip)], self.conv1.stride[0])
         t, tsp = self.conv1._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
-        t = self.conv2._f(t, presplit=tsp)
+        t, tsq = self.conv2._f(t, presplit=tsp, emit_split=True, emit_square=True)     # GDN's norm pool reads t*t: planes from here
         identity = x if self.skip is None else self.skip._f(x, presplit=sp)
-        return self.gdn._f(t, res=identity, out=out)
+        return self.gdn._f(t, res=identity, out=out, presplit=tsq, emit_split=emit_split)
 
 
 class ResidualBlockUpsample(_Block):
@@ -156,12 +159,13 @@ class ResidualBlockUpsample(_Block):
         self.igdn = GDN(out_ch, inverse=True)
         self.upsample = subpel_conv3x3(in_ch, out_ch, upsample)
 
-    def _f(self, x, out=None):
-        sp = ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
+    def _f(self, x, out=None, presplit=None, emit_split=False):
+        """presplit: operand planes of x from its producer; emit_split: returns (out, planes of out)."""
+        sp = presplit if presplit is not None else ops.shared_split(x, [ops.pack(self.subpel_conv[0]), ops.pack(self.upsample[0])])
         t, tsp = self.subpel_conv._f(x, act=ACT_LRELU, slope=0.01, presplit=sp, emit_split=True, keep_fp32=False)
-        t = self.conv._f(t, presplit=tsp)
-        t = self.igdn._f(t)
-        return self.upsample._f(x, res=t, out=out, presplit=sp)
+        t, tsq = self.conv._f(t, presplit=tsp, emit_split=True, emit_square=True)
+        t = self.igdn._f(t, presplit=tsq)
+        return self.upsample._f(x, res=t, out=out, presplit=sp, emit_split=emit_split)
 
 
 class ResidualBlock(_Block):

@@ -315,14 +315,15 @@ def shared_split(x, pcs, stride=1):
 
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
            cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None,
-           emit_split=False, keep_fp32=True, split_out=None, emit_stride=1):
+           emit_split=False, keep_fp32=True, split_out=None, emit_stride=1, emit_square=False):
     """One conv / linear layer with its fused epilogue.
 
     x may be None when `presplit` carries operand planes that a previous tcgen05 conv emitted (conv->conv chains never
     materialise the fp32 intermediate).  emit_split=True returns (out, SplitOperand | None): the epilogue additionally
     writes the NEXT layer's bf16 hi/lo planes; with keep_fp32=False `out` is None when that was possible.
     split_out: planes allocated by the caller (e.g. one half of a concat's planes) to emit into; implies emit_split.
-    emit_stride=2: the emitted planes use the polyphase layout of a stride-2 consumer (no rcn_split_bf16_s2 pass)."""
+    emit_stride=2: the emitted planes use the polyphase layout of a stride-2 consumer (no rcn_split_bf16_s2 pass).
+    emit_square=True: the emitted planes hold the square of the result (operand of a GDN norm pool, conv2d(..., in_square=True))."""
     if split_out is not None:
         emit_split = True
     eng = engine or _ENGINE
@@ -399,6 +400,12 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
             if tuple(sp_out.hi.shape) != want_shape or sp_out.key[7] != emit_stride:
                 raise ValueError("conv2d: split_out planes do not have the stored output geometry")
             d.planes_s2 = int(emit_stride == 2)
+            d.planes_square = int(bool(emit_square))
+            if emit_square:
+                if split_out is not None or emit_stride != 1:
+                    raise ValueError("conv2d: emit_square works on freshly allocated stride-1 planes only")
+                k_ = sp_out.key
+                sp_out = SplitOperand(sp_out.hi, sp_out.lo, k_[:8] + (True,), sp_out.fmt)
             d.out_fmt = sp_out.fmt
             d.y_hi, d.y_lo, d.Cp_out = sp_out.hi.data_ptr(), (sp_out.lo.data_ptr() if sp_out.lo is not None else None), sp_out.ld
         elif out is None:

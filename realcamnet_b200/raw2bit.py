@@ -112,13 +112,14 @@ class ConvTransBlock_mzj(nn.Module):
         self.conv_block = ResidualBlockWithCA(conv_dim, conv_dim, 8)
         self.spatial_transform = SpatialFeatureTransform(cond_channels=conv_dim, n_features=conv_dim)
 
-    def _f(self, x, cond, out=None, cond_split=None, emit_stride=0):
-        """emit_stride=2: returns (fea | None, polyphase operand planes) for a stride-2 consumer that is the only reader."""
+    def _f(self, x, cond, out=None, cond_split=None, emit_stride=0, presplit=None):
+        """emit_stride=2: returns (fea | None, polyphase operand planes) for a stride-2 consumer that is the only reader;
+        emit_stride=1: returns (fea, operand planes of fea) for the next block's conv1_1; presplit: operand planes of x."""
         cd, td = self.conv_dim, self.trans_dim
-        planes = ops.planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
+        planes = ops.bf16_planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
             ops.plane_channels(cd + td) == cd + td
         if not planes:
-            both = self.conv1_1._f(x)
+            both = self.conv1_1._f(x, presplit=presplit)
             cat = torch.empty_like(both)
             conv_identity = both[..., :cd]
             cx = self.conv_block._f(conv_identity)
@@ -127,15 +128,17 @@ class ConvTransBlock_mzj(nn.Module):
             fea = self.conv1_2._f(cat, res=x, out=out)
             return (fea, None) if emit_stride else fea
         # tcgen05 engine: see ConvTransBlock._f -- the concat read by conv1_2 only exists as operand planes
-        both, bsp = self.conv1_1._f(x, emit_split=True)
+        both, bsp = self.conv1_1._f(x, emit_split=True, presplit=presplit)
         N, H, W, _ = both.shape
         csp = ops.alloc_planes(N, H, W, cd + td, both.device)
         conv_identity = both[..., :cd]
         cx = self.conv_block._f(conv_identity, presplit=bsp.channels(0, cd))
         self.spatial_transform._f(cx, cond, extra=conv_identity, cond_split=cond_split, split_out=csp.channels(0, cd), keep_fp32=False)
         self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
-        if emit_stride:
-            return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=True, keep_fp32=False, emit_stride=emit_stride)
+        if emit_stride == 2:
+            return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=True, keep_fp32=False, emit_stride=2)
+        if emit_stride == 1:
+            return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=True)
         return self.conv1_2._f(None, res=x, out=out, presplit=csp)
 
     def forward(self, xx):
@@ -338,30 +341,43 @@ class raw_compression_tcm_final(SliceCodecModel):
         local = self.local_condition._f(raw, presplit=rsp)
         # conv_first(x) * (lsc + 1): only conv_down (stride 2) reads it -> written once, as polyphase operand planes
         fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, presplit=rsp, emit_split=True, keep_fp32=False, emit_stride=2)
-        fea = self.conv_down._f(fea, presplit=fsp)
+        # every layer below hands its result to the next one as operand planes written by its own epilogue (the fp32 map is kept
+        # only where a residual / aux operand needs it): no rcn_split_bf16 pass between the layers of a level
+        fea, gsp = self.conv_down._f(fea, presplit=fsp, emit_split=True)
         for lvl, (gfm, blocks, down) in enumerate(((self.gfm1, self.m_down1, self.m_down1_down),
                                                    (self.gfm2, self.m_down2, self.m_down2_down),
                                                    (self.gfm3, self.m_down3, self.m_down3_down))):
             for g in gfm:
-                fea = g._f(fea, vec)
+                fea, gsp = g._f(fea, vec, presplit=gsp, emit_split=True)
             csp = ops.shared_split(local[lvl], [ops.pack(blocks[0].spatial_transform.cond_scale[0]),
                                                 ops.pack(blocks[0].spatial_transform.cond_shift[0])])   # cond planes: once per level
             fsp = None
             for j, blk in enumerate(blocks):
                 if j == len(blocks) - 1:     # the level's last block feeds the stride-2 `down` layer only
-                    fea, fsp = blk._f(fea, local[lvl], cond_split=csp, emit_stride=2)
+                    fea, fsp = blk._f(fea, local[lvl], cond_split=csp, emit_stride=2, presplit=gsp)
                 else:
-                    fea = blk._f(fea, local[lvl], cond_split=csp)
-            fea = down._f(fea, presplit=fsp)
+                    fea, gsp = blk._f(fea, local[lvl], cond_split=csp, emit_stride=1, presplit=gsp)
+            if lvl < 2:
+                fea, gsp = down._f(fea, presplit=fsp, emit_split=True)
+            else:
+                fea = down._f(fea, presplit=fsp)
         return fea, lsc_fea, local
 
     def _g_s(self, y_hat, clamp=False):
         h = y_hat
         mods = list(self.g_s)
         ts = self.tail_start if self.tail_start is not None else len(mods) - 3
+        sp = None
         for i, m in enumerate(mods[:-3]):
             with self._tail_scope(i >= ts):     # experiments only (profiles/r2_precision_policy.md): a tail starting earlier
-                h = m._f(h)
+                # layer -> layer hand-over as operand planes (no split pass), except across an engine boundary and into the tail
+                chain = isinstance(m, (ConvTransBlock, ResidualBlockUpsample)) and i < ts
+                nxt_ok = chain and (i + 1 < len(mods) - 3) and (i + 1 < ts) and isinstance(mods[i + 1], (ConvTransBlock, ResidualBlockUpsample))
+                if chain:
+                    r = m._f(h, presplit=sp, emit_split=nxt_ok)
+                    h, sp = r if nxt_ok else (r, None)
+                else:
+                    h, sp = m._f(h), None
         # tail at full resolution (raw2bit.py:1680-1682): subpel -> ResidualBlock -> subpel.  The 128-channel maps are 2.1 GB
         # each: the producers write the consumers' bf16 operand planes themselves, and the ResidualBlock output (read by the
         # last conv only) never exists in fp32.

@@ -108,16 +108,18 @@ class ConvTransBlock(nn.Module):
         self.conv1_2 = Conv2d(conv_dim + trans_dim, conv_dim + trans_dim, 1, 1, 0, bias=True)
         self.conv_block = ResidualBlock(conv_dim, conv_dim)
 
-    def _f(self, x, out=None, presplit=None):
+    def _f(self, x, out=None, presplit=None, emit_split=False):
+        """presplit: operand planes of x from its producer; emit_split: returns (out, planes of out | None)."""
         cd, td = self.conv_dim, self.trans_dim
-        planes = ops.planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
+        planes = ops.bf16_planes_enabled() and ops.plane_channels(cd) == cd and ops.plane_channels(td) == td and \
             ops.plane_channels(cd + td) == cd + td
         if not planes:
             both = self.conv1_1._f(x, presplit=presplit)   # torch.split -> channel views
             cat = torch.empty_like(both)
             self.conv_block._f(both[..., :cd], out=cat[..., :cd], extra_identity=True)
             self.trans_block._f(both[..., cd:], out=cat[..., cd:])
-            return self.conv1_2._f(cat, res=x, out=out)     # x + conv1_2(cat(conv_x, trans_x))
+            y = self.conv1_2._f(cat, res=x, out=out)        # x + conv1_2(cat(conv_x, trans_x))
+            return (y, None) if emit_split else y
         # tcgen05 engine: conv1_1 also emits the planes its conv half is read through, and the concat that conv1_2 reads only
         # exists as operand planes written half by half by the two branches (no fp32 cat, no split passes)
         both, bsp = self.conv1_1._f(x, presplit=presplit, emit_split=True)
@@ -126,7 +128,7 @@ class ConvTransBlock(nn.Module):
         self.conv_block._f(both[..., :cd], extra_identity=True, presplit=bsp.channels(0, cd), split_out=csp.channels(0, cd),
                            keep_fp32=False)
         self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
-        return self.conv1_2._f(None, res=x, out=out, presplit=csp)
+        return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=emit_split)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
