@@ -191,6 +191,7 @@ struct TcParams {
     int wcw;      // accumulator columns per epilogue warp: 64, or Ntile / 2 when that keeps all 8 warps busy (Ntile = 64, 96)
     int halo;     // halo-tile kernel (3x3 stride-1 layers with 64-channel K chunks): A operand = one (16+2) x (8+2)-pixel box per chunk
     int na;       // halo kernel: number of A (halo box) buffers in the ring
+    int tps;      // halo kernel: filter taps per weight stage (9 when the nine weight tiles of a chunk fit in one stage, else 1)
     int rv;       // epilogue: row-vector (256-bit, no transposition) instead of the transposing one (VEC kernels only)
     int in_f16;   // operand planes and packed weights are fp16 (kind::f16 with f16 A/B formats) instead of bf16
     int dbg;      // RCN_TC_DEBUG bit mask (perf triage only): 1 no stores, 2 no MMA, 4 no A loads, 8 no epilogue math, 16 centre-tap A loads only
@@ -1033,19 +1034,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // Loop order is chunk-major (A box outermost), one issuing warp, one 128-column accumulator per tile (double-buffered).
 constexpr int HT_H = 16, HT_W = 8;                          // tile: 16 image rows x 8 pixels
 constexpr int HB_H = HT_H + 2, HB_W = HT_W + 2;             // halo box
-constexpr int HALO_TX = HB_H * HB_W * 128;                  // bytes one box carries (23040)
-constexpr int HALO_BYTES = (HALO_TX + 1023) & ~1023;        // 23552: box buffers stay 1024-byte aligned
+// The same construction serves the few-channel layers (K chunk bk = 16 / 32 channels: box rows of 32 / 64 bytes, 32- / 64-byte
+// swizzle): the packed-Bayer ingest convs and the condition UNet used to run 9 single-MMA pipeline stages per tile.  Where all
+// nine weight tiles of a chunk fit in one stage (small bk or few output channels) they are fetched on ONE barrier ("taps per
+// stage" = 9) and the issuer runs the chunk's 9 x bk/16 x passes MMAs back to back: 2 barrier hand-shakes per tile and chunk
+// instead of 10.
+__host__ __device__ constexpr int halo_tx(int bk) { return HB_H * HB_W * bk * 2; }                    // bytes one box carries
+__host__ __device__ constexpr int halo_bytes(int bk) { return (halo_tx(bk) + 1023) & ~1023; }         // buffers stay 1024-byte aligned
 
-__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr, uint32_t row_shift, int base_off_mode) {
-    const uint32_t start = smem_addr + row_shift * 128u;
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t smem_addr, uint32_t row_shift, int bk, int base_off_mode) {
+    const uint32_t start = smem_addr + row_shift * (uint32_t)(bk * 2);
     uint64_t d = 0;
     d |= (uint64_t)((start & 0x3FFFF) >> 4);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((uint32_t)(HB_W * 128) >> 4) << 32;     // 8-row groups are one box row (10 pixels) apart
+    d |= (uint64_t)((uint32_t)(HB_W * bk * 2) >> 4) << 32;  // 8-row groups are one box row (10 pixels) apart
     d |= (uint64_t)1 << 46;
     if (base_off_mode) d |= (uint64_t)((start >> 7) & 7u) << 49;
-    d |= (uint64_t)2 << 61;                                  // SWIZZLE_128B
+    d |= (uint64_t)(bk == 64 ? 2 : (bk == 32 ? 4 : 6)) << 61;   // SWIZZLE_128B / 64B / 32B
     return d;
+}
+
+// issue loop of the halo kernel for one (passes, k16 steps per tap) combination
+struct HaloLoopArgs {
+    uint32_t total_tiles, tiles_n, grid, first_tile;
+    int Ntile, Cout, nch, stages, na, tps, bk, skip_mma, bo_mode;
+    uint32_t abytes, bsbytes, bbytes, halo_b;
+    uint32_t a0, afull, aempty, bfull, bempty, tfull, tempty, tmem_base, idesc_fmt;
+    uint64_t bdesc0;
+};
+template <int PASSES, int KS>
+__device__ __forceinline__ void halo_issue_loop(const HaloLoopArgs& A) {
+    uint32_t ab = 0, aph = 0, st = 0, bph = 0, local = 0;
+    const int groups = 9 / A.tps;
+    for (uint32_t t = A.first_tile; t < A.total_tiles; t += A.grid, ++local) {
+        const int n0 = (int)(t % A.tiles_n) * A.Ntile;
+        int nact = A.Cout - n0;
+        if (nact > A.Ntile) nact = A.Ntile;
+        nact = (nact + 15) & ~15;
+        const uint32_t idesc = (1u << 4) | A.idesc_fmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t acb = local & 1;
+        mbar_wait_a(A.tempty + 8u * acb, ((local >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = A.tmem_base + acb * 256;
+        uint32_t acc = 0;
+        for (int c = 0; c < A.nch; ++c) {
+            mbar_wait_a(A.afull + 8u * ab, aph);
+            const uint32_t abase = A.a0 + ab * A.abytes;
+            int tap = 0;
+            for (int sg = 0; sg < groups; ++sg) {
+                mbar_wait_a(A.bfull + 8u * st, bph);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t bst = A.bdesc0 + (uint64_t)((st * A.bsbytes) >> 4);
+                    for (int tt = 0; tt < A.tps; ++tt) {
+                        const int tp = tap + tt;
+                        const uint32_t shift = (uint32_t)((tp / 3) * HB_W + (tp % 3));
+                        const uint64_t a_hi = make_halo_desc(abase, shift, A.bk, A.bo_mode);
+                        const uint64_t a_lo = make_halo_desc(abase + A.halo_b, shift, A.bk, A.bo_mode);
+                        const uint64_t b_hi = bst + (uint64_t)((tt * A.bbytes) >> 4);
+                        const uint64_t b_lo = b_hi + (uint64_t)((A.tps * A.bbytes) >> 4);
+                        if (!A.skip_mma) issue_stage<PASSES, KS>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
+                        acc = 1;
+                    }
+                    umma_commit_a(A.bempty + 8u * st);
+                }
+                __syncwarp();
+                acc = 1;
+                tap += A.tps;
+                if (++st == (uint32_t)A.stages) { st = 0; bph ^= 1; }
+            }
+            if (elect_one()) umma_commit_a(A.aempty + 8u * ab);     // the box is free once every MMA reading it has retired
+            __syncwarp();
+            if (++ab == (uint32_t)A.na) { ab = 0; aph ^= 1; }
+        }
+        if (elect_one()) umma_commit_a(A.tfull + 8u * acb);
+        __syncwarp();
+    }
 }
 
 template <int ACT, int EPI, bool VEC>
@@ -1057,7 +1121,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     const rcn_conv_desc& p = P.d;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int planes = P.passes == 3 ? 2 : 1;
-    const int abuf_bytes = planes * HALO_BYTES, bstage_bytes = planes * P.b_bytes;
+    const int BK = P.bk, TPS = P.tps;
+    const int abuf_bytes = planes * halo_bytes(BK), bstage_bytes = planes * TPS * P.b_bytes;
     uint8_t* bsm = smem + (size_t)P.na * abuf_bytes;
     uint8_t* tail = bsm + (size_t)P.stages * bstage_bytes;
     float* stg = reinterpret_cast<float*>(tail);
@@ -1069,7 +1134,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
     uint64_t* tmem_full = bempty + P.stages;   // [2]
     uint64_t* tmem_empty = tmem_full + 2;      // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-    const int chunks = P.Cp / 64;
+    const int chunks = P.Cp / BK;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < P.na; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
@@ -1108,7 +1173,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         regs_light();
         // ================= TMA producer: per tile and chunk one halo box (hi [+ lo]), then the 9 weight tiles of that chunk
         RCN_HALO_INVARIANTS;
-        const uint32_t a_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)HALO_TX, b_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)Ntile * 128u;
+        int bk = BK, tps = TPS;
+        opaque(bk); opaque(tps);
+        const uint32_t halo_b = (uint32_t)halo_bytes(bk);
+        const uint32_t a_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)halo_tx(bk);
+        const uint32_t b_tx = (uint32_t)(three ? 2 : 1) * (uint32_t)tps * (uint32_t)Ntile * (uint32_t)(bk * 2);
+        const int groups = 9 / tps;
         uint32_t ab = 0, aph = 0, st = 0, bph = 0;
         for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
             const int nt = (int)(t % tiles_n);
@@ -1122,20 +1192,25 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
                 if (elect_one()) {
                     const uint32_t fb = afull_a + 8u * ab, dst = a0 + ab * abytes;
                     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(a_tx) : "memory");
-                    tma_load_4d_a(dst, &map_a_hi, fb, c * 64, x0 - 1, y0 - 1, n);
-                    if (three) tma_load_4d_a(dst + (uint32_t)HALO_BYTES, &map_a_lo, fb, c * 64, x0 - 1, y0 - 1, n);
+                    tma_load_4d_a(dst, &map_a_hi, fb, c * bk, x0 - 1, y0 - 1, n);
+                    if (three) tma_load_4d_a(dst + halo_b, &map_a_lo, fb, c * bk, x0 - 1, y0 - 1, n);
                 }
                 __syncwarp();
                 if (++ab == (uint32_t)na) { ab = 0; aph ^= 1; }
-                for (int tap = 0; tap < 9; ++tap) {
+                int tap = 0;
+                for (int sg = 0; sg < groups; ++sg) {
                     mbar_wait_a(bempty_a + 8u * st, bph ^ 1);
                     if (elect_one()) {
                         const uint32_t fb = bfull_a + 8u * st, dst = b0 + st * bsbytes;
                         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(fb), "r"(b_tx) : "memory");
-                        tma_load_2d_a(dst, &map_w_hi, fb, tap * Cp + c * 64, n0);
-                        if (three) tma_load_2d_a(dst + bbytes, &map_w_lo, fb, tap * Cp + c * 64, n0);
+                        for (int tt = 0; tt < tps; ++tt) {       // stage layout: hi tiles of the taps, then lo tiles
+                            const int w0 = (tap + tt) * Cp + c * bk;
+                            tma_load_2d_a(dst + (uint32_t)tt * bbytes, &map_w_hi, fb, w0, n0);
+                            if (three) tma_load_2d_a(dst + (uint32_t)(tps + tt) * bbytes, &map_w_lo, fb, w0, n0);
+                        }
                     }
                     __syncwarp();
+                    tap += tps;
                     if (++st == (uint32_t)stages) { st = 0; bph ^= 1; }
                 }
             }
@@ -1144,50 +1219,26 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         regs_light();
         // ================= MMA issuer (one warp, converged, tcgen05 instructions behind elect.sync)
         RCN_HALO_INVARIANTS;
-        const uint32_t tfull_a = smem_u32(tmem_full), tempty_a = smem_u32(tmem_empty);
-        const uint32_t idesc_fmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
-        const int bo_mode = (dbg & 64) ? 1 : 0;   // triage only: 1 sets the descriptor's base-offset field (WRONG on B200, see above)
-        const uint64_t bdesc0 = make_kmajor_desc(b0, 64);
-        uint32_t ab = 0, aph = 0, st = 0, bph = 0, local = 0;
-        for (uint32_t t = blockIdx.x; t < total_tiles; t += gridDim.x, ++local) {
-            const int n0 = (int)(t % tiles_n) * Ntile;
-            int nact = Cout - n0;
-            if (nact > Ntile) nact = Ntile;
-            nact = (nact + 15) & ~15;
-            const uint32_t idesc = (1u << 4) | idesc_fmt | ((uint32_t)(nact >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-            const uint32_t acb = local & 1;
-            mbar_wait_a(tempty_a + 8u * acb, ((local >> 1) & 1) ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acb * 256;
-            uint32_t acc = 0;
-            for (int c = 0; c < nch; ++c) {
-                mbar_wait_a(afull_a + 8u * ab, aph);
-                const uint32_t abase = a0 + ab * abytes;
-                for (int tap = 0; tap < 9; ++tap) {
-                    mbar_wait_a(bfull_a + 8u * st, bph);
-                    tc_fence_after();
-                    if (elect_one()) {
-                        const uint32_t shift = (uint32_t)((tap / 3) * HB_W + (tap % 3));
-                        const uint64_t a_hi = make_halo_desc(abase, shift, bo_mode);
-                        const uint64_t a_lo = make_halo_desc(abase + (uint32_t)HALO_BYTES, shift, bo_mode);
-                        const uint64_t b_hi = bdesc0 + (uint64_t)((st * bsbytes) >> 4);
-                        const uint64_t b_lo = b_hi + (uint64_t)(bbytes >> 4);
-                        if (!(dbg & 2)) {
-                            if (three) issue_stage<3, 4>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
-                            else issue_stage<1, 4>(tmem_d, a_hi, b_hi, a_hi, b_hi, idesc, acc);
-                        }
-                        umma_commit_a(bempty_a + 8u * st);
-                    }
-                    __syncwarp();
-                    acc = 1;
-                    if (++st == (uint32_t)stages) { st = 0; bph ^= 1; }
-                }
-                if (elect_one()) umma_commit_a(aempty_a + 8u * ab);     // the box is free once every MMA reading it has retired
-                __syncwarp();
-                if (++ab == (uint32_t)na) { ab = 0; aph ^= 1; }
-            }
-            if (elect_one()) umma_commit_a(tfull_a + 8u * acb);
-            __syncwarp();
+        HaloLoopArgs A;
+        A.total_tiles = total_tiles; A.tiles_n = tiles_n; A.grid = gridDim.x; A.first_tile = blockIdx.x;
+        A.Ntile = Ntile; A.Cout = Cout; A.nch = nch; A.stages = stages; A.na = na; A.tps = TPS; A.bk = BK;
+        A.skip_mma = (dbg & 2) != 0;
+        A.bo_mode = (dbg & 64) ? 1 : 0;   // triage only: 1 sets the descriptor's base-offset field (WRONG on B200, see above)
+        A.abytes = abytes; A.bsbytes = bsbytes; A.bbytes = bbytes; A.halo_b = (uint32_t)halo_bytes(BK);
+        A.a0 = a0; A.afull = afull_a; A.aempty = aempty_a; A.bfull = bfull_a; A.bempty = bempty_a;
+        A.tfull = smem_u32(tmem_full); A.tempty = smem_u32(tmem_empty); A.tmem_base = tmem_base;
+        A.idesc_fmt = P.in_f16 ? 0u : ((1u << 7) | (1u << 10));
+        A.bdesc0 = make_kmajor_desc(b0, BK);
+        opaque(A.tps); opaque(A.bk); opaque(A.skip_mma); opaque(A.bo_mode); opaque(A.halo_b); opaque(A.idesc_fmt);
+        asm volatile("" : "+l"(A.bdesc0));
+        if (three) {
+            if (BK == 64) halo_issue_loop<3, 4>(A);
+            else if (BK == 32) halo_issue_loop<3, 2>(A);
+            else halo_issue_loop<3, 1>(A);
+        } else {
+            if (BK == 64) halo_issue_loop<1, 4>(A);
+            else if (BK == 32) halo_issue_loop<1, 2>(A);
+            else halo_issue_loop<1, 1>(A);
         }
     } else if (warp < EPI_WARP0) {
         regs_light();      // idle warps of the first warp group
@@ -1380,8 +1431,8 @@ TcKernel tc_variant_d() {
 struct TcDebugEnv {
     int dbg = 0, nmma = 0, stages = 0, halo = 1, rv = 1;
     TcDebugEnv() {
-        const char* h = getenv("RCN_TC_HALO");       // 0: keep 3x3 stride-1 layers on the tap-by-tap kernel
-        if (h) halo = atoi(h) != 0;
+        const char* h = getenv("RCN_TC_HALO");       // 0: keep 3x3 stride-1 layers on the tap-by-tap kernel; 64: halo kernel for 64-channel chunks only
+        if (h) halo = atoi(h);
         const char* rvs = getenv("RCN_TC_RV");       // 0: transposing epilogue everywhere
         if (rvs) rv = atoi(rvs) != 0;
         const char* e = getenv("RCN_TC_DEBUG");
@@ -1560,9 +1611,10 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     P.wcw = (!ps && nt >= 64 && nt % 32 == 0) ? nt / 2 : WCOLS;
     P.a_bytes = 128 * bk * 2;                          // 16 / 8 / 4 KB
     P.b_bytes = (nt * bk * 2 + 1023) & ~1023;
-    // halo-tile kernel: 3x3, stride 1, 64-channel K chunks
-    P.halo = (env.halo && d->k == 3 && d->stride == 1 && bk == 64) ? 1 : 0;
+    // halo-tile kernel: 3x3, stride 1 (RCN_TC_HALO=0: off; =64: 64-channel K chunks only)
+    P.halo = (env.halo && d->k == 3 && d->stride == 1 && (bk == 64 || env.halo != 64)) ? 1 : 0;
     P.na = 0;
+    P.tps = 1;
     const int planes_n = passes == 3 ? 2 : 1;
     int stages;
     size_t smem;
@@ -1571,13 +1623,15 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
         P.tiles_x = (P.d.W + HT_W - 1) / HT_W;
         P.tiles_y = (P.d.H + HT_H - 1) / HT_H;
         P.na = planes_n == 2 ? 2 : 3;
-        const int fixed = P.na * planes_n * HALO_BYTES + STG_BYTES + BIAS_BYTES + 1024 + 512;
-        stages = (226 * 1024 - fixed) / (planes_n * P.b_bytes);
-        if (stages > 12) stages = 12;
+        const int fixed = P.na * planes_n * halo_bytes(bk) + STG_BYTES + BIAS_BYTES + 1024 + 512;
+        const int avail = 226 * 1024 - fixed;
+        if (avail / (planes_n * 9 * P.b_bytes) >= 2) P.tps = 9;     // all nine weight tiles of a chunk behind one barrier
+        stages = avail / (planes_n * P.tps * P.b_bytes);
+        if (stages > (P.tps == 9 ? 4 : 12)) stages = (P.tps == 9 ? 4 : 12);
         RCN_CHECK_ARG(stages >= 2, "rcn_conv2d_tc: halo kernel does not fit in shared memory");
         if (env.stages && env.stages <= stages) stages = env.stages;
         P.stages = stages;
-        smem = (size_t)fixed + (size_t)stages * planes_n * P.b_bytes;
+        smem = (size_t)fixed + (size_t)stages * planes_n * P.tps * P.b_bytes;
     } else {
         const int stage_bytes = planes_n * (P.a_bytes + P.b_bytes);
         stages = (226 * 1024 - STG_BYTES - BIAS_BYTES - 1024 - 512) / stage_bytes;
