@@ -99,6 +99,9 @@ typedef struct rcn_conv_desc {
                           * is a stride-2 conv); stride-1 NHWC layers with even H, W only */
     int ps_perm;         /* rcn_conv2d_tc with RCN_STORE_PS2: w_hi/w_lo were packed with ps_perm = 1 (rows grouped by sub-pixel),
                           * which lets the pixel-shuffle store write 64 contiguous bytes per pixel like the NHWC store */
+    int aux_nchw;        /* aux is a contiguous NCHW tensor (N,Cout,Ho,Wo) instead of NHWC with pixel stride ldaux: lets an API-facing
+                          * map (the lens-shading features returned by forward(), models/raw2bit.py:1776,1853) be written once, in
+                          * the layout the caller gets, and still feed `fea * (lsc + 1)` */
     int planes_square;   /* emitted planes hold the SQUARE of the result (the next layer is a GDN norm pool, in_square) */
     int in_fmt;          /* rcn_conv2d_tc: element format RCN_PLANE_* of the INPUT planes x_hi/x_lo and of the packed weights */
     int out_fmt;         /* element format RCN_PLANE_* of the emitted planes y_hi/y_lo (what the NEXT layer's in_fmt will be) */

@@ -76,11 +76,13 @@ class Lens_Shading_Correction(nn.Module):
             Conv2d(nf, nf, 1, 1), nn.LeakyReLU(negative_slope=0.1, inplace=True),
             Conv2d(nf, out_c, 1, 1))
 
-    def _f(self, x):
+    def _f(self, x, nchw=False):
+        """nchw=True: the result is written once, as the contiguous NCHW map the API returns (`lsc` of forward()); consumers read
+        it through conv2d(aux=..., aux_nchw=True)."""
         sp = None
         for i in (0, 2, 4):   # per-pixel MLP: the hidden maps only exist as the next layer's bf16 planes
             x, sp = self.model[i]._f(x, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
-        return self.model[6]._f(x, presplit=sp)
+        return self.model[6]._f(x, presplit=sp, store=ops.STORE_NCHW if nchw else ops.STORE_NHWC)
 
     def forward(self, img_input):
         return ops.to_nchw(self._f(ops.to_nhwc(img_input)))

@@ -23,7 +23,7 @@ class ConvDesc(ctypes.Structure):
         ("res", c_void_p), ("ldres", c_int), ("res_pre", c_int),
         ("act", c_int), ("slope", c_float), ("res_scale", c_float),
         ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int), ("ldp_in", c_int), ("planes_s2", c_int), ("ps_perm", c_int),
-        ("planes_square", c_int), ("in_fmt", c_int), ("out_fmt", c_int),
+        ("aux_nchw", c_int), ("planes_square", c_int), ("in_fmt", c_int), ("out_fmt", c_int),
     ]
 
 

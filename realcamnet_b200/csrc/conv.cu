@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(256) conv2d_kernel(const rcn_conv_desc p, int 
             if (p.bias) v += p.bias[c];
             if (p.cscale) v = v * (1.f + p.cscale[ri.n * p.Cout + c]) + p.cshift[ri.n * p.Cout + c];
             if (p.epi != RCN_EPI_NONE) {
-                const float a = p.aux[m * p.ldaux + c];
+                const float a = p.aux_nchw ? p.aux[(((long long)ri.n * p.Cout + c) * Ho + ho) * Wo + wo] : p.aux[m * p.ldaux + c];
                 switch (p.epi) {
                     case RCN_EPI_GDN: v = a * rsqrtf(v); break;
                     case RCN_EPI_IGDN: v = a * sqrtf(v); break;

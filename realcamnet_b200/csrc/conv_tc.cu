@@ -330,7 +330,7 @@ struct EpiRegs {
     uint32_t flags;
 };
 enum { EF_Y = 1, EF_HI = 2, EF_LO = 4, EF_CS = 8, EF_RES = 16, EF_PS = 32, EF_NOSTORE = 64, EF_SKIP = 128, EF_PROF = 256, EF_S2OUT = 512,
-       EF_DUAL = 1024, EF_F16OUT = 2048, EF_SQOUT = 4096 };
+       EF_DUAL = 1024, EF_F16OUT = 2048, EF_SQOUT = 4096, EF_YNCHW = 8192, EF_AUXNCHW = 16384 };
 __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg, bool dual) {
     EpiRegs r;
     r.y = p.y; r.res = p.res; r.aux = p.aux; r.cscale = p.cscale; r.cshift = p.cshift;
@@ -341,7 +341,8 @@ __device__ __forceinline__ EpiRegs make_epi_regs(const rcn_conv_desc& p, int dbg
     r.rpost = (p.res && !p.res_pre) ? p.res_scale : 0.f;
     r.flags = (p.y ? EF_Y : 0) | (p.y_hi ? EF_HI : 0) | (p.y_lo ? EF_LO : 0) | (p.cscale ? EF_CS : 0) | (p.res ? EF_RES : 0) |
               (p.store == RCN_STORE_PS2 ? EF_PS : 0) | ((dbg & 1) ? EF_NOSTORE : 0) | ((dbg & 8) ? EF_SKIP : 0) |
-              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0) | (p.out_fmt ? EF_F16OUT : 0) | (p.planes_square ? EF_SQOUT : 0);
+              ((dbg & 128) ? EF_PROF : 0) | (p.planes_s2 ? EF_S2OUT : 0) | (dual ? EF_DUAL : 0) | (p.out_fmt ? EF_F16OUT : 0) | (p.planes_square ? EF_SQOUT : 0) |
+              (p.store == RCN_STORE_NCHW ? EF_YNCHW : 0) | (p.aux_nchw ? EF_AUXNCHW : 0);
     opaque_ptr(r.y); opaque_ptr(r.res); opaque_ptr(r.aux); opaque_ptr(r.cscale); opaque_ptr(r.cshift); opaque_ptr(r.y_hi); opaque_ptr(r.y_lo);
     opaque(r.H); opaque(r.W); opaque(r.N); opaque(r.Cout); opaque(r.ldy); opaque(r.ldres); opaque(r.ldaux); opaque(r.cpo);
     opaque(r.slope); opaque(r.rpre); opaque(r.rpost); opaque(r.flags);
@@ -559,9 +560,18 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
 #pragma unroll
         for (int j = 0; j < 16; ++j) pre[hh][j] = 0.f;
         if (pre_ptr && 16 * hh < wcols && ok) {
-            const float* pp = pre_ptr + (pix0 + RCN_QOFF(hh)) * pre_ld + chb + chs * hh;
-            ldg256(pp, &pre[hh][0]);
-            ldg256(pp + 8, &pre[hh][8]);
+            if (!has_res && (r.flags & EF_AUXNCHW)) {
+                // aux is an NCHW tensor (an API-facing map such as the lens-shading features): lanes are consecutive pixels of an
+                // image row, so each channel's load is 32 / 64 contiguous bytes per image row of the tile
+                const float* pp = r.aux + (((long long)n * r.Cout + cb + 16 * hh) * r.H + ho) * r.W + wo;
+                const long long cst = (long long)r.H * r.W;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) pre[hh][j] = __ldg(pp + j * cst);
+            } else {
+                const float* pp = pre_ptr + (pix0 + RCN_QOFF(hh)) * pre_ld + chb + chs * hh;
+                ldg256(pp, &pre[hh][0]);
+                ldg256(pp + 8, &pre[hh][8]);
+            }
         }
     }
     static_assert(!DUAL, "the row-vector epilogue reads one accumulator per tile");
@@ -634,9 +644,16 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
         }
         if (r.flags & EF_NOSTORE) continue;
         if (r.flags & EF_Y) {
-            float* yp = r.y + spix * r.ldy + ch;
-            stg256(yp, &val[0]);
-            stg256(yp + 8, &val[8]);
+            if (r.flags & EF_YNCHW) {      // API-facing NCHW map: 16 channel planes, each store coalesced along the image row
+                float* yp = r.y + (((long long)n * r.Cout + cb + 16 * hh) * r.H + ho) * r.W + wo;
+                const long long cst = (long long)r.H * r.W;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) yp[j * cst] = val[j];
+            } else {
+                float* yp = r.y + spix * r.ldy + ch;
+                stg256(yp, &val[0]);
+                stg256(yp + 8, &val[8]);
+            }
         }
         if (r.flags & EF_HI) {
             // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16), converted two
@@ -704,7 +721,8 @@ __device__ __forceinline__ void rows_block(const EpiRegs& r, int act, int epi, i
         float val = __uint_as_float(v[col]);
         if (sbias) val += lds1(sbias + 4u * (uint32_t)c);
         if (has_cs) val = val * (1.f + __ldg(r.cscale + n * r.Cout + c)) + __ldg(r.cshift + n * r.Cout + c);
-        if (has_aux) val = epi_ct<EPI>(val, r.aux[mpix * r.ldaux + c], epi);
+        if (has_aux)
+            val = epi_ct<EPI>(val, (r.flags & EF_AUXNCHW) ? r.aux[(((long long)n * r.Cout + c) * Ho + ho) * Wo + wo] : r.aux[mpix * r.ldaux + c], epi);
         int hh = ho, ww = wo, cc = c;
         if (ps) { cc = c >> 2; hh = 2 * ho + ((c >> 1) & 1); ww = 2 * wo + (c & 1); }
         float rv = 0.f;
@@ -1651,20 +1669,26 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     else { ma_lo = ma_hi; mw_lo = mw_hi; }
     RCN_CHECK_ARG(ok, "rcn_conv2d_tc: cuTensorMapEncodeTiled failed");
     // epilogue variant (mirrors the alignment rules of the 16-byte path)
-    const bool vec = ((d->store == RCN_STORE_NHWC && (d->Cout & 3) == 0) ||
-                      (d->store == RCN_STORE_PS2 && d->ps_perm && (d->Cout & 63) == 0 && d->epi == RCN_EPI_NONE && !d->cscale)) &&
-                     ((d->ldy & 3) == 0) && (!d->y || (reinterpret_cast<uintptr_t>(d->y) & 15) == 0) &&
-                     (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
-                     (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
-    RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
-    // row-vector epilogue: 16-column blocks and 32-byte accesses
+    // epilogue variant.  Row-vector (16-column blocks, 32-byte accesses; also serves NCHW aux reads and NCHW fp32 stores, coalesced
+    // along image rows), else the transposing 16-byte epilogue (NHWC / pixel-shuffle stores), else the generic rows path.
     auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    const bool nchw_io = d->aux_nchw || d->store == RCN_STORE_NCHW;
     const int cs_store = (d->store == RCN_STORE_PS2) ? d->Cout / 4 : d->Cout;
-    P.rv = (vec && env.rv && P.nmma == 1 && (d->Cout % 16) == 0 && (cs_store % 16) == 0 && (!d->y || ((d->ldy & 7) == 0 && al32(d->y))) &&
-            (!d->res || ((d->ldres & 7) == 0 && al32(d->res))) && (d->epi == RCN_EPI_NONE || ((d->ldaux & 7) == 0 && al32(d->aux))) &&
-            (!d->y_hi || ((d->Cp_out & 15) == 0 && al32(d->y_hi) && (!d->y_lo || al32(d->y_lo)))) &&
-            (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0))
-               ? 1 : 0;
+    const bool store_ok = d->store == RCN_STORE_NHWC || (d->store == RCN_STORE_NCHW && !d->res && !d->y_hi) ||
+                          (d->store == RCN_STORE_PS2 && d->ps_perm && (d->Cout & 63) == 0 && d->epi == RCN_EPI_NONE && !d->cscale);
+    const bool rv_ok = env.rv && P.nmma == 1 && store_ok && (d->Cout % 16) == 0 && (cs_store % 16) == 0 &&
+                       (!d->y || d->store == RCN_STORE_NCHW || ((d->ldy & 7) == 0 && al32(d->y))) &&
+                       (!d->res || ((d->ldres & 7) == 0 && al32(d->res))) &&
+                       (d->epi == RCN_EPI_NONE || d->aux_nchw || ((d->ldaux & 7) == 0 && al32(d->aux))) &&
+                       (!d->y_hi || ((d->Cp_out & 15) == 0 && al32(d->y_hi) && (!d->y_lo || al32(d->y_lo)))) &&
+                       (!d->bias || (reinterpret_cast<uintptr_t>(d->bias) & 15) == 0);
+    const bool vec16_ok = !nchw_io && store_ok && (d->store != RCN_STORE_NHWC || (d->Cout & 3) == 0) && ((d->ldy & 3) == 0) &&
+                          (!d->y || (reinterpret_cast<uintptr_t>(d->y) & 15) == 0) &&
+                          (!d->res || (((d->ldres & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->res) & 15) == 0))) &&
+                          (d->epi == RCN_EPI_NONE || (((d->ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(d->aux) & 15) == 0)));
+    const bool vec = rv_ok || vec16_ok;
+    P.rv = rv_ok ? 1 : 0;
+    RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
     const TcKernel kern = select_kernel(d->act, d->epi, vec, P.halo ? 2 : (P.nmma == 2 ? 1 : 0));
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;

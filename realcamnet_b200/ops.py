@@ -273,6 +273,11 @@ def alloc_planes(N, H, W, C, device, passes=None, stride=1, fmt=None) -> SplitOp
     return SplitOperand(hi, lo, (None, N, H, W, C, None, C, stride, False), fmt)
 
 
+def sp_align32(cs: int) -> bool:
+    """plane pixel strides of freshly allocated planes are the channel count: the row-vector epilogue wants multiples of 16"""
+    return cs % 16 == 0
+
+
 def planes_enabled() -> bool:
     return _ENGINE != "fp32"
 
@@ -315,7 +320,7 @@ def shared_split(x, pcs, stride=1):
 
 def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store=STORE_NHWC, epi=EPI_NONE, aux=None,
            cscale=None, cshift=None, res=None, res_pre=False, in_square=False, bias=True, res_scale=1.0, engine=None, presplit=None,
-           emit_split=False, keep_fp32=True, split_out=None, emit_stride=1, emit_square=False):
+           emit_split=False, keep_fp32=True, split_out=None, emit_stride=1, emit_square=False, aux_nchw=False):
     """One conv / linear layer with its fused epilogue.
 
     x may be None when `presplit` carries operand planes that a previous tcgen05 conv emitted (conv->conv chains never
@@ -376,10 +381,16 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     d.epi = epi
     lda = ldr = 0
     if epi != EPI_NONE:
-        aN, aH, aW, aC, lda = geom(aux, "conv2d.aux")
-        if (aN, aH, aW, aC) != (N, Ho, Wo, pc.cout):
-            raise ValueError("conv2d: aux must have the conv output geometry")
-        d.aux, d.ldaux = aux.data_ptr(), lda
+        if aux_nchw:     # a contiguous NCHW map (N,Cout,Ho,Wo), e.g. an API-facing tensor written by conv2d(store=STORE_NCHW)
+            _chk(aux, "conv2d.aux")
+            if tuple(aux.shape) != (N, pc.cout, Ho, Wo) or not aux.is_contiguous():
+                raise ValueError("conv2d: an NCHW aux must be contiguous with the conv output geometry")
+            d.aux, d.ldaux, d.aux_nchw = aux.data_ptr(), 0, 1
+        else:
+            aN, aH, aW, aC, lda = geom(aux, "conv2d.aux")
+            if (aN, aH, aW, aC) != (N, Ho, Wo, pc.cout):
+                raise ValueError("conv2d: aux must have the conv output geometry")
+            d.aux, d.ldaux = aux.data_ptr(), lda
     if cscale is not None:
         _chk(cscale), _chk(cshift)
         assert cscale.is_contiguous() and cshift.is_contiguous() and cscale.numel() == N * pc.cout == cshift.numel()
@@ -394,6 +405,8 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     if can_emit:   # alignment requirements of the 16-byte epilogue path
         ok = (ldy % 4 == 0 and (out is None or out.data_ptr() % 16 == 0) and lda % 4 == 0 and ldr % 4 == 0 and
               (aux is None or aux.data_ptr() % 16 == 0) and (res is None or res.data_ptr() % 16 == 0))
+        if aux_nchw:         # served by the row-vector epilogue only (32-byte rules)
+            ok = ok and pc.cout % 16 == 0 and (out is None or (ldy % 8 == 0 and out.data_ptr() % 32 == 0)) and sp_align32(Cs)
         if ok:
             sp_out = split_out if split_out is not None else alloc_planes(N, Hs, Ws, Cs, dev, stride=emit_stride)
             want_shape = (N, Hs, Ws, Cs) if emit_stride == 1 else (4 * N, Hs // 2, Ws // 2, Cs)

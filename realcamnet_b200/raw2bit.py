@@ -336,11 +336,12 @@ class raw_compression_tcm_final(SliceCodecModel):
         """models/raw2bit.py:1771-1796 (and 1877-1901 in compress)."""
         raw, cond, coord = ops.to_nhwc(x[0]), ops.to_nhwc(x[1]), ops.to_nhwc(x[2])
         vec = self.classifier._f(cond)                                  # (B,1,1,128) gfm_vector
-        lsc_fea = self.lsc._f(coord)
+        lsc_fea = self.lsc._f(coord, nchw=True)                         # NCHW: it is an output of forward() (raw2bit.py:1853)
         rsp = ops.shared_split(raw, [ops.pack(self.conv_first), ops.pack(self.local_condition.in_conv.conv)])   # both read raw
         local = self.local_condition._f(raw, presplit=rsp)
         # conv_first(x) * (lsc + 1): only conv_down (stride 2) reads it -> written once, as polyphase operand planes
-        fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, presplit=rsp, emit_split=True, keep_fp32=False, emit_stride=2)
+        fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, aux_nchw=True, presplit=rsp, emit_split=True, keep_fp32=False,
+                                      emit_stride=2)
         # every layer below hands its result to the next one as operand planes written by its own epilogue (the fp32 map is kept
         # only where a residual / aux operand needs it): no rcn_split_bf16 pass between the layers of a level
         fea, gsp = self.conv_down._f(fea, presplit=fsp, emit_split=True)
@@ -403,7 +404,7 @@ class raw_compression_tcm_final(SliceCodecModel):
             # the coder front end (CDF lookups) ran inside the Gaussian kernel of stage a; its D2H copy is started between the
             # stages so the host state chain runs WHILE the synthesis transform g_s (half of the FLOPs) executes
             y_nchw = ops.to_nchw(E.y)
-            return {"x_hat": self._g_s(E.ms[..., 320:]), "y": y_nchw, "lft": ops.to_nchw(E.lft), "lsc": ops.to_nchw(E.lsc_fea),
+            return {"x_hat": self._g_s(E.ms[..., 320:]), "y": y_nchw, "lft": ops.to_nchw(E.lft), "lsc": E.lsc_fea,
                     "likelihoods": {"y": ops.to_nchw(E.y_lik), "z": ops.to_nchw(E.z_lik)},
                     "para": {"means": ops.to_nchw(E.means), "scales": ops.to_nchw(E.scales), "y": y_nchw}}
 

@@ -166,6 +166,16 @@ def test_conv2d_epilogues_and_views(dev, engine):
     conv = F.conv2d(x, w, b, padding=1)
     chk = lambda y, r: rel(ops.to_nchw(y), r) < CONV_TOL
     assert chk(ops.conv2d(xn, pc, epi=ops.EPI_MUL_AUXP1, aux=an), conv * (aux + 1))
+    # aux given as the contiguous NCHW map an API-facing producer wrote (store=STORE_NCHW): same result, also with plane emission
+    # (stride-1 and polyphase) -- the `conv_first(x) * (lsc + 1)` ingest of the RAW model
+    aux_dev = aux.to(dev).contiguous()
+    assert chk(ops.conv2d(xn, pc, epi=ops.EPI_MUL_AUXP1, aux=aux_dev, aux_nchw=True), conv * (aux + 1))
+    if ops.planes_enabled():
+        yv, spv = ops.conv2d(xn, pc, epi=ops.EPI_MUL_AUXP1, aux=aux_dev, aux_nchw=True, emit_split=True)
+        assert chk(yv, conv * (aux + 1)) and spv is not None
+        assert rel(spv.hi.float() + spv.lo.float(), yv) < 1e-5
+    # NCHW store of a 32-channel result straight from the row-vector epilogue
+    assert rel(ops.conv2d(xn, pc, store=ops.STORE_NCHW, act=ops.ACT_LRELU, slope=0.1), F.leaky_relu(conv, 0.1)) < CONV_TOL
     assert chk(ops.conv2d(xn, pc, epi=ops.EPI_MULP1_AUX, aux=an, res=rn), (conv + 1) * aux + res)
     assert chk(ops.conv2d(xn, pc, epi=ops.EPI_SIGMOID_GATE, aux=an, res=rn), aux * torch.sigmoid(conv) + res)
     assert chk(ops.conv2d(xn, pc, res=rn, res_pre=True, act=ops.ACT_RELU), F.relu(conv + res))
