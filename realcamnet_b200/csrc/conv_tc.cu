@@ -536,7 +536,12 @@ __device__ __forceinline__ void stg256u(void* p, const uint32_t* v) {
 // consecutive shuffled channels of OUTPUT pixel (2y + (hh >> 1), 2x + (hh & 1)).
 // Requirements (host-checked, else the transposing epilogue runs): Cout % 16 == 0, pixel strides % 8 == 0 (fp32) / % 16 == 0
 // (planes), 32-byte aligned bases.
-template <int ACT, int EPI, bool DUAL, int TW>
+// FEAT: compile-time mask of the RARE options (bit 0 NCHW aux / NCHW store, bit 1 squared planes, bit 2 polyphase planes, bit 3
+// Res_GFM scale / shift).  They occur in ~15 of the ~1000 launches of a step, but with their code inlined behind run-time flags
+// the common layers paid for them: measured on one box, 1x1 128 -> 128 0.949 ms with all four compiled in vs 0.785 ms without,
+// GELU 64 -> 256 0.604 vs 0.487 ms (the epilogue is bound by instruction issue / fetch).  Kernels are instantiated lean (FEAT = 0)
+// and, for the few (activation, combinator) pairs that need them, full.
+template <int ACT, int EPI, bool DUAL, int TW, int FEAT>
 __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int epi, uint32_t sbias, uint32_t taddr, uint64_t* full_bar,
                                                  uint32_t parity, uint64_t* empty_bar, int n, int x0, int y0, int cb, int wcols, int q,
                                                  int lane) {
@@ -560,7 +565,7 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
 #pragma unroll
         for (int j = 0; j < 16; ++j) pre[hh][j] = 0.f;
         if (pre_ptr && 16 * hh < wcols && ok) {
-            if (!has_res && (r.flags & EF_AUXNCHW)) {
+            if ((FEAT & 1) && !has_res && (r.flags & EF_AUXNCHW)) {
                 // aux is an NCHW tensor (an API-facing map such as the lens-shading features): lanes are consecutive pixels of an
                 // image row, so each channel's load is 32 / 64 contiguous bytes per image row of the tile
                 const float* pp = r.aux + (((long long)n * r.Cout + cb + 16 * hh) * r.H + ho) * r.W + wo;
@@ -628,7 +633,7 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
         // this buffer's registers are consumed: request block hh + 2 into it; after the last request the accumulator is free
         if (16 * (hh + 2) < wcols) tmem_ld16_async(taddr + 16 * (hh + 2), v);
         if (!ok) continue;
-        if (r.flags & EF_CS) {
+        if ((FEAT & 8) && (r.flags & EF_CS)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j)
                 val[j] = fmaf(val[j], 1.f + __ldg(r.cscale + n * r.Cout + c0 + ce * j), __ldg(r.cshift + n * r.Cout + c0 + ce * j));
@@ -644,7 +649,7 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
         }
         if (r.flags & EF_NOSTORE) continue;
         if (r.flags & EF_Y) {
-            if (r.flags & EF_YNCHW) {      // API-facing NCHW map: 16 channel planes, each store coalesced along the image row
+            if ((FEAT & 1) && (r.flags & EF_YNCHW)) {      // API-facing NCHW map: 16 channel planes, each store coalesced along the image row
                 float* yp = r.y + (((long long)n * r.Cout + cb + 16 * hh) * r.H + ho) * r.W + wo;
                 const long long cst = (long long)r.H * r.W;
 #pragma unroll
@@ -659,7 +664,7 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
             // the consumer's tcgen05 operand planes: x = hi + lo in bf16 / fp16 (same rounding as rcn_split_bf16), converted two
             // elements per instruction (F2FP pack); the format branch is warp-uniform and sits outside the element loop
             uint32_t hp[8], lp[8];
-            if (r.flags & EF_SQOUT) {   // the consumer is a GDN norm pool: its operand is x^2 (rcn_split_bf16 with square = 1)
+            if ((FEAT & 2) && (r.flags & EF_SQOUT)) {   // the consumer is a GDN norm pool: its operand is x^2 (rcn_split_bf16 with square = 1)
 #pragma unroll
                 for (int j = 0; j < 16; ++j) val[j] *= val[j];
             }
@@ -688,7 +693,7 @@ __device__ __forceinline__ void epilogue_tile_rv(const EpiRegs& r, int act, int 
                 }
             }
             long long po = spix * r.cpo + ch;
-            if (r.flags & EF_S2OUT) {
+            if ((FEAT & 4) && (r.flags & EF_S2OUT)) {
                 // polyphase layout of a stride-2 consumer: pixel (h, w) -> plane (h&1)*2 + (w&1), position (h>>1, w>>1)
                 const long long plane = (long long)(((ho & 1) * 2 + (wo & 1)) * r.N + n);
                 po = ((plane * (r.H >> 1) + (ho >> 1)) * (r.W >> 1) + (wo >> 1)) * r.cpo + ch;
@@ -834,7 +839,7 @@ __device__ __forceinline__ void mma_issue_loop(const MmaLoopArgs& A) {
 #else
 #define RCN_TC_BOUNDS __launch_bounds__(TC_THREADS, 1)
 #endif
-template <int ACT, int EPI, bool VEC, bool DUAL>
+template <int ACT, int EPI, bool VEC, bool DUAL, int FEAT>
 __global__ void RCN_TC_BOUNDS
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
@@ -1013,7 +1018,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                 bool done = false;
                 if constexpr (!DUAL) {
                     if (rvflag) {
-                        epilogue_tile_rv<ACT, EPI, false, TILE_W>(er, act, epi, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0,
+                        epilogue_tile_rv<ACT, EPI, false, TILE_W, FEAT>(er, act, epi, sbias, taddr, &tmem_full[ab], (local >> 1) & 1, &tmem_empty[ab], n, x0,
                                                                   y0, n0 + wcw * jsub, wcols, q, lane);
                         done = true;
                     }
@@ -1080,10 +1085,14 @@ struct HaloLoopArgs {
     uint32_t a0, afull, aempty, bfull, bempty, tfull, tempty, tmem_base, idesc_fmt;
     uint64_t bdesc0;
 };
-template <int PASSES, int KS>
+// TPS (taps per weight stage) and the chunk width are compile-time: with them at run time the descriptor arithmetic of every tap
+// (tap / 3, tap % 3, shifts by the chunk width, the swizzle mode) sat in the single issuing thread's way -- the fp16 x1 tail conv
+// (4 MMAs per stage) went from 1.106 to 1.27 ms.
+template <int PASSES, int KS, int TPS>
 __device__ __forceinline__ void halo_issue_loop(const HaloLoopArgs& A) {
+    constexpr int BKC = KS * 16;
+    constexpr int groups = 9 / TPS;
     uint32_t ab = 0, aph = 0, st = 0, bph = 0, local = 0;
-    const int groups = 9 / A.tps;
     for (uint32_t t = A.first_tile; t < A.total_tiles; t += A.grid, ++local) {
         const int n0 = (int)(t % A.tiles_n) * A.Ntile;
         int nact = A.Cout - n0;
@@ -1098,19 +1107,28 @@ __device__ __forceinline__ void halo_issue_loop(const HaloLoopArgs& A) {
         for (int c = 0; c < A.nch; ++c) {
             mbar_wait_a(A.afull + 8u * ab, aph);
             const uint32_t abase = A.a0 + ab * A.abytes;
-            int tap = 0;
+            // descriptors of tap 0; a tap moves the A start address by a compile-time number of 16-byte units (no carry out of the
+            // 14-bit field: shared memory is < 256 KB)
+            const uint64_t a_hi0 = make_halo_desc(abase, 0, BKC, A.bo_mode);
+            const uint64_t a_lo0 = make_halo_desc(abase + A.halo_b, 0, BKC, A.bo_mode);
+#pragma unroll
             for (int sg = 0; sg < groups; ++sg) {
                 mbar_wait_a(A.bfull + 8u * st, bph);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bst = A.bdesc0 + (uint64_t)((st * A.bsbytes) >> 4);
-                    for (int tt = 0; tt < A.tps; ++tt) {
-                        const int tp = tap + tt;
-                        const uint32_t shift = (uint32_t)((tp / 3) * HB_W + (tp % 3));
-                        const uint64_t a_hi = make_halo_desc(abase, shift, A.bk, A.bo_mode);
-                        const uint64_t a_lo = make_halo_desc(abase + A.halo_b, shift, A.bk, A.bo_mode);
+#pragma unroll
+                    for (int tt = 0; tt < TPS; ++tt) {
+                        constexpr int unit = BKC * 2 / 16;                 // 16-byte units per box pixel
+                        const int tp = sg * TPS + tt;
+                        const uint32_t shift = (uint32_t)(((tp / 3) * HB_W + (tp % 3)) * unit);
+                        uint64_t a_hi = a_hi0 + shift, a_lo = a_lo0 + shift;
+                        if (A.bo_mode) {                                   // triage only
+                            a_hi = make_halo_desc(abase, (tp / 3) * HB_W + (tp % 3), BKC, 1);
+                            a_lo = make_halo_desc(abase + A.halo_b, (tp / 3) * HB_W + (tp % 3), BKC, 1);
+                        }
                         const uint64_t b_hi = bst + (uint64_t)((tt * A.bbytes) >> 4);
-                        const uint64_t b_lo = b_hi + (uint64_t)((A.tps * A.bbytes) >> 4);
+                        const uint64_t b_lo = b_hi + (uint64_t)((TPS * A.bbytes) >> 4);
                         if (!A.skip_mma) issue_stage<PASSES, KS>(tmem_d, a_hi, b_hi, a_lo, b_lo, idesc, acc);
                         acc = 1;
                     }
@@ -1118,7 +1136,6 @@ __device__ __forceinline__ void halo_issue_loop(const HaloLoopArgs& A) {
                 }
                 __syncwarp();
                 acc = 1;
-                tap += A.tps;
                 if (++st == (uint32_t)A.stages) { st = 0; bph ^= 1; }
             }
             if (elect_one()) umma_commit_a(A.aempty + 8u * ab);     // the box is free once every MMA reading it has retired
@@ -1130,7 +1147,7 @@ __device__ __forceinline__ void halo_issue_loop(const HaloLoopArgs& A) {
     }
 }
 
-template <int ACT, int EPI, bool VEC>
+template <int ACT, int EPI, bool VEC, int FEAT>
 __global__ void RCN_TC_BOUNDS
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                     const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo, const TcParams P) {
@@ -1249,14 +1266,24 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
         A.bdesc0 = make_kmajor_desc(b0, BK);
         opaque(A.tps); opaque(A.bk); opaque(A.skip_mma); opaque(A.bo_mode); opaque(A.halo_b); opaque(A.idesc_fmt);
         asm volatile("" : "+l"(A.bdesc0));
-        if (three) {
-            if (BK == 64) halo_issue_loop<3, 4>(A);
-            else if (BK == 32) halo_issue_loop<3, 2>(A);
-            else halo_issue_loop<3, 1>(A);
+        if (TPS == 9) {
+            if (three) {
+                if (BK == 64) halo_issue_loop<3, 4, 9>(A);
+                else if (BK == 32) halo_issue_loop<3, 2, 9>(A);
+                else halo_issue_loop<3, 1, 9>(A);
+            } else {
+                if (BK == 64) halo_issue_loop<1, 4, 9>(A);
+                else if (BK == 32) halo_issue_loop<1, 2, 9>(A);
+                else halo_issue_loop<1, 1, 9>(A);
+            }
+        } else if (three) {
+            if (BK == 64) halo_issue_loop<3, 4, 1>(A);
+            else if (BK == 32) halo_issue_loop<3, 2, 1>(A);
+            else halo_issue_loop<3, 1, 1>(A);
         } else {
-            if (BK == 64) halo_issue_loop<1, 4>(A);
-            else if (BK == 32) halo_issue_loop<1, 2>(A);
-            else halo_issue_loop<1, 1>(A);
+            if (BK == 64) halo_issue_loop<1, 4, 1>(A);
+            else if (BK == 32) halo_issue_loop<1, 2, 1>(A);
+            else halo_issue_loop<1, 1, 1>(A);
         }
     } else if (warp < EPI_WARP0) {
         regs_light();      // idle warps of the first warp group
@@ -1288,7 +1315,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_c
             const uint32_t taddr = tmem_base + acb * 256 + ((uint32_t)(q * 32) << 16) + (uint32_t)(wcw * jsub);
             if constexpr (VEC) {
                 if (rvflag)
-                    epilogue_tile_rv<ACT, EPI, false, HT_W>(er, act, epi, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb], n,
+                    epilogue_tile_rv<ACT, EPI, false, HT_W, FEAT>(er, act, epi, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb], n,
                                                             x0, y0, n0 + wcw * jsub, wcols, q, lane);
                 else
                     epilogue_tile_vec<ACT, EPI, false, HT_W>(er, act, epi, slab, sbias, taddr, &tmem_full[acb], (local >> 1) & 1, &tmem_empty[acb], n,
@@ -1433,10 +1460,10 @@ inline int current_device() {
     return (dev >= 0 && dev < MAX_DEVICES) ? dev : 0;
 }
 
-template <int ACT, int EPI, bool VEC, bool DUAL>
+template <int ACT, int EPI, bool VEC, bool DUAL, int FEAT>
 TcKernel tc_variant_d() {
     static bool attr_set[MAX_DEVICES] = {};   // function attributes are per device: once per (instantiation, device)
-    TcKernel k = conv_tc_kernel<ACT, EPI, VEC, DUAL>;
+    TcKernel k = conv_tc_kernel<ACT, EPI, VEC, DUAL, FEAT>;
     const int dev = current_device();
     if (!attr_set[dev]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1477,10 +1504,10 @@ int sm_count() {
     return sms[dev];
 }
 
-template <int ACT, int EPI, bool VEC>
+template <int ACT, int EPI, bool VEC, int FEAT>
 TcKernel tc_variant_h() {
     static bool attr_set[MAX_DEVICES] = {};
-    TcKernel k = conv_tc_halo_kernel<ACT, EPI, VEC>;
+    TcKernel k = conv_tc_halo_kernel<ACT, EPI, VEC, FEAT>;
     const int dev = current_device();
     if (!attr_set[dev]) {
         cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -1489,43 +1516,62 @@ TcKernel tc_variant_h() {
     return k;
 }
 
-// mode: 0 = tap-by-tap kernel, one issuing warp; 1 = tap-by-tap, two issuing warps; 2 = halo-tile kernel
-template <int ACT, int EPI, bool VEC>
+// mode: 0 = tap-by-tap kernel, one issuing warp; 1 = tap-by-tap, two issuing warps (triage); 2 = halo-tile kernel
+template <int ACT, int EPI, bool VEC, int FEAT>
 TcKernel tc_variant(int mode) {
-    if (mode == 2) return tc_variant_h<ACT, EPI, VEC>();
-    return mode == 1 ? tc_variant_d<ACT, EPI, VEC, true>() : tc_variant_d<ACT, EPI, VEC, false>();
+    if (mode == 2) return tc_variant_h<ACT, EPI, VEC, FEAT>();
+    if constexpr (FEAT == 0) {
+        if (mode == 1) return tc_variant_d<ACT, EPI, VEC, true, 0>();
+    }
+    return tc_variant_d<ACT, EPI, VEC, false, FEAT>();
 }
 
-// (act, epi, 16-byte path?, two MMA warps?) -> instantiation; combinations the path never uses share the generic (-1, -1) variant
-TcKernel select_kernel(int act, int epi, bool vec, int dual) {
+constexpr int FEAT_ALL = 0xF;
+
+// (act, epi, 16-byte path?, kernel mode, rare epilogue options needed?) -> instantiation; combinations the path never uses share the
+// generic (-1, -1) variant
+TcKernel select_kernel(int act, int epi, bool vec, int mode, bool full) {
+    if (vec && full) {
+        // the (activation, combinator) pairs that occur with NCHW aux / store, squared planes, polyphase planes or Res_GFM modulation
+        if (epi == RCN_EPI_NONE) {
+            switch (act) {
+                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true, FEAT_ALL>(mode);
+                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true, FEAT_ALL>(mode);
+                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true, FEAT_ALL>(mode);
+                default: break;
+            }
+        }
+        if (act == RCN_ACT_NONE && epi == RCN_EPI_MUL_AUXP1) return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true, FEAT_ALL>(mode);
+        return tc_variant<-1, -1, true, FEAT_ALL>(mode);
+    }
     if (vec) {
         if (epi == RCN_EPI_NONE) {
             switch (act) {
-                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true>(dual);
-                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true>(dual);
-                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true>(dual);
-                case RCN_ACT_GELU: return tc_variant<RCN_ACT_GELU, 0, true>(dual);
-                case RCN_ACT_SIGMOID: return tc_variant<RCN_ACT_SIGMOID, 0, true>(dual);
-                case RCN_ACT_HALF_TANH: return tc_variant<RCN_ACT_HALF_TANH, 0, true>(dual);
-                case RCN_ACT_HSWISH: return tc_variant<RCN_ACT_HSWISH, 0, true>(dual);
-                default: return tc_variant<-1, -1, true>(dual);
+                case RCN_ACT_NONE: return tc_variant<RCN_ACT_NONE, 0, true, 0>(mode);
+                case RCN_ACT_RELU: return tc_variant<RCN_ACT_RELU, 0, true, 0>(mode);
+                case RCN_ACT_LRELU: return tc_variant<RCN_ACT_LRELU, 0, true, 0>(mode);
+                case RCN_ACT_GELU: return tc_variant<RCN_ACT_GELU, 0, true, 0>(mode);
+                case RCN_ACT_SIGMOID: return tc_variant<RCN_ACT_SIGMOID, 0, true, 0>(mode);
+                case RCN_ACT_HALF_TANH: return tc_variant<RCN_ACT_HALF_TANH, 0, true, 0>(mode);
+                case RCN_ACT_HSWISH: return tc_variant<RCN_ACT_HSWISH, 0, true, 0>(mode);
+                default: return tc_variant<-1, -1, true, 0>(mode);
             }
         }
         if (act == RCN_ACT_NONE) {
             switch (epi) {
-                case RCN_EPI_GDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_GDN, true>(dual);
-                case RCN_EPI_IGDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_IGDN, true>(dual);
-                case RCN_EPI_MUL_AUXP1: return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true>(dual);
-                case RCN_EPI_MULP1_AUX: return tc_variant<RCN_ACT_NONE, RCN_EPI_MULP1_AUX, true>(dual);
-                case RCN_EPI_SIGMOID_GATE: return tc_variant<RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE, true>(dual);
+                case RCN_EPI_GDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_GDN, true, 0>(mode);
+                case RCN_EPI_IGDN: return tc_variant<RCN_ACT_NONE, RCN_EPI_IGDN, true, 0>(mode);
+                case RCN_EPI_MUL_AUXP1: return tc_variant<RCN_ACT_NONE, RCN_EPI_MUL_AUXP1, true, 0>(mode);
+                case RCN_EPI_MULP1_AUX: return tc_variant<RCN_ACT_NONE, RCN_EPI_MULP1_AUX, true, 0>(mode);
+                case RCN_EPI_SIGMOID_GATE: return tc_variant<RCN_ACT_NONE, RCN_EPI_SIGMOID_GATE, true, 0>(mode);
                 default: break;
             }
         }
-        return tc_variant<-1, -1, true>(dual);
+        return tc_variant<-1, -1, true, 0>(mode);
     }
-    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) return tc_variant<RCN_ACT_NONE, 0, false>(dual);
-    if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) return tc_variant<RCN_ACT_CLAMP01, 0, false>(dual);
-    return tc_variant<-1, -1, false>(dual);
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_NONE) return tc_variant<RCN_ACT_NONE, 0, false, 0>(mode);
+    if (epi == RCN_EPI_NONE && act == RCN_ACT_CLAMP01) return tc_variant<RCN_ACT_CLAMP01, 0, false, 0>(mode);
+    return tc_variant<-1, -1, false, 0>(mode);
 }
 
 }  // namespace
@@ -1689,7 +1735,9 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
     const bool vec = rv_ok || vec16_ok;
     P.rv = rv_ok ? 1 : 0;
     RCN_CHECK_ARG(vec || (d->y && !d->y_hi), "rcn_conv2d_tc: this store / alignment combination cannot emit operand planes (y_hi) and needs y");
-    const TcKernel kern = select_kernel(d->act, d->epi, vec, P.halo ? 2 : (P.nmma == 2 ? 1 : 0));
+    // rare epilogue options -> the full instantiation; they are served by the row-vector epilogue only
+    const bool full = d->cscale || d->planes_s2 || d->planes_square || nchw_io;
+    const TcKernel kern = select_kernel(d->act, d->epi, vec, P.halo ? 2 : (P.nmma == 2 ? 1 : 0), full);
     P.tiles_n = (d->Cout + nt - 1) / nt;
     P.total_tiles = (long long)P.tiles_x * P.tiles_y * d->N * P.tiles_n;
     RCN_CHECK_ARG(P.total_tiles < (1ll << 31), "rcn_conv2d_tc: too many tiles");
