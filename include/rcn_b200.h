@@ -257,6 +257,35 @@ int rcn_split_bf16_s2(const float* x, int ldx, int N, int H, int W, int C, int C
  * 64g + 16s + c holds conv channel 64g + 4c + s, i.e. the four PixelShuffle(2) sub-pixels s of 16 shuffled channels c. */
 int rcn_pack_conv_weight_tc(const float* w_oihw, int Cout, int Cin, int k, int Cp, int ps_perm, int fmt, void* hi, void* lo, void* stream);
 
+/* ---- fused packed-Bayer ingest ------------------------------------------------------------------------- */
+/* models/raw2bit.py:1771-1780 with models/LiteISP.py:363-378 as ONE kernel (csrc/ingest.cu):
+ *   lsc = Lens_Shading_Correction(coord)   4-layer per-pixel MLP 2 -> 128 -> 128 -> 128 -> 128, LeakyReLU(slope) between layers
+ *   fea = conv_first(raw) * (lsc + 1)      3x3, 4 -> 128, padding 1   (optional: raw == NULL computes lsc only)
+ * Hidden maps never leave the SM (activations are the tcgen05 A operand in tensor memory); lsc is written once as the
+ * contiguous NCHW map forward() returns (raw2bit.py:1853) and fea once, as the bf16 hi/lo operand planes of its consumer
+ * conv_down (planes_s2 != 0: polyphase layout of rcn_split_bf16_s2; else (N,H,W,128)).  bf16x3 arithmetic.
+ * Requirements: 128-wide layers, even H, W % 64 == 0 (the codec's tiles are multiples of 64). */
+typedef struct rcn_ingest_desc {
+    const float* coord;            /* 2 channels; element (n, y, x, c) at coord[n*coord_bs + (y*W + x)*coord_ps + c*coord_cs] */
+    long long coord_bs; int coord_ps, coord_cs;
+    const float* w0; const float* b0;                 /* layer 0: nn.Conv2d(2, 128, 1) weight [128][2] and bias */
+    const void* w1_hi; const void* w1_lo;             /* layers 1-3: [128][128] bf16 hi/lo from rcn_pack_conv_weight_tc (Cp = 128) */
+    const void* w2_hi; const void* w2_lo;
+    const void* w3_hi; const void* w3_lo;
+    const float* b1; const float* b2; const float* b3;
+    float slope;
+    float* lsc;                    /* out: (N,128,H,W) fp32, contiguous */
+    int N, H, W;
+    const float* raw; int ldraw;   /* NHWC packed-Bayer tile (N,H,W,4), pixel stride ldraw floats; NULL: lens-shading map only */
+    const void* wc_hi; const void* wc_lo;             /* conv_first: [128][48] bf16 hi/lo from rcn_pack_ingest_weight */
+    const float* bc;
+    void* fea_hi; void* fea_lo;    /* out: bf16 operand planes of fea, pixel stride 128 */
+    int planes_s2;
+} rcn_ingest_desc;
+int rcn_ingest_fused(const rcn_ingest_desc* d, void* stream);
+/* conv_first weight (128,4,3,3) OIHW -> [128][48] bf16 hi/lo, K index = (ky*3 + kx)*4 + c (zero beyond 36) */
+int rcn_pack_ingest_weight(const float* w_oihw, void* hi, void* lo, void* stream);
+
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */
 int rcn_tc_prof(unsigned long long* out16, int reset);

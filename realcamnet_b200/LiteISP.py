@@ -84,7 +84,17 @@ class Lens_Shading_Correction(nn.Module):
             x, sp = self.model[i]._f(x, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
         return self.model[6]._f(x, presplit=sp, store=ops.STORE_NCHW if nchw else ops.STORE_NHWC)
 
+    def layers(self):
+        return [self.model[i] for i in (0, 2, 4, 6)]
+
+    def _f_fused(self, coord_nchw, raw=None, conv_first=None, emit_stride=2):
+        """One kernel for the whole MLP (+ conv_first(raw) * (lsc + 1) of models/raw2bit.py:1780): hidden maps stay in tensor memory.
+        Returns (lsc NCHW, operand planes of the product | None).  Callers check ops.fused_ingest_ok first."""
+        return ops.ingest_fused(coord_nchw, self.layers(), 0.1, raw=raw, conv_first=conv_first, emit_stride=emit_stride)
+
     def forward(self, img_input):
+        if ops.fused_ingest_ok(self.layers(), img_input):
+            return self._f_fused(img_input)[0]
         return ops.to_nchw(self._f(ops.to_nhwc(img_input)))
 
 

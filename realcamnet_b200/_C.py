@@ -27,6 +27,21 @@ class ConvDesc(ctypes.Structure):
     ]
 
 
+class IngestDesc(ctypes.Structure):
+    """struct rcn_ingest_desc"""
+    _fields_ = [
+        ("coord", c_void_p), ("coord_bs", c_longlong), ("coord_ps", c_int), ("coord_cs", c_int),
+        ("w0", c_void_p), ("b0", c_void_p),
+        ("w1_hi", c_void_p), ("w1_lo", c_void_p), ("w2_hi", c_void_p), ("w2_lo", c_void_p), ("w3_hi", c_void_p), ("w3_lo", c_void_p),
+        ("b1", c_void_p), ("b2", c_void_p), ("b3", c_void_p),
+        ("slope", c_float),
+        ("lsc", c_void_p), ("N", c_int), ("H", c_int), ("W", c_int),
+        ("raw", c_void_p), ("ldraw", c_int),
+        ("wc_hi", c_void_p), ("wc_lo", c_void_p), ("bc", c_void_p),
+        ("fea_hi", c_void_p), ("fea_lo", c_void_p), ("planes_s2", c_int),
+    ]
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 
 # name -> (restype, argtypes); must list every symbol of include/rcn_b200.h (tests check this)
@@ -40,6 +55,8 @@ PROTOTYPES = {
     "rcn_split_bf16_s2": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_tc_prof": (_I, [_P, _I]),
+    "rcn_ingest_fused": (_I, [POINTER(IngestDesc), _P]),
+    "rcn_pack_ingest_weight": (_I, [_P, _P, _P, _P]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),
     "rcn_wmsa": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P, _I, _P, _P, _I, _P]),

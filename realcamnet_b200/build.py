@@ -33,9 +33,9 @@ def build(force=False, verbose=False):
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
-        if (not force) and os.path.isfile(obj) and os.path.getmtime(obj) > max(
-                os.path.getmtime(src), os.path.getmtime(os.path.join(CSRC, "common.cuh")),
-                os.path.getmtime(os.path.join(os.path.dirname(HERE), "include", "rcn_b200.h"))):
+        hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+        hdrs.append(os.path.join(os.path.dirname(HERE), "include", "rcn_b200.h"))
+        if (not force) and os.path.isfile(obj) and os.path.getmtime(obj) > max(os.path.getmtime(f) for f in [src] + hdrs):
             continue
         cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu", "-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -485,6 +485,64 @@ def wmsa(qkv, relpos, head_dim, ws, shifted, out=None, emit_split=False):
 
 
 # ----------------------------------------------------------------------------- layout
+
+# ----------------------------------------------------------------------------- fused packed-Bayer ingest
+_FUSED_INGEST = os.environ.get("RCN_FUSED_INGEST", "1") != "0"    # 0: the lens-shading MLP and conv_first run layer by layer (triage / A-B)
+
+
+def fused_ingest_ok(lsc_layers, coord, conv_first=None) -> bool:
+    """Shapes rcn_ingest_fused serves: the 2 -> 128 -> 128 -> 128 -> 128 lens-shading MLP (+ a 3x3 4 -> 128 conv_first) on the
+    bf16x3 engine, even H, W % 64 == 0."""
+    if not _FUSED_INGEST or _ENGINE != "bf16x3" or len(lsc_layers) != 4:
+        return False
+    shapes = [tuple(m.weight.shape) for m in lsc_layers]
+    if shapes != [(128, 2, 1, 1)] + [(128, 128, 1, 1)] * 3 or any(m.bias is None for m in lsc_layers):
+        return False
+    if conv_first is not None and (tuple(conv_first.weight.shape) != (128, 4, 3, 3) or conv_first.bias is None or conv_first.stride[0] != 1):
+        return False
+    N, C, H, W = coord.shape
+    return C == 2 and H % 2 == 0 and W % 64 == 0
+
+
+def ingest_fused(coord_nchw, lsc_layers, slope, raw=None, conv_first=None, emit_stride=2):
+    """models/raw2bit.py:1771-1780 as one kernel (rcn_ingest_fused): returns (lsc NCHW fp32, operand planes of
+    conv_first(raw) * (lsc + 1) | None).  coord_nchw: the API tensor (N,2,H,W); raw: NHWC (N,H,W,4)."""
+    _chk(coord_nchw, "ingest_fused.coord")
+    coord = coord_nchw.contiguous()
+    N, _, H, W = coord.shape
+    d = _C.IngestDesc()
+    d.coord, d.coord_bs, d.coord_ps, d.coord_cs = coord.data_ptr(), 2 * H * W, 1, H * W
+    l0 = lsc_layers[0]
+    w0, b0 = l0.weight.detach().contiguous(), l0.bias.detach().contiguous()
+    d.w0, d.b0 = w0.data_ptr(), b0.data_ptr()
+    pcs = [pack(m) for m in lsc_layers[1:]]
+    (d.w1_hi, d.w1_lo), (d.w2_hi, d.w2_lo), (d.w3_hi, d.w3_lo) = [(pc.w_hi.data_ptr(), pc.w_lo.data_ptr()) for pc in pcs]
+    d.b1, d.b2, d.b3 = [pc.bias.data_ptr() for pc in pcs]
+    d.slope = float(slope)
+    lsc = torch.empty((N, 128, H, W), device=coord.device, dtype=torch.float32)
+    d.lsc, d.N, d.H, d.W = lsc.data_ptr(), N, H, W
+    sp = None
+    keep = [coord, w0, b0, pcs]
+    if raw is not None:
+        rN, rH, rW, rC, ldr = geom(raw, "ingest_fused.raw")
+        if (rN, rH, rW, rC) != (N, H, W, 4):
+            raise ValueError(f"ingest_fused: raw {tuple(raw.shape)} does not match coord {tuple(coord.shape)}")
+        pc = pack(conv_first)
+        hit = pc._alt.get("ingest")
+        if hit is None:
+            hi = torch.empty((128, 48), device=raw.device, dtype=torch.bfloat16)
+            lo = torch.empty_like(hi)
+            _C.check(_C.lib().rcn_pack_ingest_weight(_ptr(pc.w_src), _ptr(hi), _ptr(lo), _stream()), "rcn_pack_ingest_weight")
+            hit = pc._alt["ingest"] = (hi, lo)
+        sp = alloc_planes(N, H, W, 128, raw.device, passes=3, stride=emit_stride, fmt=FMT_BF16)
+        d.raw, d.ldraw = raw.data_ptr(), ldr
+        d.wc_hi, d.wc_lo, d.bc = hit[0].data_ptr(), hit[1].data_ptr(), pc.bias.data_ptr()
+        d.fea_hi, d.fea_lo, d.planes_s2 = sp.hi.data_ptr(), sp.lo.data_ptr(), int(emit_stride == 2)
+        keep.append(hit)
+    _C.check(_C.lib().rcn_ingest_fused(ctypes.byref(d), _stream()), "rcn_ingest_fused")
+    return lsc, sp
+
+
 def to_nhwc(x, out=None):
     _chk(x, "to_nhwc.x")
     x = x.contiguous()

@@ -334,14 +334,20 @@ class raw_compression_tcm_final(SliceCodecModel):
     # ------------------------------------------------------------------------------ transforms (NHWC)
     def _analysis(self, x):
         """models/raw2bit.py:1771-1796 (and 1877-1901 in compress)."""
-        raw, cond, coord = ops.to_nhwc(x[0]), ops.to_nhwc(x[1]), ops.to_nhwc(x[2])
+        raw, cond = ops.to_nhwc(x[0]), ops.to_nhwc(x[1])
         vec = self.classifier._f(cond)                                  # (B,1,1,128) gfm_vector
-        lsc_fea = self.lsc._f(coord, nchw=True)                         # NCHW: it is an output of forward() (raw2bit.py:1853)
         rsp = ops.shared_split(raw, [ops.pack(self.conv_first), ops.pack(self.local_condition.in_conv.conv)])   # both read raw
         local = self.local_condition._f(raw, presplit=rsp)
-        # conv_first(x) * (lsc + 1): only conv_down (stride 2) reads it -> written once, as polyphase operand planes
-        fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, aux_nchw=True, presplit=rsp, emit_split=True, keep_fp32=False,
-                                      emit_stride=2)
+        if ops.fused_ingest_ok(self.lsc.layers(), x[2], self.conv_first) and tuple(x[2].shape[2:]) == tuple(raw.shape[1:3]):
+            # fused ingest (csrc/ingest.cu): lens-shading MLP + conv_first(x) * (lsc + 1) in one kernel; lsc is written once as the
+            # NCHW map forward() returns (raw2bit.py:1853), the product once as the polyphase operand planes of conv_down
+            lsc_fea, fsp = self.lsc._f_fused(x[2], raw, self.conv_first, emit_stride=2)
+            fea = None
+        else:
+            lsc_fea = self.lsc._f(ops.to_nhwc(x[2]), nchw=True)
+            # conv_first(x) * (lsc + 1): only conv_down (stride 2) reads it -> written once, as polyphase operand planes
+            fea, fsp = self.conv_first._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea, aux_nchw=True, presplit=rsp, emit_split=True,
+                                          keep_fp32=False, emit_stride=2)
         # every layer below hands its result to the next one as operand planes written by its own epilogue (the fp32 map is kept
         # only where a residual / aux operand needs it): no rcn_split_bf16 pass between the layers of a level
         fea, gsp = self.conv_down._f(fea, presplit=fsp, emit_split=True)

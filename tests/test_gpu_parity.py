@@ -414,6 +414,59 @@ def test_conditioning_blocks_match_oracle(dev, engine):
     assert rel(l.to(dev)(x.to(dev)), refpath.lens_shading(sd, "l", x)) < 1e-4
 
 
+@pytest.mark.parametrize("shape", [(1, 64, 64), (2, 34, 128), (1, 64, 1024), (1, 256, 256), (3, 2, 64)])
+@pytest.mark.parametrize("emit_stride", [1, 2])
+def test_fused_ingest_matches_reference(dev, shape, emit_stride):
+    """rcn_ingest_fused (lens-shading MLP + conv_first * (lsc + 1), models/raw2bit.py:1771-1780) against torch fp32 and against
+    the layer-by-layer product path; 1 .. 4 tiles per CTA, odd and even counts, batches, image borders."""
+    from realcamnet_b200 import LiteISP, ops
+    from realcamnet_b200.layers import conv3x3
+
+    N, H, W = shape
+    g = torch.Generator().manual_seed(H * 7 + W + N)
+    l = LiteISP.Lens_Shading_Correction(2, 128, 128)
+    weights.fill_(l, seed=6)
+    cf = conv3x3(4, 128)
+    weights.fill_(cf, seed=7)
+    coord = (torch.rand(N, 2, H, W, generator=g) * 2 - 1)
+    raw = torch.rand(N, 4, H, W, generator=g)
+    h = coord
+    mods = [l.model[i] for i in (0, 2, 4, 6)]
+    for i, m in enumerate(mods):
+        h = F.conv2d(h, m.weight, m.bias)
+        if i < 3:
+            h = F.leaky_relu(h, 0.1)
+    ref_lsc = h
+    ref_fea = F.conv2d(raw, cf.weight, cf.bias, padding=1) * (ref_lsc + 1)
+    l, cf = l.to(dev), cf.to(dev)
+    old = ops.get_engine()
+    ops.set_engine("bf16x3")
+    try:
+        assert ops.fused_ingest_ok(l.layers(), coord.to(dev), cf)
+        rawn = ops.to_nhwc(raw.to(dev))
+        lsc, sp = l._f_fused(coord.to(dev), rawn, cf, emit_stride=emit_stride)
+        lsc_only, none = l._f_fused(coord.to(dev))
+        torch.cuda.synchronize()
+        assert none is None
+        assert rel(lsc, ref_lsc) < CONV_TOL
+        assert torch.equal(lsc, lsc_only)          # the same arithmetic with and without the fused conv
+        fea = sp.hi.float() + sp.lo.float()         # (N,H,W,128) or polyphase (4N,H/2,W/2,128)
+        if emit_stride == 2:
+            full = torch.empty(N, H, W, 128, device=dev)
+            for py in range(2):
+                for px in range(2):
+                    full[:, py::2, px::2] = fea[(py * 2 + px) * N:(py * 2 + px + 1) * N]
+            fea = full
+        assert rel(fea.permute(0, 3, 1, 2), ref_fea) < CONV_TOL
+        # layer-by-layer path of the same engine
+        lw = l._f(ops.to_nhwc(coord.to(dev)), nchw=True)
+        assert rel(lsc, lw) < 2e-5
+        f2, sp2 = cf._f(rawn, epi=ops.EPI_MUL_AUXP1, aux=lw, aux_nchw=True, emit_split=True, keep_fp32=True, emit_stride=emit_stride)
+        assert rel(fea, f2) < 2e-5
+    finally:
+        ops.set_engine(old)
+
+
 @pytest.mark.parametrize("dim", [80, 200])
 def test_gma_block_matches_oracle_and_fixture(dev, engine, golden_dir, dim):
     from realcamnet_b200 import groupmix
