@@ -286,6 +286,23 @@ int rcn_ingest_fused(const rcn_ingest_desc* d, void* stream);
 /* conv_first weight (128,4,3,3) OIHW -> [128][48] bf16 hi/lo, K index = (ky*3 + kx)*4 + c (zero beyond 36) */
 int rcn_pack_ingest_weight(const float* w_oihw, void* hi, void* lo, void* stream);
 
+/* ---- fused Swin MLP ------------------------------------------------------------------------------------- */
+/* models/tcm.py:225-236: y = res + fc2(GELU(fc1(x))) for C = 64, hidden = 256 as ONE kernel (csrc/mlp.cu): x comes as the bf16
+ * hi/lo operand planes the LayerNorm kernel emits, the 4C-wide hidden activations live in tensor memory only (fc2 reads them
+ * as its tcgen05 A operand), the result is written as fp32 rows (y, pixel stride ldy) and / or as the consumer's operand planes
+ * (y_hi / y_lo, pixel stride Cp_out).  bf16x3 arithmetic. */
+typedef struct rcn_mlp_desc {
+    const void* x_hi; const void* x_lo; int ldp_in;   /* (npix, C) bf16 planes, pixel stride ldp_in elements */
+    long long npix;
+    int C, hidden;
+    const void* w1_hi; const void* w1_lo; const float* b1;   /* fc1: [hidden][C] bf16 hi/lo (rcn_pack_conv_weight_tc, Cp = C), bias */
+    const void* w2_hi; const void* w2_lo; const float* b2;   /* fc2: [C][hidden] */
+    const float* res; int ldres;                      /* residual rows (may be NULL) */
+    float* y; int ldy;                                /* may be NULL when y_hi is given */
+    void* y_hi; void* y_lo; int Cp_out;               /* may be NULL */
+} rcn_mlp_desc;
+int rcn_mlp_fused(const rcn_mlp_desc* d, void* stream);
+
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */
 int rcn_tc_prof(unsigned long long* out16, int reset);

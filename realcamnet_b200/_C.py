@@ -42,6 +42,19 @@ class IngestDesc(ctypes.Structure):
     ]
 
 
+class MlpDesc(ctypes.Structure):
+    """struct rcn_mlp_desc"""
+    _fields_ = [
+        ("x_hi", c_void_p), ("x_lo", c_void_p), ("ldp_in", c_int),
+        ("npix", c_longlong), ("C", c_int), ("hidden", c_int),
+        ("w1_hi", c_void_p), ("w1_lo", c_void_p), ("b1", c_void_p),
+        ("w2_hi", c_void_p), ("w2_lo", c_void_p), ("b2", c_void_p),
+        ("res", c_void_p), ("ldres", c_int),
+        ("y", c_void_p), ("ldy", c_int),
+        ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int),
+    ]
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 
 # name -> (restype, argtypes); must list every symbol of include/rcn_b200.h (tests check this)
@@ -56,6 +69,7 @@ PROTOTYPES = {
     "rcn_pack_conv_weight_tc": (_I, [_P, _I, _I, _I, _I, _I, _I, _P, _P, _P]),
     "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_ingest_fused": (_I, [POINTER(IngestDesc), _P]),
+    "rcn_mlp_fused": (_I, [POINTER(MlpDesc), _P]),
     "rcn_pack_ingest_weight": (_I, [_P, _P, _P, _P]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),

@@ -49,48 +49,6 @@ struct IngestParams {
     uint32_t total_tiles;
 };
 
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
-                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
-                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (128 rows = TMEM lanes, K = 16 bf16 = 8 columns at a_tmem) comes from tensor memory
-__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-
-// 16 fp32 values (channels 16j .. 16j+15 of this lane's pixel) -> the A operand columns of k-step j: 8 words of bf16 hi pairs, then
-// 8 words of bf16 lo pairs (element 2m in the low half-word).  Rounding as rcn_split_bf16: hi = rn(v), lo = rn(v - hi).
-__device__ __forceinline__ void split_pack16(const float* val, uint32_t* out) {
-#pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * m], val[2 * m + 1]);
-        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-        const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
-        const __nv_bfloat162 l = __floats2bfloat162_rn(val[2 * m] - h0, val[2 * m + 1] - h1);
-        out[m] = hb;
-        out[8 + m] = *reinterpret_cast<const uint32_t*>(&l);
-    }
-}
-
-__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-
-__device__ __forceinline__ void ig_arrive(uint32_t bar, int lane) {
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 // CONV: also conv_first * (lsc + 1) -> operand planes
 template <bool CONV>
 __global__ void __launch_bounds__(IG_THREADS, 1)
@@ -222,17 +180,38 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
         opaque(H); opaque(W); opaque(N); opaque(slope); opaque_ptr(coord); opaque_ptr(lsc); opaque_ptr(raw); opaque_ptr(fhi); opaque_ptr(flo);
         const long long HW = (long long)H * W;
         uint32_t dph = 0;
+        const uint32_t tiles_x = (uint32_t)P.tiles_x, tiles_y = (uint32_t)P.tiles_y;
+        // this lane's pixel of tile t: tile = 2 image rows x 64 pixels
+        auto locate = [&](uint32_t t, int& n, int& yy, int& xx) {
+            const int tx = (int)(t % tiles_x); t /= tiles_x;
+            const int ty = (int)(t % tiles_y);
+            n = (int)(t / tiles_y);
+            yy = 2 * ty + (q >> 1);
+            xx = 64 * tx + 32 * (q & 1) + lane;
+        };
+        auto load_coord = [&](int n, int yy, int xx, float& cx, float& cy) {
+            const float* cp = coord + (long long)n * p.coord_bs + ((long long)yy * W + xx) * p.coord_ps;
+            cx = __ldg(cp);
+            cy = __ldg(cp + p.coord_cs);
+        };
+        float ncx = 0.f, ncy = 0.f;     // coordinates of the NEXT tile, fetched one tile ahead (a global-load latency per tile otherwise)
+        if ((uint32_t)s < cnt) {
+            int n, yy, xx;
+            locate(blockIdx.x + (uint32_t)s * gridDim.x, n, yy, xx);
+            load_coord(n, yy, xx, ncx, ncy);
+        }
         for (uint32_t i = (uint32_t)s; i < cnt; i += 2) {
-            uint32_t t = blockIdx.x + i * gridDim.x;
-            const int tx = (int)(t % (uint32_t)P.tiles_x); t /= (uint32_t)P.tiles_x;
-            const int ty = (int)(t % (uint32_t)P.tiles_y);
-            const int n = (int)(t / (uint32_t)P.tiles_y);
-            const int yy = 2 * ty + (q >> 1), xx = 64 * tx + 32 * (q & 1) + lane;   // tile = 2 image rows x 64 pixels
+            int n, yy, xx;
+            locate(blockIdx.x + i * gridDim.x, n, yy, xx);
             const long long pix = (long long)yy * W + xx;
             // ---- layer 0 on the CUDA cores -> A operand of layer 1 in X
             {
-                const float* cp = coord + (long long)n * p.coord_bs + pix * p.coord_ps;
-                const float cx = __ldg(cp), cy = __ldg(cp + p.coord_cs);
+                const float cx = ncx, cy = ncy;
+                if (i + 2 < cnt) {
+                    int n2, y2, x2;
+                    locate(blockIdx.x + (i + 2) * gridDim.x, n2, y2, x2);
+                    load_coord(n2, y2, x2, ncx, ncy);
+                }
 #pragma unroll 2
                 for (int b = 0; b < 8; ++b) {
                     float val[16];
@@ -247,12 +226,12 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                         val[4 * g + 3] = fmaf(wy.w, cy, fmaf(wx.w, cx, bb.w));
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) val[j] = val[j] > 0.f ? val[j] : val[j] * slope;
+                    for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);   // LeakyReLU for 0 <= slope <= 1 (host-checked)
                     split_pack16(val, pk);
                     tmem_st16(X + 16u * b, pk);
                 }
                 tmem_wait_st();
-                ig_arrive(arb, lane);
+                chain_arrive(arb, lane);
             }
             // ---- layers 1, 2: accumulator -> bias + LeakyReLU -> hi/lo pairs, in place
 #pragma unroll 1
@@ -279,12 +258,12 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                         val[4 * g + 3] = __uint_as_float(v[b & 1][4 * g + 3]) + bb.w;
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) val[j] = val[j] > 0.f ? val[j] : val[j] * slope;
+                    for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);   // LeakyReLU for 0 <= slope <= 1 (host-checked)
                     split_pack16(val, pk);
                     tmem_st16(D + 16u * b, pk);
                 }
                 tmem_wait_st();
-                ig_arrive(arb, lane);
+                chain_arrive(arb, lane);
             }
             // ---- im2col operand of conv_first: gathered while layer 3 runs
             float4 tap[9];
@@ -311,7 +290,13 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                     tmem_wait_ld16(v[b & 1]);
                     if (b < 7) tmem_ld16_async(Y + 16u * (b + 1), v[(b + 1) & 1]);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) lp[(long long)(16 * b + j) * HW] = __uint_as_float(v[b & 1][j]) + lds1(c_b3 + 4u * (16 * b + j));
+                    for (int g = 0; g < 4; ++g) {
+                        const float4 bb = lds4(c_b3 + 64u * b + 16u * g);
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 0]) + bb.x; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 1]) + bb.y; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 2]) + bb.z; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 3]) + bb.w; lp += HW;
+                    }
                 }
                 // the next tile of this slot starts by overwriting X; Y is rewritten by its layer 1, issued after this group's
                 // next a_ready arrival -- program order of these warps covers both
@@ -331,7 +316,7 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                     tmem_st16(X + 16u * j, pk);
                 }
                 tmem_wait_st();
-                ig_arrive(arb, lane);
+                chain_arrive(arb, lane);
                 // plane addresses of this pixel
                 long long po;
                 if (p.planes_s2) {
@@ -360,10 +345,18 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                         float val[16];
                         uint32_t pk[16];
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float a = __uint_as_float(va[b & 1][j]) + lds1(c_b3 + 4u * (c0 + j));
-                            lp[(long long)(c0 + j) * HW] = a;
-                            val[j] = (__uint_as_float(vc[b & 1][j]) + lds1(c_bc + 4u * (c0 + j))) * (a + 1.f);
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 b3 = lds4(c_b3 + 4u * (uint32_t)c0 + 16u * g), bc = lds4(c_bc + 4u * (uint32_t)c0 + 16u * g);
+                            const float a0 = __uint_as_float(va[b & 1][4 * g + 0]) + b3.x, a1 = __uint_as_float(va[b & 1][4 * g + 1]) + b3.y,
+                                        a2 = __uint_as_float(va[b & 1][4 * g + 2]) + b3.z, a3 = __uint_as_float(va[b & 1][4 * g + 3]) + b3.w;
+                            lp[0] = a0; lp += HW;
+                            lp[0] = a1; lp += HW;
+                            lp[0] = a2; lp += HW;
+                            lp[0] = a3; lp += HW;
+                            val[4 * g + 0] = (__uint_as_float(vc[b & 1][4 * g + 0]) + bc.x) * (a0 + 1.f);
+                            val[4 * g + 1] = (__uint_as_float(vc[b & 1][4 * g + 1]) + bc.y) * (a1 + 1.f);
+                            val[4 * g + 2] = (__uint_as_float(vc[b & 1][4 * g + 2]) + bc.z) * (a2 + 1.f);
+                            val[4 * g + 3] = (__uint_as_float(vc[b & 1][4 * g + 3]) + bc.w) * (a3 + 1.f);
                         }
                         split_pack16(val, pk);
                         stg128(fhi + po + c0, pk[0], pk[1], pk[2], pk[3]);
@@ -371,7 +364,7 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                         stg128(flo + po + c0, pk[8], pk[9], pk[10], pk[11]);
                         stg128(flo + po + c0 + 8, pk[12], pk[13], pk[14], pk[15]);
                     }
-                    if (half == 0) ig_arrive(arb, lane);    // X[64..128) is drained: the second half may overwrite it
+                    if (half == 0) chain_arrive(arb, lane);    // X[64..128) is drained: the second half may overwrite it
                 }
             }
         }
@@ -426,6 +419,7 @@ extern "C" int rcn_ingest_fused(const rcn_ingest_desc* d, void* stream) {
     RCN_CHECK_ARG(d->w1_hi && d->w1_lo && d->w2_hi && d->w2_lo && d->w3_hi && d->w3_lo, "rcn_ingest_fused: null weight plane");
     RCN_CHECK_ARG(d->N > 0 && d->H > 0 && d->W > 0 && d->H % 2 == 0 && d->W % 64 == 0,
                   "rcn_ingest_fused: needs even H and W %% 64 == 0 (got %d x %d)", d->H, d->W);
+    RCN_CHECK_ARG(d->slope >= 0.f && d->slope <= 1.f, "rcn_ingest_fused: LeakyReLU slope must be in [0, 1]");
     const bool conv = d->raw != nullptr;
     if (conv) {
         RCN_CHECK_ARG(d->wc_hi && d->wc_lo && d->bc && d->fea_hi && d->fea_lo, "rcn_ingest_fused: the fused conv_first needs its weights, bias and output planes");

@@ -188,6 +188,50 @@ __device__ __forceinline__ float lds1(uint32_t addr) {
 }
 
 
+// ---- chained contractions with the activations as the A operand in tensor memory (ingest.cu, mlp.cu)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+                 "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                 "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (128 rows = TMEM lanes, K = 16 bf16 = 8 columns at a_tmem) comes from tensor memory
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// 16 fp32 values (channels 16j .. 16j+15 of this lane's pixel) -> the A operand columns of k-step j: 8 words of bf16 hi pairs, then
+// 8 words of bf16 lo pairs (element 2m in the low half-word).  Rounding as rcn_split_bf16: hi = rn(v), lo = rn(v - hi).
+__device__ __forceinline__ void split_pack16(const float* val, uint32_t* out) {
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(val[2 * m], val[2 * m + 1]);
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+        const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(val[2 * m] - h0, val[2 * m + 1] - h1);
+        out[m] = hb;
+        out[8 + m] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+}
+
+__device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+__device__ __forceinline__ void chain_arrive(uint32_t bar, int lane) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

@@ -542,6 +542,47 @@ def ingest_fused(coord_nchw, lsc_layers, slope, raw=None, conv_first=None, emit_
     _C.check(_C.lib().rcn_ingest_fused(ctypes.byref(d), _stream()), "rcn_ingest_fused")
     return lsc, sp
 
+_FUSED_MLP = os.environ.get("RCN_FUSED_MLP", "1") != "0"    # 0: fc1 and fc2 of the Swin MLP run as two conv launches (triage / A-B)
+
+
+def mlp_fused_ok(fc1, fc2, xsp) -> bool:
+    """Shapes rcn_mlp_fused serves: Linear(64, 256) -> GELU -> Linear(256, 64) on the bf16x3 engine, input as bf16 hi/lo planes."""
+    return (_FUSED_MLP and _ENGINE == "bf16x3" and xsp is not None and xsp.fmt == FMT_BF16 and xsp.lo is not None and xsp.key[7] == 1 and
+            tuple(fc1.weight.shape[:2]) == (256, 64) and tuple(fc2.weight.shape[:2]) == (64, 256) and fc1.bias is not None and
+            fc2.bias is not None and xsp.hi.shape[-1] == 64)
+
+
+def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True):
+    """models/tcm.py:225-236 as one kernel (rcn_mlp_fused): res + fc2(GELU(fc1(x))), x given as operand planes.
+    Returns (y | None, planes | None) like conv2d(emit_split=True)."""
+    N, H, W, C = xsp.hi.shape
+    p1, p2 = pack(fc1), pack(fc2)
+    d = _C.MlpDesc()
+    d.x_hi, d.x_lo, d.ldp_in = xsp.hi.data_ptr(), xsp.lo.data_ptr(), plane_ld(xsp.hi)
+    d.npix, d.C, d.hidden = N * H * W, 64, 256
+    d.w1_hi, d.w1_lo, d.b1 = p1.w_hi.data_ptr(), p1.w_lo.data_ptr(), p1.bias.data_ptr()
+    d.w2_hi, d.w2_lo, d.b2 = p2.w_hi.data_ptr(), p2.w_lo.data_ptr(), p2.bias.data_ptr()
+    _on_current_device(xsp.hi, "mlp_fused.x")
+    if res is not None:
+        rN, rH, rW, rC, ldr = geom(res, "mlp_fused.res")
+        if (rN, rH, rW, rC) != (N, H, W, 64):
+            raise ValueError("mlp_fused: residual geometry mismatch")
+        d.res, d.ldres = res.data_ptr(), ldr
+    want_out = keep_fp32 or split_out is None or out is not None
+    if want_out:
+        if out is None:
+            out = torch.empty((N, H, W, 64), device=xsp.hi.device, dtype=torch.float32)
+        oN, oH, oW, oC, ldy = geom(out, "mlp_fused.out")
+        if (oN, oH, oW, oC) != (N, H, W, 64):
+            raise ValueError("mlp_fused: output geometry mismatch")
+        d.y, d.ldy = out.data_ptr(), ldy
+    if split_out is not None:
+        if tuple(split_out.hi.shape) != (N, H, W, 64) or split_out.lo is None or split_out.fmt != FMT_BF16 or split_out.key[7] != 1:
+            raise ValueError("mlp_fused: split_out must be stride-1 bf16 hi/lo planes of the output geometry")
+        d.y_hi, d.y_lo, d.Cp_out = split_out.hi.data_ptr(), split_out.lo.data_ptr(), plane_ld(split_out.hi)
+    _C.check(_C.lib().rcn_mlp_fused(ctypes.byref(d), _stream()), "rcn_mlp_fused")
+    return (out if want_out else None), split_out
+
 
 def to_nhwc(x, out=None):
     _chk(x, "to_nhwc.x")

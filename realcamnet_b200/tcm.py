@@ -86,6 +86,9 @@ class Block(nn.Module):
         t, tsp = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps, emit_split=True)
         x1 = self.msa._f(t, res=x, presplit=tsp)
         t, tsp = ops.layernorm(x1, self.ln2.weight, self.ln2.bias, self.ln2.eps, emit_split=True)
+        if ops.mlp_fused_ok(self.mlp[0], self.mlp[2], tsp):
+            # one kernel (csrc/mlp.cu): the 4C-wide hidden activations stay in tensor memory
+            return ops.mlp_fused(tsp, self.mlp[0], self.mlp[2], res=x1, out=out, split_out=split_out, keep_fp32=keep_fp32)[0]
         h, hsp = self.mlp[0]._f(t, act=ACT_GELU, emit_split=True, keep_fp32=False, presplit=tsp)   # 4C-wide hidden: planes only
         if split_out is None:
             return self.mlp[2]._f(h, res=x1, out=out, presplit=hsp)

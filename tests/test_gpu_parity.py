@@ -467,6 +467,50 @@ def test_fused_ingest_matches_reference(dev, shape, emit_stride):
         ops.set_engine(old)
 
 
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 16, 64), (1, 256, 320), (1, 8, 9)])
+def test_fused_swin_mlp_matches_reference(dev, shape):
+    """rcn_mlp_fused (x + fc2(GELU(fc1(LN x))), models/tcm.py:225-236) against torch fp32 and the two-launch product path: ragged
+    last tile, 1 .. 5 tiles per CTA, residual / output / plane views with wider pixel strides."""
+    from realcamnet_b200 import ops
+    from realcamnet_b200.layers import Linear
+
+    N, H, W = shape
+    g = torch.Generator().manual_seed(H * 3 + W)
+    fc1, fc2 = Linear(64, 256), Linear(256, 64)
+    weights.fill_(fc1, seed=11)
+    weights.fill_(fc2, seed=12)
+    t = torch.randn(N, H, W, 64, generator=g)          # LayerNorm output
+    xres = torch.randn(N, H, W, 128, generator=g)      # residual = a channel slice of a wider tensor
+    ref = xres[..., 64:] + F.linear(F.gelu(F.linear(t, fc1.weight, fc1.bias)), fc2.weight, fc2.bias)
+    fc1, fc2 = fc1.to(dev), fc2.to(dev)
+    old = ops.get_engine()
+    ops.set_engine("bf16x3")
+    try:
+        td, rd = t.to(dev), xres.to(dev)
+        tsp = ops.split_operand(td, 64)
+        assert ops.mlp_fused_ok(fc1, fc2, tsp)
+        # fp32 output only
+        y, none = ops.mlp_fused(tsp, fc1, fc2, res=rd[..., 64:])
+        assert none is None and rel(y, ref) < CONV_TOL
+        # output into a slice view + planes into one half of a 128-wide plane buffer
+        wide = torch.zeros(N, H, W, 128, device=dev)
+        csp = ops.alloc_planes(N, H, W, 128, dev)
+        y2, sp = ops.mlp_fused(tsp, fc1, fc2, res=rd[..., 64:], out=wide[..., :64], split_out=csp.channels(64, 128), keep_fp32=True)
+        torch.cuda.synchronize()
+        assert torch.equal(y2, y) and float(wide[..., 64:].abs().max()) == 0.0
+        assert rel(csp.hi[..., 64:].float() + csp.lo[..., 64:].float(), ref) < CONV_TOL
+        # planes only, no residual
+        y3, sp3 = ops.mlp_fused(tsp, fc1, fc2, split_out=ops.alloc_planes(N, H, W, 64, dev), keep_fp32=False)
+        assert y3 is None
+        assert rel(sp3.hi.float() + sp3.lo.float(), ref - xres[..., 64:]) < CONV_TOL
+        # the two-launch path of the same engine
+        h, hsp = fc1._f(td, act=ops.ACT_GELU, emit_split=True, keep_fp32=False, presplit=tsp)
+        y4 = fc2._f(h, res=rd[..., 64:], presplit=hsp)
+        assert rel(y, y4) < 2e-5
+    finally:
+        ops.set_engine(old)
+
+
 @pytest.mark.parametrize("dim", [80, 200])
 def test_gma_block_matches_oracle_and_fixture(dev, engine, golden_dir, dim):
     from realcamnet_b200 import groupmix
