@@ -24,7 +24,9 @@ if ROOT not in sys.path:
 METRIC = "megapixels_per_s_raw_to_bitstream_forward"
 FLOP_PER_PACKED_POS = 2.764e6      # raw_compression_tcm_final.forward, 2*MAC per packed position
 # dram__bytes_read.sum + dram__bytes_write.sum of the dominant launch, (engine, T) -> bytes, from the committed ncu captures
-NCU_TRAFFIC = {}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, from the `ncu --set full` captures summarised in
+# profiles/r2_conv_tail_ncu.md (gpurun_out/r2_t17_tail*_raw.csv): key = (engine of the launch, tile size)
+NCU_TRAFFIC = {("fp16", 2048): 1.074746e9 + 1.032225e9, ("bf16x3", 2048): 2.171822e9 + 2.107215e9}
 
 
 def load_peaks():
@@ -405,8 +407,9 @@ def main():
                 "step_tflops": world * FLOP_PER_PACKED_POS * T * T * args.steps / (ms / 1e3) / 1e12}
     del a
 
-    # ---- second view: the dominant HBM-bound kernel class (1x1 conv 128->128 + LeakyReLU at full resolution, planes in / planes out:
-    # the lens-shading MLP layers, LiteISP.py:363-378).  Algorithmic bytes = operand planes read once + result planes written once.
+    # ---- second view: the HBM-bound kernel class (1x1 conv 128->128 + activation, planes in / planes out: the shape of the
+    # ConvTransBlock 1x1 layers, tcm.py:242-268, timed at full resolution).  Algorithmic bytes = operand planes read once + result
+    # planes written once.
     roofline_hbm = None
     if args.engine != "fp32":
         try:
@@ -428,13 +431,49 @@ def main():
             per_el = 8 if args.engine == "bf16x3" else 4          # 16-bit hi (+ lo) planes in, hi (+ lo) planes out
             hbytes = float(T) * T * 128 * per_el
             hpeak = float(peaks.get("hbm_gbs", 6650.0))
-            roofline_hbm = {"kernel": "conv_tc_kernel -- 1x1 128->128 + LeakyReLU @ full res, operand planes in / out (lens-shading MLP layer)",
+            roofline_hbm = {"kernel": "conv_tc_kernel -- 1x1 128->128 + LeakyReLU @ full res, operand planes in / out (the per-pixel 1x1 layer class of the path)",
                             "bound": "hbm", "achieved": hbytes / (hms / 1e3) / 1e9, "peak": hpeak, "unit": "GB/s",
                             "frac": hbytes / (hms / 1e3) / 1e9 / hpeak, "traffic": None, "ms_per_launch": hms,
                             "algorithmic_bytes_per_launch": hbytes, "peak_source": peaks["_src"] + ", burst copy bandwidth"}
             del a1, sp1
         except Exception as e:      # an extra view must never cost the bench line
             roofline_hbm = {"error": str(e)[:200]}
+
+    # ---- third view: the fused packed-Bayer ingest kernel of the step (csrc/ingest.cu: lens-shading MLP + conv_first * (lsc + 1),
+    # raw2bit.py:1771-1780), timed alone on the step's own inputs.  Algorithmic bytes per pixel: coord 2 x 4 + raw 4 x 4 in, the
+    # lens-shading map 128 x 4 (an output of forward()) and the 128-channel bf16 hi + lo operand planes of conv_down out.
+    roofline_ingest = None
+    if args.engine == "bf16x3":
+        try:
+            coord_d, raw_d = x_dev[2], ops.to_nhwc(x_dev[0])
+            if ops.fused_ingest_ok(model.lsc.layers(), coord_d, model.conv_first):
+                f2 = lambda: model.lsc._f_fused(coord_d, raw_d, model.conv_first, emit_stride=2)
+                for _ in range(3):
+                    f2()
+                torch.cuda.synchronize()
+                h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                h0.record()
+                for _ in range(reps):
+                    f2()
+                h1.record()
+                torch.cuda.synchronize()
+                ims = h0.elapsed_time(h1) / reps
+                ibytes = float(T) * T * (2 * 4 + 4 * 4 + 128 * 4 + 128 * 2 * 2)
+                iflop = float(T) * T * 2 * (2 * 128 + 3 * 128 * 128 + 36 * 128)
+                issued_i = float(T) * T * 2 * 3 * (3 * 128 * 128 + 48 * 128)
+                hpeak = float(peaks.get("hbm_gbs", 6650.0))
+                roofline_ingest = {"kernel": "ingest_kernel<conv> -- lens-shading MLP 2->128->128->128->128 (activations as the tcgen05 A operand "
+                                             "in tensor memory) + conv_first 3x3 4->128 * (lsc + 1), one launch",
+                                   "bound": "hbm", "achieved": ibytes / (ims / 1e3) / 1e9, "peak": hpeak, "unit": "GB/s",
+                                   "frac": ibytes / (ims / 1e3) / 1e9 / hpeak, "ms_per_launch": ims, "algorithmic_bytes_per_launch": ibytes,
+                                   "traffic": 0.103809e9 + 4.239047e9 if T == 2048 else None,
+                                   "traffic_unit": "bytes/launch (ncu dram read+write, profiles/r2_ingest_ncu.md)",
+                                   "algorithmic_tflops": iflop / (ims / 1e3) / 1e12, "issued_tflops": issued_i / (ims / 1e3) / 1e12,
+                                   "replaces": "5 launches (4 lens-shading layers + conv_first), 4.89 ms at T=2048",
+                                   "peak_source": peaks["_src"] + ", burst copy bandwidth"}
+            del raw_d
+        except Exception as e:
+            roofline_ingest = {"error": str(e)[:200]}
 
     cpu, mismatch = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -469,7 +508,7 @@ def main():
                 "gpu_launches_note": "kernel nodes executed inside the timed region (eager launches + nodes of the replayed CUDA graphs)",
                 "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": ms_e2e / args.steps},
-                "roofline": roofline, "roofline_hbm": roofline_hbm, "cpu_baseline": cpu,
+                "roofline": roofline, "roofline_hbm": roofline_hbm, "roofline_ingest": roofline_ingest, "cpu_baseline": cpu,
                 "symbols_mismatch_vs_oracle": mismatch, "frame4k": frame4k,
                 "decode": {"value": mp_tile / (decode_ms / 1e3), "unit": "MP/s", "ms_per_tile": decode_ms,
                            "what": "decompress(strings, shape) -> x_hat of the same tile (eager launches; host range decoder per slice)"},

@@ -35,13 +35,18 @@ namespace rcn {
 namespace {
 
 constexpr int IG_C = 128;                      // hidden / output width
-constexpr int IG_THREADS = 384;                // warp 0: weight TMA, warp 1: MMA issuer, warps 4-11: two epilogue warp groups
+#ifndef RCN_IG_EWG
+#define RCN_IG_EWG 2
+#endif
+constexpr int IG_EWG = RCN_IG_EWG;             // epilogue warp groups per tile slot (1 or 2): 2 halves every epilogue phase's latency
+constexpr int IG_THREADS = 128 + 256 * IG_EWG; // warp 0: weight TMA, warp 1: MMA issuer, warps 4..: IG_EWG epilogue warp groups per slot
 constexpr int IG_W_LAYER = 4 * 16384;          // one layer's B operand: hi chunk 0, hi chunk 1, lo chunk 0, lo chunk 1 (64-channel K chunks)
 constexpr int IG_W_MLP = 3 * IG_W_LAYER;       // 196608
 constexpr int IG_KC = 48;                      // conv_first K: 9 taps x 4 channels = 36, zero-padded to three k16 steps
 constexpr int IG_W_CONV = 2 * 3 * 4096;        // hi chunks 0-2, lo chunks 0-2 (16-channel K chunks, 32-byte rows)
 constexpr int IG_CONST_FLOATS = 7 * IG_C;      // w0[:,0], w0[:,1], b0, b1, b2, b3, b_conv
-constexpr int IG_REGS_LIGHT = 96, IG_REGS_EPI = 200;
+// register re-split after the prologue: 384 x 168 -> 128 x 96 + 256 x 200; 640 x 96 -> 128 x 64 + 512 x 104
+constexpr int IG_REGS_LIGHT = IG_EWG == 1 ? 96 : 64, IG_REGS_EPI = IG_EWG == 1 ? 200 : 104;
 
 struct IngestParams {
     rcn_ingest_desc d;
@@ -68,7 +73,7 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
 
     if (threadIdx.x == 0) {
         mbar_init(wfull, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4); mbar_init(&d_ready[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4 * IG_EWG); mbar_init(&d_ready[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < IG_C; i += IG_THREADS) {
@@ -168,8 +173,12 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(IG_REGS_LIGHT));
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IG_REGS_EPI));
-        // ================= epilogue warp group s = slot s; warp q of the group owns TMEM lanes 32q .. 32q+31 (lane = pixel)
-        const int s = (warp - 4) >> 2, q = warp & 3;
+        // ================= epilogue: IG_EWG warp groups per slot.  Warp q of a group owns TMEM lanes 32q .. 32q+31 (lane = pixel);
+        // group h of a slot handles the channel blocks [h * NB, (h + 1) * NB) of every phase (NB = 8 / IG_EWG blocks of 16 channels).
+        const int e = warp - 4;
+        const int s = (e >> 2) & 1, h = e >> 3, q = warp & 3;
+        constexpr int NB = 8 / IG_EWG;
+        const int b0 = h * NB;
         const uint32_t X = tmem_base + (uint32_t)s * 256u + ((uint32_t)(q * 32) << 16), Y = X + 128u;
         const uint32_t arb = smem_u32(&a_ready[s]), drb = smem_u32(&d_ready[s]);
         const uint32_t c_w0x = smem_u32(cst), c_w0y = c_w0x + 4 * IG_C, c_b0 = c_w0x + 8 * IG_C;
@@ -213,17 +222,18 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                     load_coord(n2, y2, x2, ncx, ncy);
                 }
 #pragma unroll 2
-                for (int b = 0; b < 8; ++b) {
+                for (int bb = 0; bb < NB; ++bb) {
+                    const int b = b0 + bb;
                     float val[16];
                     uint32_t pk[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 wx = lds4(c_w0x + 64u * b + 16u * g), wy = lds4(c_w0y + 64u * b + 16u * g),
-                                     bb = lds4(c_b0 + 64u * b + 16u * g);
-                        val[4 * g + 0] = fmaf(wy.x, cy, fmaf(wx.x, cx, bb.x));
-                        val[4 * g + 1] = fmaf(wy.y, cy, fmaf(wx.y, cx, bb.y));
-                        val[4 * g + 2] = fmaf(wy.z, cy, fmaf(wx.z, cx, bb.z));
-                        val[4 * g + 3] = fmaf(wy.w, cy, fmaf(wx.w, cx, bb.w));
+                                     bv = lds4(c_b0 + 64u * b + 16u * g);
+                        val[4 * g + 0] = fmaf(wy.x, cy, fmaf(wx.x, cx, bv.x));
+                        val[4 * g + 1] = fmaf(wy.y, cy, fmaf(wx.y, cx, bv.y));
+                        val[4 * g + 2] = fmaf(wy.z, cy, fmaf(wx.z, cx, bv.z));
+                        val[4 * g + 3] = fmaf(wy.w, cy, fmaf(wx.w, cx, bv.w));
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);   // LeakyReLU for 0 <= slope <= 1 (host-checked)
@@ -236,43 +246,45 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
             // ---- layers 1, 2: accumulator -> bias + LeakyReLU -> hi/lo pairs, in place
 #pragma unroll 1
             for (int l = 0; l < 2; ++l) {
-                const uint32_t D = (l == 1) ? X : Y;
-                const uint32_t c_b = smem_u32(cst) + 4u * (uint32_t)((3 + l) * IG_C);
+                const uint32_t D = ((l == 1) ? X : Y) + 16u * (uint32_t)b0;
+                const uint32_t c_b = smem_u32(cst) + 4u * (uint32_t)((3 + l) * IG_C) + 64u * (uint32_t)b0;
                 mbar_wait_a(drb, dph);
                 dph ^= 1u;
                 tc_fence_after();
                 uint32_t v[2][16];
                 tmem_ld16_async(D, v[0]);
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     tmem_wait_ld16(v[b & 1]);
-                    if (b < 7) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
+                    if (b < NB - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
                     float val[16];
                     uint32_t pk[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 bb = lds4(c_b + 64u * b + 16u * g);
-                        val[4 * g + 0] = __uint_as_float(v[b & 1][4 * g + 0]) + bb.x;
-                        val[4 * g + 1] = __uint_as_float(v[b & 1][4 * g + 1]) + bb.y;
-                        val[4 * g + 2] = __uint_as_float(v[b & 1][4 * g + 2]) + bb.z;
-                        val[4 * g + 3] = __uint_as_float(v[b & 1][4 * g + 3]) + bb.w;
+                        const float4 bv = lds4(c_b + 64u * b + 16u * g);
+                        val[4 * g + 0] = __uint_as_float(v[b & 1][4 * g + 0]) + bv.x;
+                        val[4 * g + 1] = __uint_as_float(v[b & 1][4 * g + 1]) + bv.y;
+                        val[4 * g + 2] = __uint_as_float(v[b & 1][4 * g + 2]) + bv.z;
+                        val[4 * g + 3] = __uint_as_float(v[b & 1][4 * g + 3]) + bv.w;
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);   // LeakyReLU for 0 <= slope <= 1 (host-checked)
+                    for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);
                     split_pack16(val, pk);
                     tmem_st16(D + 16u * b, pk);
                 }
                 tmem_wait_st();
                 chain_arrive(arb, lane);
             }
-            // ---- im2col operand of conv_first: gathered while layer 3 runs
+            // ---- im2col operand of conv_first, gathered while layer 3 runs.  K index = tap * 4 + channel; k-step j holds taps 4j .. 4j+3
+            // (zero beyond tap 8); group h writes the k-steps [j0, j0 + nj)
+            const int j0 = (IG_EWG == 2 && h == 1) ? 2 : 0, nj = (IG_EWG == 1) ? 3 : (h == 0 ? 2 : 1);
             float4 tap[9];
             if (CONV) {
 #pragma unroll
                 for (int k = 0; k < 9; ++k) {
                     const int y2 = yy + k / 3 - 1, x2 = xx + k % 3 - 1;
                     tap[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
+                    if ((k >> 2) >= j0 && (k >> 2) < j0 + nj && y2 >= 0 && y2 < H && x2 >= 0 && x2 < W)
                         tap[k] = __ldg(reinterpret_cast<const float4*>(raw + ((long long)n * HW + (long long)y2 * W + x2) * p.ldraw));
                 }
             }
@@ -281,43 +293,47 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
             dph ^= 1u;
             tc_fence_after();
             const uint32_t c_b3 = smem_u32(cst) + 4u * (uint32_t)(5 * IG_C), c_bc = smem_u32(cst) + 4u * (uint32_t)(6 * IG_C);
-            float* lp = lsc + ((long long)n * IG_C) * HW + pix;
+            float* lbase = lsc + ((long long)n * IG_C) * HW + pix;
             if (!CONV) {
+                float* lp = lbase + (long long)(16 * b0) * HW;
+                const uint32_t D = Y + 16u * (uint32_t)b0;
                 uint32_t v[2][16];
-                tmem_ld16_async(Y, v[0]);
+                tmem_ld16_async(D, v[0]);
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     tmem_wait_ld16(v[b & 1]);
-                    if (b < 7) tmem_ld16_async(Y + 16u * (b + 1), v[(b + 1) & 1]);
+                    if (b < NB - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 bb = lds4(c_b3 + 64u * b + 16u * g);
-                        lp[0] = __uint_as_float(v[b & 1][4 * g + 0]) + bb.x; lp += HW;
-                        lp[0] = __uint_as_float(v[b & 1][4 * g + 1]) + bb.y; lp += HW;
-                        lp[0] = __uint_as_float(v[b & 1][4 * g + 2]) + bb.z; lp += HW;
-                        lp[0] = __uint_as_float(v[b & 1][4 * g + 3]) + bb.w; lp += HW;
+                        const float4 bv = lds4(c_b3 + 64u * (uint32_t)(b0 + b) + 16u * g);
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 0]) + bv.x; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 1]) + bv.y; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 2]) + bv.z; lp += HW;
+                        lp[0] = __uint_as_float(v[b & 1][4 * g + 3]) + bv.w; lp += HW;
                     }
                 }
-                // the next tile of this slot starts by overwriting X; Y is rewritten by its layer 1, issued after this group's
-                // next a_ready arrival -- program order of these warps covers both
+                // the next tile of this slot starts by overwriting X; Y is rewritten by its layer 1, issued after the groups'
+                // next a_ready arrivals -- program order of these warps covers both
             } else {
-                // X is free (layer 3 has read it): conv A operand, K index = tap * 4 + channel, into X[0..48)
+                // X is free (layer 3 has read it): conv A operand into X[0..48)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    float val[16];
-                    uint32_t pk[16];
+                    if (j >= j0 && j < j0 + nj) {
+                        float val[16];
+                        uint32_t pk[16];
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int k = 4 * j + g;
-                        const float4 tv = k < 9 ? tap[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        val[4 * g + 0] = tv.x; val[4 * g + 1] = tv.y; val[4 * g + 2] = tv.z; val[4 * g + 3] = tv.w;
+                        for (int g = 0; g < 4; ++g) {
+                            const int k = 4 * j + g;
+                            const float4 tv = k < 9 ? tap[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            val[4 * g + 0] = tv.x; val[4 * g + 1] = tv.y; val[4 * g + 2] = tv.z; val[4 * g + 3] = tv.w;
+                        }
+                        split_pack16(val, pk);
+                        tmem_st16(X + 16u * j, pk);
                     }
-                    split_pack16(val, pk);
-                    tmem_st16(X + 16u * j, pk);
                 }
                 tmem_wait_st();
                 chain_arrive(arb, lane);
-                // plane addresses of this pixel
+                // plane address of this pixel
                 long long po;
                 if (p.planes_s2) {
                     const long long plane = (long long)(((yy & 1) * 2 + (xx & 1)) * N + n);
@@ -325,23 +341,27 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                 } else {
                     po = ((long long)n * HW + pix) * IG_C;
                 }
+                constexpr int NBH = 4 / IG_EWG;      // blocks per group and 64-channel half
 #pragma unroll 1
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait_a(drb, dph);
                     dph ^= 1u;
                     tc_fence_after();
+                    const int cb = 64 * half + 16 * NBH * h;          // first channel of this group in this half
+                    float* lp = lbase + (long long)cb * HW;
+                    const uint32_t Dl = Y + (uint32_t)cb, Dc = X + 64u + (uint32_t)(16 * NBH * h);
                     uint32_t va[2][16], vc[2][16];
-                    tmem_ld16_async(Y + 64u * half, va[0]);
-                    tmem_ld16_async(X + 64u, vc[0]);
+                    tmem_ld16_async(Dl, va[0]);
+                    tmem_ld16_async(Dc, vc[0]);
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
+                    for (int b = 0; b < NBH; ++b) {
                         tmem_wait_ld16(va[b & 1]);
                         tmem_wait_ld16(vc[b & 1]);
-                        if (b < 3) {
-                            tmem_ld16_async(Y + 64u * half + 16u * (b + 1), va[(b + 1) & 1]);
-                            tmem_ld16_async(X + 64u + 16u * (b + 1), vc[(b + 1) & 1]);
+                        if (b < NBH - 1) {
+                            tmem_ld16_async(Dl + 16u * (b + 1), va[(b + 1) & 1]);
+                            tmem_ld16_async(Dc + 16u * (b + 1), vc[(b + 1) & 1]);
                         }
-                        const int c0 = 64 * half + 16 * b;
+                        const int c0 = cb + 16 * b;
                         float val[16];
                         uint32_t pk[16];
 #pragma unroll
@@ -365,6 +385,12 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                         stg128(flo + po + c0 + 8, pk[12], pk[13], pk[14], pk[15]);
                     }
                     if (half == 0) chain_arrive(arb, lane);    // X[64..128) is drained: the second half may overwrite it
+                }
+                // The conv accumulator X[64..128) lies in the columns the slot's SECOND group overwrites first thing in the next tile
+                // (layer 0 of its channel blocks): both groups of the slot must have drained it.
+                if (IG_EWG == 2) {
+                    if (s == 0) asm volatile("bar.sync 1, 256;" ::: "memory");
+                    else asm volatile("bar.sync 2, 256;" ::: "memory");
                 }
             }
         }

@@ -27,13 +27,17 @@ namespace rcn {
 namespace {
 
 constexpr int MF_C = 64, MF_HID = 256;
-constexpr int MF_THREADS = 384;          // warp 0: TMA producer, warp 1: MMA issuer, warps 4-11: two epilogue warp groups
+#ifndef RCN_MF_EWG
+#define RCN_MF_EWG 2
+#endif
+constexpr int MF_EWG = RCN_MF_EWG;       // epilogue warp groups per tile slot (1 or 2)
+constexpr int MF_THREADS = 128 + 256 * MF_EWG;   // warp 0: TMA producer, warp 1: MMA issuer, warps 4..: MF_EWG epilogue warp groups per slot
 constexpr int MF_W1 = 2 * 32768;         // hi, lo: 256 rows x 128 B (one 64-channel K chunk)
 constexpr int MF_W2 = 2 * 32768;         // hi, lo: 4 K chunks x (64 rows x 128 B)
 constexpr int MF_A = 2 * 16384;          // one stage: hi, lo tile of 128 pixels x 64 channels
 constexpr int MF_NA = 2;
 constexpr int MF_CONST_FLOATS = MF_HID + MF_C;
-constexpr int MF_REGS_LIGHT = 96, MF_REGS_EPI = 200;
+constexpr int MF_REGS_LIGHT = MF_EWG == 1 ? 96 : 64, MF_REGS_EPI = MF_EWG == 1 ? 200 : 104;   // 384 x 168 -> 128 x 96 + 256 x 200; 640 x 96 -> 128 x 64 + 512 x 104
 
 struct MlpParams {
     rcn_mlp_desc d;
@@ -63,7 +67,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
     if (threadIdx.x == 0) {
         mbar_init(wfull, 1);
         for (int i = 0; i < MF_NA; ++i) { mbar_init(&afull[i], 1); mbar_init(&aempty[i], 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4); mbar_init(&d_ready[s], 1); mbar_init(&h_free[s], 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4 * MF_EWG); mbar_init(&d_ready[s], 1); mbar_init(&h_free[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < MF_CONST_FLOATS; i += MF_THREADS) cst[i] = i < MF_HID ? __ldg(p.b1 + i) : __ldg(p.b2 + i - MF_HID);
@@ -215,8 +219,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MF_REGS_LIGHT));
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MF_REGS_EPI));
-        // ================= epilogue warp group s = slot s; warp q of the group owns TMEM lanes 32q .. 32q+31 (lane = pixel)
-        const int s = (warp - 4) >> 2, q = warp & 3;
+        // ================= epilogue: MF_EWG warp groups per slot; warp q of a group owns TMEM lanes 32q .. 32q+31 (lane = pixel);
+        // group h handles the blocks [h * NB, (h + 1) * NB) of 16 hidden channels of each fc1 half and [h * NB2, ..) of the output
+        const int e = warp - 4;
+        const int s = (e >> 2) & 1, h = e >> 3, q = warp & 3;
+        constexpr int NB = 8 / MF_EWG, NB2 = 4 / MF_EWG;
         const uint32_t H = tmem_base + (uint32_t)s * 192u + ((uint32_t)(q * 32) << 16), D2 = H + 128u;
         const uint32_t arb = smem_u32(&a_ready[s]), drb = smem_u32(&d_ready[s]);
         const uint32_t c_b1 = smem_u32(cst), c_b2 = c_b1 + 4u * MF_HID;
@@ -235,51 +242,55 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                 mbar_wait_a(drb, dph);
                 dph ^= 1u;
                 tc_fence_after();
+                const uint32_t D = H + 16u * (uint32_t)(h * NB);
+                const uint32_t cb = c_b1 + 512u * half + 64u * (uint32_t)(h * NB);
                 uint32_t v[2][16];
-                tmem_ld16_async(H, v[0]);
+                tmem_ld16_async(D, v[0]);
 #pragma unroll
-                for (int b = 0; b < 8; ++b) {
+                for (int b = 0; b < NB; ++b) {
                     tmem_wait_ld16(v[b & 1]);
-                    if (b < 7) tmem_ld16_async(H + 16u * (b + 1), v[(b + 1) & 1]);
+                    if (b < NB - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
                     float val[16];
                     uint32_t pk[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 bb = lds4(c_b1 + 512u * half + 64u * b + 16u * g);
+                        const float4 bb = lds4(cb + 64u * b + 16u * g);
                         val[4 * g + 0] = gelu_as(__uint_as_float(v[b & 1][4 * g + 0]) + bb.x);
                         val[4 * g + 1] = gelu_as(__uint_as_float(v[b & 1][4 * g + 1]) + bb.y);
                         val[4 * g + 2] = gelu_as(__uint_as_float(v[b & 1][4 * g + 2]) + bb.z);
                         val[4 * g + 3] = gelu_as(__uint_as_float(v[b & 1][4 * g + 3]) + bb.w);
                     }
                     split_pack16(val, pk);
-                    tmem_st16(H + 16u * b, pk);
+                    tmem_st16(D + 16u * b, pk);
                 }
                 tmem_wait_st();
                 chain_arrive(arb, lane);
             }
-            // ---- residual row of this pixel, fetched while fc2 finishes
-            float4 r[16];
+            // ---- residual channels of this pixel and group, fetched while fc2 finishes
+            const int c0 = 16 * NB2 * h;
+            float4 r[4 * NB2];
 #pragma unroll
-            for (int g = 0; g < 16; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int g = 0; g < 4 * NB2; ++g) r[g] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (res && ok) {
-                const float4* rp = reinterpret_cast<const float4*>(res + pix * ldres);
+                const float4* rp = reinterpret_cast<const float4*>(res + pix * ldres + c0);
 #pragma unroll
-                for (int g = 0; g < 16; ++g) r[g] = __ldg(rp + g);
+                for (int g = 0; g < 4 * NB2; ++g) r[g] = __ldg(rp + g);
             }
             mbar_wait_a(drb, dph);
             dph ^= 1u;
             tc_fence_after();
             {
+                const uint32_t D = D2 + (uint32_t)c0;
                 uint32_t v[2][16];
-                tmem_ld16_async(D2, v[0]);
+                tmem_ld16_async(D, v[0]);
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
+                for (int b = 0; b < NB2; ++b) {
                     tmem_wait_ld16(v[b & 1]);
-                    if (b < 3) tmem_ld16_async(D2 + 16u * (b + 1), v[(b + 1) & 1]);
+                    if (b < NB2 - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
                     float val[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
-                        const float4 bb = lds4(c_b2 + 64u * b + 16u * g);
+                        const float4 bb = lds4(c_b2 + 4u * (uint32_t)c0 + 64u * b + 16u * g);
                         const float4 rr = r[4 * b + g];
                         val[4 * g + 0] = __uint_as_float(v[b & 1][4 * g + 0]) + bb.x + rr.x;
                         val[4 * g + 1] = __uint_as_float(v[b & 1][4 * g + 1]) + bb.y + rr.y;
@@ -288,14 +299,14 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                     }
                     if (ok) {
                         if (y) {
-                            float4* yp = reinterpret_cast<float4*>(y + pix * ldy + 16 * b);
+                            float4* yp = reinterpret_cast<float4*>(y + pix * ldy + c0 + 16 * b);
 #pragma unroll
                             for (int g = 0; g < 4; ++g) yp[g] = make_float4(val[4 * g], val[4 * g + 1], val[4 * g + 2], val[4 * g + 3]);
                         }
                         if (yhi) {
                             uint32_t pk[16];
                             split_pack16(val, pk);
-                            const long long po = pix * cpo + 16 * b;
+                            const long long po = pix * cpo + c0 + 16 * b;
                             stg128(yhi + po, pk[0], pk[1], pk[2], pk[3]);
                             stg128(yhi + po + 8, pk[4], pk[5], pk[6], pk[7]);
                             stg128(ylo + po, pk[8], pk[9], pk[10], pk[11]);
