@@ -290,7 +290,7 @@ int rcn_pack_ingest_weight(const float* w_oihw, void* hi, void* lo, void* stream
 /* models/tcm.py:225-236: y = res + fc2(GELU(fc1(x))) for C = 64, hidden = 256 as ONE kernel (csrc/mlp.cu): x comes as the bf16
  * hi/lo operand planes the LayerNorm kernel emits, the 4C-wide hidden activations live in tensor memory only (fc2 reads them
  * as its tcgen05 A operand), the result is written as fp32 rows (y, pixel stride ldy) and / or as the consumer's operand planes
- * (y_hi / y_lo, pixel stride Cp_out).  bf16x3 arithmetic. */
+ * (y_hi / y_lo, pixel stride Cp_out).  With x_ln the LayerNorm in front (self.ln2) is part of the kernel too.  bf16x3 arithmetic. */
 typedef struct rcn_mlp_desc {
     const void* x_hi; const void* x_lo; int ldp_in;   /* (npix, C) bf16 planes, pixel stride ldp_in elements */
     long long npix;
@@ -300,6 +300,9 @@ typedef struct rcn_mlp_desc {
     const float* res; int ldres;                      /* residual rows (may be NULL) */
     float* y; int ldy;                                /* may be NULL when y_hi is given */
     void* y_hi; void* y_lo; int Cp_out;               /* may be NULL */
+    /* optional: x_ln != NULL makes the kernel apply nn.LayerNorm(C, eps) itself (models/tcm.py:234: self.ln2) on fp32 rows x_ln
+     * (pixel stride ldx) instead of reading x_hi / x_lo: no rcn_layernorm launch, no LayerNorm planes in HBM */
+    const float* x_ln; int ldx; const float* gamma; const float* beta; float eps;
 } rcn_mlp_desc;
 int rcn_mlp_fused(const rcn_mlp_desc* d, void* stream);
 

@@ -52,6 +52,7 @@ class MlpDesc(ctypes.Structure):
         ("res", c_void_p), ("ldres", c_int),
         ("y", c_void_p), ("ldy", c_int),
         ("y_hi", c_void_p), ("y_lo", c_void_p), ("Cp_out", c_int),
+        ("x_ln", c_void_p), ("ldx", c_int), ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
     ]
 
 

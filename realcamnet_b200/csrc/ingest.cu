@@ -379,10 +379,8 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                             val[4 * g + 3] = (__uint_as_float(vc[b & 1][4 * g + 3]) + bc.w) * (a3 + 1.f);
                         }
                         split_pack16(val, pk);
-                        stg128(fhi + po + c0, pk[0], pk[1], pk[2], pk[3]);
-                        stg128(fhi + po + c0 + 8, pk[4], pk[5], pk[6], pk[7]);
-                        stg128(flo + po + c0, pk[8], pk[9], pk[10], pk[11]);
-                        stg128(flo + po + c0 + 8, pk[12], pk[13], pk[14], pk[15]);
+                        stg256(fhi + po + c0, pk);          // 16 channels = one full 32-byte sector per plane
+                        stg256(flo + po + c0, pk + 8);
                     }
                     if (half == 0) chain_arrive(arb, lane);    // X[64..128) is drained: the second half may overwrite it
                 }
@@ -451,8 +449,8 @@ extern "C" int rcn_ingest_fused(const rcn_ingest_desc* d, void* stream) {
         RCN_CHECK_ARG(d->wc_hi && d->wc_lo && d->bc && d->fea_hi && d->fea_lo, "rcn_ingest_fused: the fused conv_first needs its weights, bias and output planes");
         RCN_CHECK_ARG(d->ldraw >= 4 && d->ldraw % 4 == 0 && (reinterpret_cast<uintptr_t>(d->raw) & 15) == 0,
                       "rcn_ingest_fused: raw must be NHWC with 4 channels, 16-byte aligned pixels");
-        RCN_CHECK_ARG((reinterpret_cast<uintptr_t>(d->fea_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->fea_lo) & 15) == 0,
-                      "rcn_ingest_fused: output planes must be 16-byte aligned");
+        RCN_CHECK_ARG((reinterpret_cast<uintptr_t>(d->fea_hi) & 31) == 0 && (reinterpret_cast<uintptr_t>(d->fea_lo) & 31) == 0,
+                      "rcn_ingest_fused: output planes must be 32-byte aligned");
     }
     RCN_CHECK_ARG(get_encode() != nullptr, "rcn_ingest_fused: cuTensorMapEncodeTiled is not available from the driver");
     IngestParams P;

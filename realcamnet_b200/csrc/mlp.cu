@@ -36,14 +36,19 @@ constexpr int MF_W1 = 2 * 32768;         // hi, lo: 256 rows x 128 B (one 64-cha
 constexpr int MF_W2 = 2 * 32768;         // hi, lo: 4 K chunks x (64 rows x 128 B)
 constexpr int MF_A = 2 * 16384;          // one stage: hi, lo tile of 128 pixels x 64 channels
 constexpr int MF_NA = 2;
-constexpr int MF_CONST_FLOATS = MF_HID + MF_C;
+constexpr int MF_CONST_FLOATS = MF_HID + 3 * MF_C;    // b1[256], b2[64], LayerNorm gamma[64], beta[64]
 constexpr int MF_REGS_LIGHT = MF_EWG == 1 ? 96 : 64, MF_REGS_EPI = MF_EWG == 1 ? 200 : 104;   // 384 x 168 -> 128 x 96 + 256 x 200; 640 x 96 -> 128 x 64 + 512 x 104
 
 struct MlpParams {
     rcn_mlp_desc d;
     uint32_t total_tiles;
+    int wide;      // outputs are 32-byte aligned rows: 256-bit stores (full sectors) instead of 128-bit ones
 };
 
+// LN: the kernel also applies the LayerNorm in front of fc1 (models/tcm.py:234): each epilogue thread normalises its pixel's fp32 row in
+// registers and writes the bf16 hi/lo A operand of fc1 into tensor memory (A1: 64 columns), so fc1 runs in the TS form as well and
+// neither the LayerNorm launch nor its planes exist.  TMEM slot: [A1 64] H 128, D2 64.
+template <bool LN>
 __global__ void __launch_bounds__(MF_THREADS, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo, const __grid_constant__ CUtensorMap m1h,
                  const __grid_constant__ CUtensorMap m1l, const __grid_constant__ CUtensorMap m2h, const __grid_constant__ CUtensorMap m2l,
@@ -55,7 +60,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
     uint8_t* w1s = smem;
     uint8_t* w2s = smem + MF_W1;
     uint8_t* asm_ = smem + MF_W1 + MF_W2;
-    float* cst = reinterpret_cast<float*>(asm_ + MF_NA * MF_A);      // b1[256], b2[64]
+    float* cst = reinterpret_cast<float*>(asm_ + (LN ? 0 : MF_NA * MF_A));      // b1[256], b2[64], gamma[64], beta[64]
+    constexpr uint32_t SLOT = LN ? 256u : 192u, HOFF = LN ? 64u : 0u;        // TMEM columns per tile slot, offset of H in it
     uint64_t* wfull = reinterpret_cast<uint64_t*>(cst + MF_CONST_FLOATS);
     uint64_t* afull = wfull + 1;          // [MF_NA] TMA -> issuer
     uint64_t* aempty = afull + MF_NA;     // [MF_NA] issuer (tcgen05.commit) -> TMA
@@ -70,7 +76,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
         for (int s = 0; s < 2; ++s) { mbar_init(&a_ready[s], 4 * MF_EWG); mbar_init(&d_ready[s], 1); mbar_init(&h_free[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < MF_CONST_FLOATS; i += MF_THREADS) cst[i] = i < MF_HID ? __ldg(p.b1 + i) : __ldg(p.b2 + i - MF_HID);
+    for (int i = threadIdx.x; i < MF_CONST_FLOATS; i += MF_THREADS) {
+        float v = 0.f;
+        if (i < MF_HID) v = __ldg(p.b1 + i);
+        else if (i < MF_HID + MF_C) v = __ldg(p.b2 + i - MF_HID);
+        else if (LN) v = i < MF_HID + 2 * MF_C ? __ldg(p.gamma + i - MF_HID - MF_C) : __ldg(p.beta + i - MF_HID - 2 * MF_C);
+        cst[i] = v;
+    }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -98,7 +110,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
         }
         __syncwarp();
         uint32_t st = 0, phs = 0;
-        for (uint32_t i = 0; i < cnt; ++i) {
+        const uint32_t nload = LN ? 0u : cnt;      // LN: the epilogue groups build the A operand themselves
+        for (uint32_t i = 0; i < nload; ++i) {
             const uint32_t t = blockIdx.x + i * gridDim.x;
             mbar_wait_a(ae + 8u * st, phs ^ 1u);
             if (elect_one()) {
@@ -128,21 +141,28 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
 #pragma unroll
             for (int s = 0; s < 2; ++s) {
                 if (2 * pr + s >= cnt) continue;
-                if (pr > 0) {      // the slot's previous tile has left tensor memory (its final epilogue has read D2)
+                if (LN || pr > 0) {   // LN: the slot's A1 operand is written (which the epilogue groups do after they have drained the
+                                      // previous tile); else: the slot's previous tile has left tensor memory (final epilogue read D2)
                     mbar_wait_a(ar + 8u * s, (ph >> s) & 1u);
                     ph ^= 1u << s;
                 }
-                mbar_wait_a(af + 8u * ast, aph);
+                if (!LN) mbar_wait_a(af + 8u * ast, aph);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t H = tmem_base + (uint32_t)s * 192u;
+                    const uint32_t A1 = tmem_base + (uint32_t)s * SLOT, H = A1 + HOFF;
                     const uint64_t ah = ad0 + (uint64_t)((ast * (uint32_t)MF_A) >> 4), al = ah + (uint64_t)(16384 >> 4);
                     const uint64_t bh = w1d, bl = w1d + (uint64_t)(32768 >> 4);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        umma_bf16(H, al + 2u * j, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
-                        umma_bf16(H, ah + 2u * j, bl + 2u * j, idesc128, 1u);
-                        umma_bf16(H, ah + 2u * j, bh + 2u * j, idesc128, 1u);
+                        if (LN) {
+                            umma_ts(H, A1 + 16u * j + 8u, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
+                            umma_ts(H, A1 + 16u * j, bl + 2u * j, idesc128, 1u);
+                            umma_ts(H, A1 + 16u * j, bh + 2u * j, idesc128, 1u);
+                        } else {
+                            umma_bf16(H, al + 2u * j, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
+                            umma_bf16(H, ah + 2u * j, bl + 2u * j, idesc128, 1u);
+                            umma_bf16(H, ah + 2u * j, bh + 2u * j, idesc128, 1u);
+                        }
                     }
                     umma_commit_a(dr + 8u * s);
                 }
@@ -158,7 +178,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                 ph ^= 1u << s;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t H = tmem_base + (uint32_t)s * 192u, D2 = H + 128u;
+                    const uint32_t H = tmem_base + (uint32_t)s * SLOT + HOFF, D2 = H + 128u;
                     const uint64_t ch = w2d, cl = w2d + (uint64_t)(32768 >> 4);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -178,18 +198,24 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                 hph ^= 1u << s;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t H = tmem_base + (uint32_t)s * 192u;
+                    const uint32_t A1 = tmem_base + (uint32_t)s * SLOT, H = A1 + HOFF;
                     const uint32_t sg = stage_of[s];
                     const uint64_t ah = ad0 + (uint64_t)((sg * (uint32_t)MF_A) >> 4), al = ah + (uint64_t)(16384 >> 4);
                     const uint64_t bh = w1d + (uint64_t)(16384 >> 4), bl = bh + (uint64_t)(32768 >> 4);
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        umma_bf16(H, al + 2u * j, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
-                        umma_bf16(H, ah + 2u * j, bl + 2u * j, idesc128, 1u);
-                        umma_bf16(H, ah + 2u * j, bh + 2u * j, idesc128, 1u);
+                        if (LN) {
+                            umma_ts(H, A1 + 16u * j + 8u, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
+                            umma_ts(H, A1 + 16u * j, bl + 2u * j, idesc128, 1u);
+                            umma_ts(H, A1 + 16u * j, bh + 2u * j, idesc128, 1u);
+                        } else {
+                            umma_bf16(H, al + 2u * j, bh + 2u * j, idesc128, j > 0 ? 1u : 0u);
+                            umma_bf16(H, ah + 2u * j, bl + 2u * j, idesc128, 1u);
+                            umma_bf16(H, ah + 2u * j, bh + 2u * j, idesc128, 1u);
+                        }
                     }
                     umma_commit_a(dr + 8u * s);
-                    umma_commit_a(ae + 8u * sg);       // the LN planes of this tile are consumed
+                    if (!LN) umma_commit_a(ae + 8u * sg);       // the LN planes of this tile are consumed
                 }
                 __syncwarp();
             }
@@ -201,7 +227,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                 ph ^= 1u << s;
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t H = tmem_base + (uint32_t)s * 192u, D2 = H + 128u;
+                    const uint32_t H = tmem_base + (uint32_t)s * SLOT + HOFF, D2 = H + 128u;
                     const uint64_t ch = w2d + (uint64_t)(16384 >> 4), cl = ch + (uint64_t)(32768 >> 4);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
@@ -224,18 +250,74 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
         const int e = warp - 4;
         const int s = (e >> 2) & 1, h = e >> 3, q = warp & 3;
         constexpr int NB = 8 / MF_EWG, NB2 = 4 / MF_EWG;
-        const uint32_t H = tmem_base + (uint32_t)s * 192u + ((uint32_t)(q * 32) << 16), D2 = H + 128u;
+        const uint32_t A1 = tmem_base + (uint32_t)s * SLOT + ((uint32_t)(q * 32) << 16), H = A1 + HOFF, D2 = H + 128u;
         const uint32_t arb = smem_u32(&a_ready[s]), drb = smem_u32(&d_ready[s]);
-        const uint32_t c_b1 = smem_u32(cst), c_b2 = c_b1 + 4u * MF_HID;
+        const uint32_t c_b1 = smem_u32(cst), c_b2 = c_b1 + 4u * MF_HID, c_g = c_b2 + 4u * MF_C, c_be = c_g + 4u * MF_C;
+        const float* xln = p.x_ln;
+        int ldx = p.ldx;
+        float eps = p.eps;
+        opaque_ptr(xln); opaque(ldx); opaque(eps);
         const float* res = p.res; float* y = p.y;
         uint16_t* yhi = reinterpret_cast<uint16_t*>(p.y_hi); uint16_t* ylo = reinterpret_cast<uint16_t*>(p.y_lo);
-        int ldres = p.ldres, ldy = p.ldy, cpo = p.Cp_out;
+        int ldres = p.ldres, ldy = p.ldy, cpo = p.Cp_out, wide = P.wide;
+        opaque(wide);
         long long npix = p.npix;
         opaque_ptr(res); opaque_ptr(y); opaque_ptr(yhi); opaque_ptr(ylo); opaque(ldres); opaque(ldy); opaque(cpo);
         uint32_t dph = 0;
         for (uint32_t i = (uint32_t)s; i < cnt; i += 2) {
             const long long pix = (long long)(blockIdx.x + i * gridDim.x) * 128 + q * 32 + lane;
             const bool ok = pix < npix;
+            if (LN) {
+                // ---- LayerNorm of this pixel's row in registers (two-pass statistics like rcn_layernorm) -> A operand of fc1 in A1;
+                // group h writes the k-steps [j0, j0 + nj).  The next tile's rows are pulled into L2 meanwhile.
+                if (i + 2 < cnt) {
+                    const long long pn = pix + (long long)2 * gridDim.x * 128;
+                    if (pn < npix) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xln + pn * ldx));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(xln + pn * ldx + 32));
+                    }
+                }
+                float4 xv[16];
+#pragma unroll
+                for (int g = 0; g < 16; ++g) xv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                    const float4* xp = reinterpret_cast<const float4*>(xln + pix * ldx);
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) xv[g] = __ldg(xp + g);
+                }
+                float sm = 0.f;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) sm += (xv[g].x + xv[g].y) + (xv[g].z + xv[g].w);
+                const float mean = sm * (1.f / 64.f);
+                float sq = 0.f;
+#pragma unroll
+                for (int g = 0; g < 16; ++g) {
+                    const float dx = xv[g].x - mean, dy = xv[g].y - mean, dz = xv[g].z - mean, dw = xv[g].w - mean;
+                    sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+                }
+                const float rstd = rsqrtf(sq * (1.f / 64.f) + eps);
+                const int j0 = (MF_EWG == 2 && h == 1) ? 2 : 0, nj = 4 / MF_EWG;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j >= j0 && j < j0 + nj) {
+                        float val[16];
+                        uint32_t pk[16];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const float4 gg = lds4(c_g + 64u * j + 16u * g), be = lds4(c_be + 64u * j + 16u * g);
+                            const float4 xx = xv[4 * j + g];
+                            val[4 * g + 0] = (xx.x - mean) * rstd * gg.x + be.x;
+                            val[4 * g + 1] = (xx.y - mean) * rstd * gg.y + be.y;
+                            val[4 * g + 2] = (xx.z - mean) * rstd * gg.z + be.z;
+                            val[4 * g + 3] = (xx.w - mean) * rstd * gg.w + be.w;
+                        }
+                        split_pack16(val, pk);
+                        tmem_st16(A1 + 16u * j, pk);
+                    }
+                }
+                tmem_wait_st();
+                chain_arrive(arb, lane);
+            }
             // ---- fc1 halves: accumulator -> bias + GELU -> hi/lo pairs, in place
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
@@ -299,23 +381,38 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                     }
                     if (ok) {
                         if (y) {
-                            float4* yp = reinterpret_cast<float4*>(y + pix * ldy + c0 + 16 * b);
+                            float* yp = y + pix * ldy + c0 + 16 * b;
+                            if (wide) {
+                                uint32_t u[16];
 #pragma unroll
-                            for (int g = 0; g < 4; ++g) yp[g] = make_float4(val[4 * g], val[4 * g + 1], val[4 * g + 2], val[4 * g + 3]);
+                                for (int j = 0; j < 16; ++j) u[j] = __float_as_uint(val[j]);
+                                stg256(yp, u);
+                                stg256(yp + 8, u + 8);
+                            } else {
+#pragma unroll
+                                for (int g = 0; g < 4; ++g)
+                                    reinterpret_cast<float4*>(yp)[g] = make_float4(val[4 * g], val[4 * g + 1], val[4 * g + 2], val[4 * g + 3]);
+                            }
                         }
                         if (yhi) {
                             uint32_t pk[16];
                             split_pack16(val, pk);
                             const long long po = pix * cpo + c0 + 16 * b;
-                            stg128(yhi + po, pk[0], pk[1], pk[2], pk[3]);
-                            stg128(yhi + po + 8, pk[4], pk[5], pk[6], pk[7]);
-                            stg128(ylo + po, pk[8], pk[9], pk[10], pk[11]);
-                            stg128(ylo + po + 8, pk[12], pk[13], pk[14], pk[15]);
+                            if (wide) {
+                                stg256(yhi + po, pk);
+                                stg256(ylo + po, pk + 8);
+                            } else {
+                                stg128(yhi + po, pk[0], pk[1], pk[2], pk[3]);
+                                stg128(yhi + po + 8, pk[4], pk[5], pk[6], pk[7]);
+                                stg128(ylo + po, pk[8], pk[9], pk[10], pk[11]);
+                                stg128(ylo + po + 8, pk[12], pk[13], pk[14], pk[15]);
+                            }
                         }
                     }
                 }
             }
-            chain_arrive(arb, lane);     // D2 is drained: the slot may take its next tile
+            // D2 is drained: the slot may take its next tile.  With LN the groups' A1 arrivals of the next tile say so (program order)
+            if (!LN) chain_arrive(arb, lane);
         }
     }
     tc_fence_before();
@@ -342,12 +439,16 @@ bool make_rows_map(CUtensorMap* m, const void* base, long long rows, int cols, l
 using namespace rcn;
 
 extern "C" int rcn_mlp_fused(const rcn_mlp_desc* d, void* stream) {
-    RCN_CHECK_ARG(d && d->x_hi && d->x_lo && d->w1_hi && d->w1_lo && d->w2_hi && d->w2_lo && d->b1 && d->b2, "rcn_mlp_fused: null pointer");
+    const bool ln = d && d->x_ln != nullptr;
+    RCN_CHECK_ARG(d && (ln || (d->x_hi && d->x_lo)) && d->w1_hi && d->w1_lo && d->w2_hi && d->w2_lo && d->b1 && d->b2, "rcn_mlp_fused: null pointer");
     RCN_CHECK_ARG(d->C == MF_C && d->hidden == MF_HID, "rcn_mlp_fused: only C = 64, hidden = 256 is built (got %d, %d)", d->C, d->hidden);
     RCN_CHECK_ARG(d->npix > 0 && d->npix < (1ll << 31), "rcn_mlp_fused: bad pixel count");
     RCN_CHECK_ARG(d->y || d->y_hi, "rcn_mlp_fused: no output");
     auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-    RCN_CHECK_ARG(d->ldp_in >= MF_C && d->ldp_in % 8 == 0 && al16(d->x_hi) && al16(d->x_lo), "rcn_mlp_fused: input planes need a pixel stride >= 64 (multiple of 8), 16-byte aligned");
+    RCN_CHECK_ARG(ln || (d->ldp_in >= MF_C && d->ldp_in % 8 == 0 && al16(d->x_hi) && al16(d->x_lo)),
+                  "rcn_mlp_fused: input planes need a pixel stride >= 64 (multiple of 8), 16-byte aligned");
+    RCN_CHECK_ARG(!ln || (d->gamma && d->beta && d->ldx >= MF_C && d->ldx % 4 == 0 && al16(d->x_ln)),
+                  "rcn_mlp_fused: the LayerNorm input needs gamma, beta and 16-byte aligned rows");
     RCN_CHECK_ARG(!d->res || (d->ldres >= MF_C && d->ldres % 4 == 0 && al16(d->res)), "rcn_mlp_fused: residual must be 16-byte aligned rows");
     RCN_CHECK_ARG(!d->y || (d->ldy >= MF_C && d->ldy % 4 == 0 && al16(d->y)), "rcn_mlp_fused: output must be 16-byte aligned rows");
     RCN_CHECK_ARG(!d->y_hi || (d->y_lo && d->Cp_out >= MF_C && d->Cp_out % 8 == 0 && al16(d->y_hi) && al16(d->y_lo)),
@@ -357,21 +458,27 @@ extern "C" int rcn_mlp_fused(const rcn_mlp_desc* d, void* stream) {
     P.d = *d;
     const long long tiles = (d->npix + 127) / 128;
     P.total_tiles = (uint32_t)tiles;
+    auto al32 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 31) == 0; };
+    P.wide = (!d->y || (al32(d->y) && d->ldy % 8 == 0)) && (!d->y_hi || (al32(d->y_hi) && al32(d->y_lo) && d->Cp_out % 16 == 0));
     CUtensorMap ma_hi, ma_lo, m1h, m1l, m2h, m2l;
-    const bool ok = make_rows_map(&ma_hi, d->x_hi, d->npix, MF_C, d->ldp_in, 128) && make_rows_map(&ma_lo, d->x_lo, d->npix, MF_C, d->ldp_in, 128) &&
-                    make_rows_map(&m1h, d->w1_hi, MF_HID, MF_C, MF_C, 256) && make_rows_map(&m1l, d->w1_lo, MF_HID, MF_C, MF_C, 256) &&
+    bool ok = true;
+    if (!ln) ok = make_rows_map(&ma_hi, d->x_hi, d->npix, MF_C, d->ldp_in, 128) && make_rows_map(&ma_lo, d->x_lo, d->npix, MF_C, d->ldp_in, 128);
+    ok = ok && make_rows_map(&m1h, d->w1_hi, MF_HID, MF_C, MF_C, 256) && make_rows_map(&m1l, d->w1_lo, MF_HID, MF_C, MF_C, 256) &&
                     make_rows_map(&m2h, d->w2_hi, MF_C, MF_HID, MF_HID, 64) && make_rows_map(&m2l, d->w2_lo, MF_C, MF_HID, MF_HID, 64);
     RCN_CHECK_ARG(ok, "rcn_mlp_fused: cuTensorMapEncodeTiled failed");
+    if (ln) { ma_hi = m1h; ma_lo = m1l; }
     static bool attr_set[MAX_DEVICES] = {};
     const int dev = current_device();
     if (!attr_set[dev]) {
-        cudaFuncSetAttribute(mlp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(mlp_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(mlp_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         attr_set[dev] = true;
     }
-    const size_t smem = (size_t)MF_W1 + MF_W2 + MF_NA * MF_A + MF_CONST_FLOATS * 4 + 128 + 1024;
+    const size_t smem = (size_t)MF_W1 + MF_W2 + (ln ? 0 : MF_NA * MF_A) + MF_CONST_FLOATS * 4 + 128 + 1024;
     const int sms = sm_count();
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
-    mlp_fused_kernel<<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, m1h, m1l, m2h, m2l, P);
+    if (ln) mlp_fused_kernel<true><<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, m1h, m1l, m2h, m2l, P);
+    else mlp_fused_kernel<false><<<grid, MF_THREADS, smem, (cudaStream_t)stream>>>(ma_hi, ma_lo, m1h, m1l, m2h, m2l, P);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_mlp_fused");
     return RCN_OK;

@@ -225,6 +225,12 @@ __device__ __forceinline__ void stg128(void* p, uint32_t a, uint32_t b, uint32_t
     asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// 32 contiguous bytes (a full sector) per lane: 16 bf16 of one operand plane, or 8 floats
+__device__ __forceinline__ void stg256(void* p, const uint32_t* v) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]),
+                 "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
 __device__ __forceinline__ void chain_arrive(uint32_t bar, int lane) {
     tc_fence_before();
     __syncwarp();

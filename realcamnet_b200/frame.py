@@ -58,8 +58,12 @@ def _coder_pool() -> ThreadPoolExecutor:
     return _pool
 
 
-def batch_size_for(n_tiles: int, max_batch: int = 8) -> int:
-    """Largest divisor of n_tiles that is <= max_batch: equal batches, one captured graph per rank."""
+MAX_BATCH = int(os.environ.get("RCN_FRAME_MAX_BATCH", "8"))     # tiles per graph replay (a tile's streams do not depend on it)
+
+
+def batch_size_for(n_tiles: int, max_batch: int = 0) -> int:
+    """Largest divisor of n_tiles that is <= max_batch (default MAX_BATCH): equal batches, one captured graph per rank."""
+    max_batch = max_batch or MAX_BATCH
     for b in range(min(max_batch, n_tiles), 0, -1):
         if n_tiles % b == 0:
             return b
@@ -84,7 +88,7 @@ def _encode_tile(model, pending, n: int, B: int) -> Tuple[bytes, bytes]:
 
 
 @torch.no_grad()
-def compress_tiles(model, tiles: torch.Tensor, cond: torch.Tensor, coords: torch.Tensor, max_batch: int = 8):
+def compress_tiles(model, tiles: torch.Tensor, cond: torch.Tensor, coords: torch.Tensor, max_batch: int = 0):
     """tiles (n,4,T,T), cond (1,4,h,w), coords (n,2,T,T) on the model's device -> [(y_bytes, z_bytes, (zh, zw))] * n.
 
     Tiles are independent images, so they are pushed through the compress stage in equal batches of up to `max_batch` (one CUDA

@@ -545,24 +545,39 @@ def ingest_fused(coord_nchw, lsc_layers, slope, raw=None, conv_first=None, emit_
 _FUSED_MLP = os.environ.get("RCN_FUSED_MLP", "1") != "0"    # 0: fc1 and fc2 of the Swin MLP run as two conv launches (triage / A-B)
 
 
-def mlp_fused_ok(fc1, fc2, xsp) -> bool:
-    """Shapes rcn_mlp_fused serves: Linear(64, 256) -> GELU -> Linear(256, 64) on the bf16x3 engine, input as bf16 hi/lo planes."""
-    return (_FUSED_MLP and _ENGINE == "bf16x3" and xsp is not None and xsp.fmt == FMT_BF16 and xsp.lo is not None and xsp.key[7] == 1 and
-            tuple(fc1.weight.shape[:2]) == (256, 64) and tuple(fc2.weight.shape[:2]) == (64, 256) and fc1.bias is not None and
-            fc2.bias is not None and xsp.hi.shape[-1] == 64)
+def mlp_fused_ok(fc1, fc2, xsp=None, ln_x=None, ln=None) -> bool:
+    """Shapes rcn_mlp_fused serves: Linear(64, 256) -> GELU -> Linear(256, 64) on the bf16x3 engine; the input either as bf16 hi/lo
+    planes (xsp) or as the fp32 rows ln_x of the LayerNorm `ln` in front, which the kernel then applies itself."""
+    if not (_FUSED_MLP and _ENGINE == "bf16x3" and tuple(fc1.weight.shape[:2]) == (256, 64) and tuple(fc2.weight.shape[:2]) == (64, 256) and
+            fc1.bias is not None and fc2.bias is not None):
+        return False
+    if ln_x is not None:
+        return (_FUSED_MLP_LN and ln is not None and tuple(ln.normalized_shape) == (64,) and ln.weight is not None and ln.bias is not None and
+                ln_x.shape[-1] == 64 and ln_x.data_ptr() % 16 == 0 and geom(ln_x)[4] % 4 == 0)
+    return (xsp is not None and xsp.fmt == FMT_BF16 and xsp.lo is not None and xsp.key[7] == 1 and xsp.hi.shape[-1] == 64)
 
 
-def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True):
-    """models/tcm.py:225-236 as one kernel (rcn_mlp_fused): res + fc2(GELU(fc1(x))), x given as operand planes.
-    Returns (y | None, planes | None) like conv2d(emit_split=True)."""
-    N, H, W, C = xsp.hi.shape
+_FUSED_MLP_LN = os.environ.get("RCN_FUSED_MLP_LN", "1") != "0"     # 0: the LayerNorm in front of the fused MLP stays its own launch
+
+
+def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True, ln_x=None, ln=None):
+    """models/tcm.py:225-236 as one kernel (rcn_mlp_fused): res + fc2(GELU(fc1(x))); x given as operand planes (xsp), or as
+    ln(ln_x) with the LayerNorm applied inside the kernel (tcm.py:234).  Returns (y | None, planes | None) like conv2d(emit_split=True)."""
     p1, p2 = pack(fc1), pack(fc2)
     d = _C.MlpDesc()
-    d.x_hi, d.x_lo, d.ldp_in = xsp.hi.data_ptr(), xsp.lo.data_ptr(), plane_ld(xsp.hi)
+    if ln_x is not None:
+        N, H, W, C, ldx = geom(ln_x, "mlp_fused.ln_x")
+        g, b = ln.weight.detach(), ln.bias.detach()
+        d.x_ln, d.ldx, d.gamma, d.beta, d.eps = ln_x.data_ptr(), ldx, g.data_ptr(), b.data_ptr(), float(ln.eps)
+        dev_t = ln_x
+    else:
+        N, H, W, C = xsp.hi.shape
+        d.x_hi, d.x_lo, d.ldp_in = xsp.hi.data_ptr(), xsp.lo.data_ptr(), plane_ld(xsp.hi)
+        dev_t = xsp.hi
     d.npix, d.C, d.hidden = N * H * W, 64, 256
     d.w1_hi, d.w1_lo, d.b1 = p1.w_hi.data_ptr(), p1.w_lo.data_ptr(), p1.bias.data_ptr()
     d.w2_hi, d.w2_lo, d.b2 = p2.w_hi.data_ptr(), p2.w_lo.data_ptr(), p2.bias.data_ptr()
-    _on_current_device(xsp.hi, "mlp_fused.x")
+    _on_current_device(dev_t, "mlp_fused.x")
     if res is not None:
         rN, rH, rW, rC, ldr = geom(res, "mlp_fused.res")
         if (rN, rH, rW, rC) != (N, H, W, 64):
@@ -571,7 +586,7 @@ def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True)
     want_out = keep_fp32 or split_out is None or out is not None
     if want_out:
         if out is None:
-            out = torch.empty((N, H, W, 64), device=xsp.hi.device, dtype=torch.float32)
+            out = torch.empty((N, H, W, 64), device=dev_t.device, dtype=torch.float32)
         oN, oH, oW, oC, ldy = geom(out, "mlp_fused.out")
         if (oN, oH, oW, oC) != (N, H, W, 64):
             raise ValueError("mlp_fused: output geometry mismatch")

@@ -85,6 +85,11 @@ class Block(nn.Module):
         split_out / keep_fp32: also / only write the block output as planes for the layer that reads it."""
         t, tsp = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps, emit_split=True)
         x1 = self.msa._f(t, res=x, presplit=tsp)
+        if ops.mlp_fused_ok(self.mlp[0], self.mlp[2], ln_x=x1, ln=self.ln2):
+            # one kernel (csrc/mlp.cu): LayerNorm in registers, its result is fc1's A operand in tensor memory, the 4C-wide hidden
+            # activations stay there too
+            return ops.mlp_fused(None, self.mlp[0], self.mlp[2], res=x1, out=out, split_out=split_out, keep_fp32=keep_fp32,
+                                 ln_x=x1, ln=self.ln2)[0]
         t, tsp = ops.layernorm(x1, self.ln2.weight, self.ln2.bias, self.ln2.eps, emit_split=True)
         if ops.mlp_fused_ok(self.mlp[0], self.mlp[2], tsp):
             # one kernel (csrc/mlp.cu): the 4C-wide hidden activations stay in tensor memory

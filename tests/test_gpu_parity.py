@@ -499,10 +499,28 @@ def test_fused_swin_mlp_matches_reference(dev, shape):
         torch.cuda.synchronize()
         assert torch.equal(y2, y) and float(wide[..., 64:].abs().max()) == 0.0
         assert rel(csp.hi[..., 64:].float() + csp.lo[..., 64:].float(), ref) < CONV_TOL
+        # rows that are only 16-byte aligned (128-bit store path)
+        odd = torch.zeros(N, H, W, 132, device=dev)
+        y2b, _ = ops.mlp_fused(tsp, fc1, fc2, res=rd[..., 64:], out=odd[..., 4:68])
+        assert torch.equal(y2b, y)
         # planes only, no residual
         y3, sp3 = ops.mlp_fused(tsp, fc1, fc2, split_out=ops.alloc_planes(N, H, W, 64, dev), keep_fp32=False)
         assert y3 is None
         assert rel(sp3.hi.float() + sp3.lo.float(), ref - xres[..., 64:]) < CONV_TOL
+        # LayerNorm inside the kernel (tcm.py:234): x1 rows are a channel slice of a wider tensor and double as the residual
+        ln = torch.nn.LayerNorm(64)
+        weights.fill_(ln, seed=13)
+        x1 = xres[..., 64:]
+        ref_ln = x1 + F.linear(F.gelu(F.linear(F.layer_norm(x1, (64,), ln.weight, ln.bias, ln.eps), fc1.weight.cpu(), fc1.bias.cpu())),
+                               fc2.weight.cpu(), fc2.bias.cpu())
+        ln = ln.to(dev)
+        assert ops.mlp_fused_ok(fc1, fc2, ln_x=rd[..., 64:], ln=ln)
+        csp5 = ops.alloc_planes(N, H, W, 64, dev)
+        y5, sp5 = ops.mlp_fused(None, fc1, fc2, res=rd[..., 64:], split_out=csp5, keep_fp32=True, ln_x=rd[..., 64:], ln=ln)
+        assert rel(y5, ref_ln) < CONV_TOL and rel(sp5.hi.float() + sp5.lo.float(), ref_ln) < CONV_TOL
+        t6, tsp6 = ops.layernorm(rd[..., 64:], ln.weight, ln.bias, ln.eps, emit_split=True)
+        y6, _ = ops.mlp_fused(tsp6, fc1, fc2, res=rd[..., 64:])
+        assert rel(y5, y6) < 2e-5
         # the two-launch path of the same engine
         h, hsp = fc1._f(td, act=ops.ACT_GELU, emit_split=True, keep_fp32=False, presplit=tsp)
         y4 = fc2._f(h, res=rd[..., 64:], presplit=hsp)
