@@ -306,6 +306,20 @@ typedef struct rcn_mlp_desc {
 } rcn_mlp_desc;
 int rcn_mlp_fused(const rcn_mlp_desc* d, void* stream);
 
+/* ---- fused LayerNorm + Linear ----------------------------------------------------------------------------- */
+/* y = Linear(nn.LayerNorm(C)(x)) for C = 64 as ONE kernel (csrc/lnlinear.cu): models/tcm.py:233 + 193, the qkv embedding of the
+ * Swin blocks (`self.msa(self.ln1(x))` -> `self.embedding_layer`).  The normalised row never leaves the SM: it is written as the
+ * bf16 hi/lo tcgen05 A operand into tensor memory.  x, y: fp32 rows (pixel strides ldx, ldy); w_hi / w_lo: [Cout][64] bf16
+ * (rcn_pack_conv_weight_tc, Cp = 64); Cout a multiple of 16, <= 192; bias may be NULL.  bf16x3 arithmetic. */
+typedef struct rcn_lnlinear_desc {
+    const float* x; int ldx; long long npix;
+    int C, Cout;
+    const float* gamma; const float* beta; float eps;
+    const void* w_hi; const void* w_lo; const float* bias;
+    float* y; int ldy;
+} rcn_lnlinear_desc;
+int rcn_ln_linear_fused(const rcn_lnlinear_desc* d, void* stream);
+
 /* perf triage only (RCN_TC_DEBUG bit 128): cycles one epilogue warp of CTA 0 spent {waiting for accumulators, working},
  * tiles seen, 0.  reset != 0 clears the counters. */
 int rcn_tc_prof(unsigned long long* out16, int reset);

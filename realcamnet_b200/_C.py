@@ -56,6 +56,16 @@ class MlpDesc(ctypes.Structure):
     ]
 
 
+class LnLinearDesc(ctypes.Structure):
+    """struct rcn_lnlinear_desc"""
+    _fields_ = [
+        ("x", c_void_p), ("ldx", c_int), ("npix", c_longlong), ("C", c_int), ("Cout", c_int),
+        ("gamma", c_void_p), ("beta", c_void_p), ("eps", c_float),
+        ("w_hi", c_void_p), ("w_lo", c_void_p), ("bias", c_void_p),
+        ("y", c_void_p), ("ldy", c_int),
+    ]
+
+
 _P, _I, _L, _F = c_void_p, c_int, c_longlong, c_float
 
 # name -> (restype, argtypes); must list every symbol of include/rcn_b200.h (tests check this)
@@ -71,6 +81,7 @@ PROTOTYPES = {
     "rcn_tc_prof": (_I, [_P, _I]),
     "rcn_ingest_fused": (_I, [POINTER(IngestDesc), _P]),
     "rcn_mlp_fused": (_I, [POINTER(MlpDesc), _P]),
+    "rcn_ln_linear_fused": (_I, [POINTER(LnLinearDesc), _P]),
     "rcn_pack_ingest_weight": (_I, [_P, _P, _P, _P]),
     "rcn_pack_conv_weight": (_I, [_P, _I, _I, _I, _P, _P]),
     "rcn_layernorm": (_I, [_P, _L, _I, _I, _P, _P, _F, _P, _I, _I, _P, _P, _I, _P]),

@@ -486,6 +486,53 @@ def wmsa(qkv, relpos, head_dim, ws, shifted, out=None, emit_split=False):
 
 # ----------------------------------------------------------------------------- layout
 
+# ----------------------------------------------------------------------------- independent branches on two streams
+# 0: branches run one after the other (triage / A-B)
+_CONCURRENT_BRANCHES = os.environ.get("RCN_CONCURRENT_BRANCHES", "1") != "0"
+_side_streams = {}
+_fork_path = ""      # position in the tree of nested fork_join calls ("" = not inside one): one side stream per position
+
+
+def fork_join(fa, fb, dev):
+    """fa() on the current stream, fb() concurrently on a side stream, joined before returning (ra, rb).
+
+    The entropy-parameter networks are chains of launches on 128^2 / 64^2 maps: one wave of <= 128 CTAs each, bound by launch
+    latency and prologue / drain, not by throughput.  Independent chains (mean / scale halves, models/raw2bit.py:1812-1828; the two
+    branches of an attention gate, compressai AttentionBlock) are issued on two streams so that the block scheduler starts one
+    chain's next kernel while the other chain's CTAs drain.  Inside a CUDA-graph capture the fork / join events become parallel
+    branches of the graph.  Same kernels, same arithmetic: results are bit-identical to the serial order.  Nested calls get a side
+    stream of their own per position in the call tree."""
+    global _fork_path
+    if not _CONCURRENT_BRANCHES or dev.type != "cuda":
+        return fa(), fb()
+    cur = torch.cuda.current_stream(dev)
+    path = _fork_path
+    key = (dev.index, path)
+    side = _side_streams.get(key)
+    if side is None:
+        side = _side_streams[key] = torch.cuda.Stream(device=dev)
+    fork, join = torch.cuda.Event(), torch.cuda.Event()
+    fork.record(cur)
+    side.wait_event(fork)
+    try:
+        _fork_path = path + "b"
+        with torch.cuda.stream(side):
+            rb = fb()
+            join.record(side)
+        _fork_path = path + "a"
+        ra = fa()
+    finally:
+        _fork_path = path
+    cur.wait_event(join)
+    if not torch.cuda.is_current_stream_capturing():
+        # rb was allocated on the side stream and is consumed on the current one: tell the caching allocator (eager mode; a
+        # capture's private pool never recycles during the capture)
+        for t in (rb if isinstance(rb, (tuple, list)) else (rb,)):
+            if torch.is_tensor(t):
+                t.record_stream(cur)
+    return ra, rb
+
+
 # ----------------------------------------------------------------------------- fused packed-Bayer ingest
 _FUSED_INGEST = os.environ.get("RCN_FUSED_INGEST", "1") != "0"    # 0: the lens-shading MLP and conv_first run layer by layer (triage / A-B)
 
@@ -557,7 +604,10 @@ def mlp_fused_ok(fc1, fc2, xsp=None, ln_x=None, ln=None) -> bool:
     return (xsp is not None and xsp.fmt == FMT_BF16 and xsp.lo is not None and xsp.key[7] == 1 and xsp.hi.shape[-1] == 64)
 
 
-_FUSED_MLP_LN = os.environ.get("RCN_FUSED_MLP_LN", "1") != "0"     # 0: the LayerNorm in front of the fused MLP stays its own launch
+# 1: the LayerNorm in front of the fused MLP runs inside it (A operand of fc1 built in tensor memory).  Correct and tested, but OFF by
+# default: measured at step level it costs 0.5 ms (54.5 against 54.0 ms) -- the streaming LayerNorm kernel runs near the HBM roofline,
+# while inside the chain kernel it adds a serial phase (row loads, statistics, tcgen05.st, hand-over) to every tile slot.
+_FUSED_MLP_LN = os.environ.get("RCN_FUSED_MLP_LN", "0") != "0"
 
 
 def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True, ln_x=None, ln=None):
@@ -597,6 +647,40 @@ def mlp_fused(xsp, fc1, fc2, res=None, out=None, split_out=None, keep_fp32=True,
         d.y_hi, d.y_lo, d.Cp_out = split_out.hi.data_ptr(), split_out.lo.data_ptr(), plane_ld(split_out.hi)
     _C.check(_C.lib().rcn_mlp_fused(ctypes.byref(d), _stream()), "rcn_mlp_fused")
     return (out if want_out else None), split_out
+
+# 1: LayerNorm + qkv embedding as one kernel (csrc/lnlinear.cu).  Correct and tested, OFF by default: no gain at step level (54.0 against
+# 53.8 ms), for the same reason as _FUSED_MLP_LN.
+_FUSED_LN_LINEAR = os.environ.get("RCN_FUSED_LN_LINEAR", "0") != "0"
+
+
+def ln_linear_ok(x, ln, fc) -> bool:
+    """Shapes rcn_ln_linear_fused serves: Linear(64, Cout <= 192, Cout % 16 == 0) of a LayerNorm(64), bf16x3 engine, fp32 rows."""
+    if not (_FUSED_LN_LINEAR and _ENGINE == "bf16x3" and x is not None):
+        return False
+    w = fc.weight
+    return (tuple(ln.normalized_shape) == (64,) and ln.weight is not None and ln.bias is not None and w.shape[1] == 64 and
+            w.shape[0] % 16 == 0 and w.shape[0] <= 192 and x.shape[-1] == 64 and x.data_ptr() % 16 == 0 and geom(x)[4] % 4 == 0)
+
+
+def ln_linear(x, ln, fc, out=None):
+    """models/tcm.py:233 + 193 as one kernel (rcn_ln_linear_fused): fc(ln(x)) with the normalised rows as the tcgen05 A operand in
+    tensor memory.  x: (N,H,W,64) fp32 NHWC / channel slice; returns (N,H,W,Cout) fp32."""
+    N, H, W, C, ldx = geom(x, "ln_linear.x")
+    pc = pack(fc)
+    if out is None:
+        out = torch.empty((N, H, W, pc.cout), device=x.device, dtype=torch.float32)
+    oN, oH, oW, oC, ldy = geom(out, "ln_linear.out")
+    if (oN, oH, oW, oC) != (N, H, W, pc.cout):
+        raise ValueError("ln_linear: output geometry mismatch")
+    d = _C.LnLinearDesc()
+    d.x, d.ldx, d.npix, d.C, d.Cout = x.data_ptr(), ldx, N * H * W, 64, pc.cout
+    g, b = ln.weight.detach(), ln.bias.detach()
+    d.gamma, d.beta, d.eps = g.data_ptr(), b.data_ptr(), float(ln.eps)
+    d.w_hi, d.w_lo = pc.w_hi.data_ptr(), pc.w_lo.data_ptr()
+    d.bias = pc.bias.data_ptr() if pc.bias is not None else None
+    d.y, d.ldy = out.data_ptr(), ldy
+    _C.check(_C.lib().rcn_ln_linear_fused(ctypes.byref(d), _stream()), "rcn_ln_linear_fused")
+    return out
 
 
 def to_nhwc(x, out=None):

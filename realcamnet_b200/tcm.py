@@ -52,9 +52,11 @@ class WMSA(nn.Module):
             p.view(2 * window_size - 1, 2 * window_size - 1, self.n_heads).transpose(1, 2).transpose(0, 1).contiguous())
         self.linear = Linear(input_dim, output_dim)
 
-    def _f(self, x, res=None, out=None, presplit=None):
-        """x may be None when `presplit` carries its operand planes (LayerNorm output)."""
-        qkv = self.embedding_layer._f(x, presplit=presplit)
+    def _f(self, x, res=None, out=None, presplit=None, qkv=None):
+        """x may be None when `presplit` carries its operand planes (LayerNorm output), or when the caller already ran the
+        embedding (qkv: the fused LayerNorm + embedding kernel of Block._f)."""
+        if qkv is None:
+            qkv = self.embedding_layer._f(x, presplit=presplit)
         rel = self.relative_position_params
         if not rel.is_contiguous():
             rel = rel.contiguous()
@@ -83,8 +85,12 @@ class Block(nn.Module):
     def _f(self, x, out=None, split_out=None, keep_fp32=True):
         """LayerNorm and attention outputs only exist as the next contraction's bf16 operand planes (tcgen05 engine).
         split_out / keep_fp32: also / only write the block output as planes for the layer that reads it."""
-        t, tsp = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps, emit_split=True)
-        x1 = self.msa._f(t, res=x, presplit=tsp)
+        if ops.ln_linear_ok(x, self.ln1, self.msa.embedding_layer):
+            # one kernel (csrc/lnlinear.cu): LayerNorm in registers -> A operand in tensor memory -> qkv embedding
+            x1 = self.msa._f(None, res=x, qkv=ops.ln_linear(x, self.ln1, self.msa.embedding_layer))
+        else:
+            t, tsp = ops.layernorm(x, self.ln1.weight, self.ln1.bias, self.ln1.eps, emit_split=True)
+            x1 = self.msa._f(t, res=x, presplit=tsp)
         if ops.mlp_fused_ok(self.mlp[0], self.mlp[2], ln_x=x1, ln=self.ln2):
             # one kernel (csrc/mlp.cu): LayerNorm in registers, its result is fc1's A operand in tensor memory, the 4C-wide hidden
             # activations stay there too
@@ -101,6 +107,11 @@ class Block(nn.Module):
 
     def forward(self, x):
         return self._f(x.contiguous())
+
+
+# maps up to this many pixels fill at most one or two waves of CTAs: their layers are latency bound, and independent branches are issued
+# on two streams (ops.fork_join); larger maps are throughput bound and keep the serial order
+SMALL_MAP_PIXELS = 256 * 256
 
 
 class ConvTransBlock(nn.Module):
@@ -133,9 +144,14 @@ class ConvTransBlock(nn.Module):
         both, bsp = self.conv1_1._f(x, presplit=presplit, emit_split=True)
         N, H, W, _ = both.shape
         csp = ops.alloc_planes(N, H, W, cd + td, both.device)
-        self.conv_block._f(both[..., :cd], extra_identity=True, presplit=bsp.channels(0, cd), split_out=csp.channels(0, cd),
-                           keep_fp32=False)
-        self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
+        conv_half = lambda: self.conv_block._f(both[..., :cd], extra_identity=True, presplit=bsp.channels(0, cd),
+                                               split_out=csp.channels(0, cd), keep_fp32=False)
+        trans_half = lambda: self.trans_block._f(both[..., cd:], split_out=csp.channels(cd, cd + td), keep_fp32=False)
+        if N * H * W <= SMALL_MAP_PIXELS:      # latency-bound maps (hyper-prior nets): the two halves on two streams
+            ops.fork_join(trans_half, conv_half, both.device)
+        else:
+            conv_half()
+            trans_half()
         return self.conv1_2._f(None, res=x, out=out, presplit=csp, emit_split=emit_split)
 
     def forward(self, x):
@@ -180,11 +196,22 @@ class SWAtten(AttentionBlock):
     def _f(self, x, out=None):
         if self._has_io:
             x = self.in_conv._f(x)
-        z = self.non_local_block._f(x)
-        if self._has_io:
-            g = self._gate(x, z, x)
-            return self.out_conv._f(g, out=out)
-        return self._gate(x, z, x, out=out)
+
+        def branch_a():                     # conv_a(x): three ResidualUnits
+            a = x
+            for i in range(3):
+                a = self.conv_a[i]._f(a)
+            return a
+
+        def branch_b():                     # conv_b(non_local_block(x)) up to the gate: independent of branch a (ops.fork_join)
+            b = self.non_local_block._f(x)
+            for i in range(3):
+                b = self.conv_b[i]._f(b)
+            return b
+
+        a, b = ops.fork_join(branch_a, branch_b, x.device)
+        g = self.conv_b[3]._f(b, epi=ops.EPI_SIGMOID_GATE, aux=a, res=x, out=None if self._has_io else out)
+        return self.out_conv._f(g, out=out) if self._has_io else g
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
@@ -292,8 +319,8 @@ class SliceCodecModel(CompressionModel):
         tot = 320 + (320 // self.num_slices) * self.num_slices
         ms = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_means] + y_hat_slices)
         ss = ops.empty(N, h, w, tot, like=z_hat)      # cat([latent_scales] + y_hat_slices)
-        self._h_s(self.h_scale_s, z_hat, ss[..., :320])
-        self._h_s(self.h_mean_s, z_hat, ms[..., :320])
+        ops.fork_join(lambda: self._h_s(self.h_mean_s, z_hat, ms[..., :320]),
+                           lambda: self._h_s(self.h_scale_s, z_hat, ss[..., :320]), z_hat.device)
         return ms, ss, h, w
 
     def _slice_params(self, i, ms, ss):
@@ -302,10 +329,16 @@ class SliceCodecModel(CompressionModel):
         cin = 320 + sl * min(i, self.max_support_slices if self.max_support_slices >= 0 else i)
         N, h, w, _ = ms.shape
         lrp_sup = ops.empty(N, h, w, cin + sl, like=ms)                 # cat([mean_support, y_hat_slice])
-        mean_support = self.atten_mean[i][0]._f(ms[..., :cin], out=lrp_sup[..., :cin])
-        mu = _run_cc(self.cc_mean_transforms[i], mean_support)
-        scale_support = self.atten_scale[i][0]._f(ss[..., :cin])
-        scale = _run_cc(self.cc_scale_transforms[i], scale_support)
+
+        def mean_branch():
+            mean_support = self.atten_mean[i][0]._f(ms[..., :cin], out=lrp_sup[..., :cin])
+            return _run_cc(self.cc_mean_transforms[i], mean_support)
+
+        def scale_branch():
+            scale_support = self.atten_scale[i][0]._f(ss[..., :cin])
+            return _run_cc(self.cc_scale_transforms[i], scale_support)
+
+        mu, scale = ops.fork_join(mean_branch, scale_branch, ms.device)
         return lrp_sup, cin, mu, scale
 
     def _finish_slice(self, i, lrp_sup, cin, ms, ss):

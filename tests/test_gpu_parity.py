@@ -514,6 +514,7 @@ def test_fused_swin_mlp_matches_reference(dev, shape):
         ref_ln = x1 + F.linear(F.gelu(F.linear(F.layer_norm(x1, (64,), ln.weight, ln.bias, ln.eps), fc1.weight.cpu(), fc1.bias.cpu())),
                                fc2.weight.cpu(), fc2.bias.cpu())
         ln = ln.to(dev)
+        ops._FUSED_MLP_LN = True          # off by default (no step-level gain); the kernel variant is tested regardless
         assert ops.mlp_fused_ok(fc1, fc2, ln_x=rd[..., 64:], ln=ln)
         csp5 = ops.alloc_planes(N, H, W, 64, dev)
         y5, sp5 = ops.mlp_fused(None, fc1, fc2, res=rd[..., 64:], split_out=csp5, keep_fp32=True, ln_x=rd[..., 64:], ln=ln)
@@ -521,11 +522,47 @@ def test_fused_swin_mlp_matches_reference(dev, shape):
         t6, tsp6 = ops.layernorm(rd[..., 64:], ln.weight, ln.bias, ln.eps, emit_split=True)
         y6, _ = ops.mlp_fused(tsp6, fc1, fc2, res=rd[..., 64:])
         assert rel(y5, y6) < 2e-5
+        ops._FUSED_MLP_LN = False
         # the two-launch path of the same engine
         h, hsp = fc1._f(td, act=ops.ACT_GELU, emit_split=True, keep_fp32=False, presplit=tsp)
         y4 = fc2._f(h, res=rd[..., 64:], presplit=hsp)
         assert rel(y, y4) < 2e-5
     finally:
+        ops.set_engine(old)
+
+
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 16, 64), (1, 256, 320), (1, 8, 9)])
+@pytest.mark.parametrize("cout", [192, 64, 48])
+def test_fused_ln_linear_matches_reference(dev, shape, cout):
+    """rcn_ln_linear_fused (Linear(LayerNorm(x)), models/tcm.py:233 + 193) against torch fp32 and the two-launch product path."""
+    from realcamnet_b200 import ops
+    from realcamnet_b200.layers import Linear
+
+    N, H, W = shape
+    g = torch.Generator().manual_seed(H * 5 + W + cout)
+    ln, fc = torch.nn.LayerNorm(64), Linear(64, cout)
+    weights.fill_(ln, seed=21)
+    weights.fill_(fc, seed=22)
+    wide = torch.randn(N, H, W, 128, generator=g) * 3 + 0.5
+    x = wide[..., 64:]
+    ref = F.linear(F.layer_norm(x, (64,), ln.weight, ln.bias, ln.eps), fc.weight, fc.bias)
+    ln, fc = ln.to(dev), fc.to(dev)
+    old = ops.get_engine()
+    ops.set_engine("bf16x3")
+    try:
+        xd = wide.to(dev)[..., 64:]
+        ops._FUSED_LN_LINEAR = True       # off by default (no step-level gain); the kernel is tested regardless
+        assert ops.ln_linear_ok(xd, ln, fc)
+        y = ops.ln_linear(xd, ln, fc)
+        assert rel(y, ref) < CONV_TOL
+        odd = torch.zeros(N, H, W, cout + 4, device=dev)       # rows that are only 16-byte aligned
+        y2 = ops.ln_linear(xd, ln, fc, out=odd[..., 4:])
+        assert torch.equal(y2, y) and float(odd[..., :4].abs().max()) == 0.0
+        t, tsp = ops.layernorm(xd, ln.weight, ln.bias, ln.eps, emit_split=True)
+        y3 = fc._f(t, presplit=tsp)
+        assert rel(y, y3) < 2e-5
+    finally:
+        ops._FUSED_LN_LINEAR = False
         ops.set_engine(old)
 
 
