@@ -200,9 +200,13 @@ class AttentionBlock(_Block):
                                           nn.ReLU(inplace=True), conv1x1(N // 2, N))
                 self.relu = nn.ReLU(inplace=True)
 
-            def _f(self, x):
-                t, sp = self.conv[0]._f(x, act=ACT_RELU, emit_split=True, keep_fp32=False)
+            def _f(self, x, presplit=None, emit_split=False):
+                """presplit: operand planes of x from its producer; emit_split: returns (y, planes of y | None) so that a chain of
+                units (and the 1x1 layer after it) needs no rcn_split_bf16 pass between them."""
+                t, sp = self.conv[0]._f(x, act=ACT_RELU, emit_split=True, keep_fp32=False, presplit=presplit)
                 t, sp = self.conv[2]._f(t, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+                if emit_split:
+                    return self.conv[4]._f(t, res=x, res_pre=True, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=True)
                 return self.conv[4]._f(t, res=x, res_pre=True, act=ACT_RELU, presplit=sp)
 
         self.conv_a = nn.Sequential(ResidualUnit(), ResidualUnit(), ResidualUnit())
@@ -211,10 +215,14 @@ class AttentionBlock(_Block):
     def _gate(self, x, z, identity, out=None):
         """conv_a(x) * sigmoid(conv_b(z)) + identity"""
         a, b = x, z
-        for i in range(3):
-            a = self.conv_a[i]._f(a)
-            b = self.conv_b[i]._f(b)
-        return self.conv_b[3]._f(b, epi=EPI_SIGMOID_GATE, aux=a, res=identity, out=out)
+        asp = bsp = None
+        for i in range(3):      # unit -> unit -> 1x1 hand-over as operand planes (no rcn_split_bf16 pass in between)
+            if i < 2:
+                a, asp = self.conv_a[i]._f(a, presplit=asp, emit_split=True)
+            else:
+                a = self.conv_a[i]._f(a, presplit=asp)
+            b, bsp = self.conv_b[i]._f(b, presplit=bsp, emit_split=True)
+        return self.conv_b[3]._f(b, epi=EPI_SIGMOID_GATE, aux=a, res=identity, out=out, presplit=bsp)
 
     def _f(self, x):
         return self._gate(x, x, x)

@@ -197,21 +197,27 @@ class SWAtten(AttentionBlock):
         if self._has_io:
             x = self.in_conv._f(x)
 
+        # ResidualUnit -> ResidualUnit -> 1x1 hand their results over as operand planes (no rcn_split_bf16 pass in between)
         def branch_a():                     # conv_a(x): three ResidualUnits
-            a = x
+            a, sp = x, None
             for i in range(3):
-                a = self.conv_a[i]._f(a)
+                if i < 2:
+                    a, sp = self.conv_a[i]._f(a, presplit=sp, emit_split=True)
+                else:
+                    a = self.conv_a[i]._f(a, presplit=sp)
             return a
 
         def branch_b():                     # conv_b(non_local_block(x)) up to the gate: independent of branch a (ops.fork_join)
-            b = self.non_local_block._f(x)
+            b, sp = self.non_local_block._f(x), None
             for i in range(3):
-                b = self.conv_b[i]._f(b)
-            return b
+                b, sp = self.conv_b[i]._f(b, presplit=sp, emit_split=True)
+            return b, sp
 
-        a, b = ops.fork_join(branch_a, branch_b, x.device)
-        g = self.conv_b[3]._f(b, epi=ops.EPI_SIGMOID_GATE, aux=a, res=x, out=None if self._has_io else out)
-        return self.out_conv._f(g, out=out) if self._has_io else g
+        a, (b, bsp) = ops.fork_join(branch_a, branch_b, x.device)
+        if self._has_io:
+            g, gsp = self.conv_b[3]._f(b, epi=ops.EPI_SIGMOID_GATE, aux=a, res=x, presplit=bsp, emit_split=True, keep_fp32=False)
+            return self.out_conv._f(g, out=out, presplit=gsp)
+        return self.conv_b[3]._f(b, epi=ops.EPI_SIGMOID_GATE, aux=a, res=x, out=out, presplit=bsp)
 
     def forward(self, x):
         return ops.to_nchw(self._f(ops.to_nhwc(x)))
