@@ -294,8 +294,29 @@ def main():
     def step_resident():
         return model(x_dev, emit_strings=True)
 
+    # End to end: every step copies ITS inputs from pinned host memory and ends with the bitstream bytes on the host.  The copy of step
+    # k + 1's inputs is issued on a copy stream before step k's forward, so it overlaps with compute (an input pipeline around the
+    # public call model(x, emit_strings=True)); K timed steps still contain K host->device copies (the one primed before the
+    # timed region replaces the one issued for the step after the last).
+    copy_stream = torch.cuda.Stream(device=dev)
+    prefetched = []
+
+    def prefetch():
+        cur = torch.cuda.current_stream(dev)
+        with torch.cuda.stream(copy_stream):
+            xs = [t.to(dev, non_blocking=True) for t in x_host]
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        for t in xs:
+            t.record_stream(cur)
+        prefetched.append((xs, ev))
+
     def step_e2e():
-        xs = [t.to(dev, non_blocking=True) for t in x_host]
+        if not prefetched:
+            prefetch()
+        xs, ev = prefetched.pop(0)
+        torch.cuda.current_stream(dev).wait_event(ev)
+        prefetch()                                 # next step's inputs travel while this step computes
         out = model(xs, emit_strings=True)
         return out["strings"]                      # bitstream bytes live on the host
 
@@ -503,7 +524,8 @@ def main():
                            "cuda_graphs": not args.no_graphs, "parallelism": f"tile-sharded x{world}",
                            "l2_policy": "inputs and activations (>2 GB per layer) exceed the 126 MB L2; no explicit flush",
                            "bitstream_bytes": nbytes, "symbols": nsym,
-                           "e2e_outputs": "bitstream bytes on the host; x_hat (3 x 2T x 2T fp32) is computed every step but stays on the device"},
+                           "e2e_outputs": "bitstream bytes on the host; x_hat (3 x 2T x 2T fp32) is computed every step but stays on the device",
+                           "e2e_inputs": "pinned host -> device copy of every step's inputs, issued one step ahead on a copy stream"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "gpu_launches_note": "kernel nodes executed inside the timed region (eager launches + nodes of the replayed CUDA graphs)",
                 "e2e": {"value": e2e, "unit": "MP/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

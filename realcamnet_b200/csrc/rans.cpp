@@ -309,7 +309,7 @@ extern "C" int rcn_rans_decode(rcn_rans_decoder* d, const int32_t* indexes, long
         const int32_t* row = cdfs + (long long)ci * cdf_stride;
         const uint32_t cum = (uint32_t)(x & 0xFFFFu);
         // symbol s with row[s] <= cum < row[s+1] (rows are strictly increasing): start from the bucket table, walk forward
-        int s = lut[(size_t)ci * kLutSize + (cum >> kLutShift)];
+        int s = lut[(size_t)ci * rcn_rans_decoder::kLutSize + (cum >> rcn_rans_decoder::kLutShift)];
         while (row[s + 1] <= (int32_t)cum) ++s;
         const uint32_t start = (uint32_t)row[s], freq = (uint32_t)(row[s + 1] - row[s]);
         x = (uint64_t)freq * (x >> kProbBits) + cum - start;

@@ -329,8 +329,8 @@ class SliceCodecModel(CompressionModel):
                            lambda: self._h_s(self.h_scale_s, z_hat, ss[..., :320]), z_hat.device)
         return ms, ss, h, w
 
-    def _slice_params(self, i, ms, ss):
-        """raw2bit.py:1818-1828: returns (lrp_support buffer, mu, scale)."""
+    def _slice_branches(self, i, ms, ss):
+        """raw2bit.py:1818-1828 as two independent chains: returns (lrp_support buffer, cin, mean_branch, scale_branch)."""
         sl = 320 // self.num_slices
         cin = 320 + sl * min(i, self.max_support_slices if self.max_support_slices >= 0 else i)
         N, h, w, _ = ms.shape
@@ -344,6 +344,11 @@ class SliceCodecModel(CompressionModel):
             scale_support = self.atten_scale[i][0]._f(ss[..., :cin])
             return _run_cc(self.cc_scale_transforms[i], scale_support)
 
+        return lrp_sup, cin, mean_branch, scale_branch
+
+    def _slice_params(self, i, ms, ss):
+        """returns (lrp_support buffer, cin, mu, scale); the two chains are parallel branches of a captured graph (ops.fork_join)"""
+        lrp_sup, cin, mean_branch, scale_branch = self._slice_branches(i, ms, ss)
         mu, scale = ops.fork_join(mean_branch, scale_branch, ms.device)
         return lrp_sup, cin, mu, scale
 
@@ -461,10 +466,19 @@ class SliceCodecModel(CompressionModel):
         dec = RansDecoder()
         dec.set_stream(strings[0][0])
         idx = torch.empty((N, sl, h, w), device=z_hat.device, dtype=torch.int32)
+        idx_host = torch.empty((N, sl, h, w), dtype=torch.int32, pin_memory=True)
+        ready = torch.cuda.Event()
         for i in range(self.num_slices):
-            lrp_sup, cin, mu, scale = self._slice_params(i, ms, ss)
+            # The host decoder only needs the indexes, i.e. the SCALE chain: it runs first and its indexes travel while the GPU
+            # works through the mean chain, which the host queues before it blocks on the copy and decodes the slice.
+            lrp_sup, cin, mean_branch, scale_branch = self._slice_branches(i, ms, ss)
+            scale = scale_branch()
             ops.build_indexes(scale, table, idx, gc._scale_bound)
-            rv = dec.decode_stream(idx.cpu().numpy(), cdf, length, offset)
+            idx_host.copy_(idx, non_blocking=True)
+            ready.record()
+            mu = mean_branch()
+            ready.synchronize()
+            rv = dec.decode_stream(idx_host.numpy(), cdf, length, offset)
             rv = torch.from_numpy(rv).to(z_hat.device)
             ops.gaussian_dequantize(rv, mu, lrp_sup[..., cin:])
             self._finish_slice(i, lrp_sup, cin, ms, ss)
