@@ -251,23 +251,21 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                 mbar_wait_a(drb, dph);
                 dph ^= 1u;
                 tc_fence_after();
-                // all of this group's accumulator columns are requested at once (one TMEM-load latency per phase instead of one per
-                // 16-column block: the phases of a tile slot are latency bound, profiles/r2_ingest_ncu.md)
-                uint32_t v[NB][16];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) tmem_ld16_async(D + 16u * b, v[b]);
+                uint32_t v[2][16];
+                tmem_ld16_async(D, v[0]);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    tmem_wait_ld16(v[b]);      // waits for every outstanding load: a no-op from the second block on
+                    tmem_wait_ld16(v[b & 1]);
+                    if (b < NB - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
                     float val[16];
                     uint32_t pk[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 bv = lds4(c_b + 64u * b + 16u * g);
-                        val[4 * g + 0] = __uint_as_float(v[b][4 * g + 0]) + bv.x;
-                        val[4 * g + 1] = __uint_as_float(v[b][4 * g + 1]) + bv.y;
-                        val[4 * g + 2] = __uint_as_float(v[b][4 * g + 2]) + bv.z;
-                        val[4 * g + 3] = __uint_as_float(v[b][4 * g + 3]) + bv.w;
+                        val[4 * g + 0] = __uint_as_float(v[b & 1][4 * g + 0]) + bv.x;
+                        val[4 * g + 1] = __uint_as_float(v[b & 1][4 * g + 1]) + bv.y;
+                        val[4 * g + 2] = __uint_as_float(v[b & 1][4 * g + 2]) + bv.z;
+                        val[4 * g + 3] = __uint_as_float(v[b & 1][4 * g + 3]) + bv.w;
                     }
 #pragma unroll
                     for (int j = 0; j < 16; ++j) val[j] = fmaxf(val[j], val[j] * slope);
@@ -352,32 +350,33 @@ ingest_kernel(const __grid_constant__ CUtensorMap m1h, const __grid_constant__ C
                     const int cb = 64 * half + 16 * NBH * h;          // first channel of this group in this half
                     float* lp = lbase + (long long)cb * HW;
                     const uint32_t Dl = Y + (uint32_t)cb, Dc = X + 64u + (uint32_t)(16 * NBH * h);
-                    uint32_t va[NBH][16], vc[NBH][16];
+                    uint32_t va[2][16], vc[2][16];
+                    tmem_ld16_async(Dl, va[0]);
+                    tmem_ld16_async(Dc, vc[0]);
 #pragma unroll
                     for (int b = 0; b < NBH; ++b) {
-                        tmem_ld16_async(Dl + 16u * b, va[b]);
-                        tmem_ld16_async(Dc + 16u * b, vc[b]);
-                    }
-#pragma unroll
-                    for (int b = 0; b < NBH; ++b) {
-                        tmem_wait_ld16(va[b]);
-                        tmem_wait_ld16(vc[b]);
+                        tmem_wait_ld16(va[b & 1]);
+                        tmem_wait_ld16(vc[b & 1]);
+                        if (b < NBH - 1) {
+                            tmem_ld16_async(Dl + 16u * (b + 1), va[(b + 1) & 1]);
+                            tmem_ld16_async(Dc + 16u * (b + 1), vc[(b + 1) & 1]);
+                        }
                         const int c0 = cb + 16 * b;
                         float val[16];
                         uint32_t pk[16];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
                             const float4 b3 = lds4(c_b3 + 4u * (uint32_t)c0 + 16u * g), bc = lds4(c_bc + 4u * (uint32_t)c0 + 16u * g);
-                            const float a0 = __uint_as_float(va[b][4 * g + 0]) + b3.x, a1 = __uint_as_float(va[b][4 * g + 1]) + b3.y,
-                                        a2 = __uint_as_float(va[b][4 * g + 2]) + b3.z, a3 = __uint_as_float(va[b][4 * g + 3]) + b3.w;
+                            const float a0 = __uint_as_float(va[b & 1][4 * g + 0]) + b3.x, a1 = __uint_as_float(va[b & 1][4 * g + 1]) + b3.y,
+                                        a2 = __uint_as_float(va[b & 1][4 * g + 2]) + b3.z, a3 = __uint_as_float(va[b & 1][4 * g + 3]) + b3.w;
                             lp[0] = a0; lp += HW;
                             lp[0] = a1; lp += HW;
                             lp[0] = a2; lp += HW;
                             lp[0] = a3; lp += HW;
-                            val[4 * g + 0] = (__uint_as_float(vc[b][4 * g + 0]) + bc.x) * (a0 + 1.f);
-                            val[4 * g + 1] = (__uint_as_float(vc[b][4 * g + 1]) + bc.y) * (a1 + 1.f);
-                            val[4 * g + 2] = (__uint_as_float(vc[b][4 * g + 2]) + bc.z) * (a2 + 1.f);
-                            val[4 * g + 3] = (__uint_as_float(vc[b][4 * g + 3]) + bc.w) * (a3 + 1.f);
+                            val[4 * g + 0] = (__uint_as_float(vc[b & 1][4 * g + 0]) + bc.x) * (a0 + 1.f);
+                            val[4 * g + 1] = (__uint_as_float(vc[b & 1][4 * g + 1]) + bc.y) * (a1 + 1.f);
+                            val[4 * g + 2] = (__uint_as_float(vc[b & 1][4 * g + 2]) + bc.z) * (a2 + 1.f);
+                            val[4 * g + 3] = (__uint_as_float(vc[b & 1][4 * g + 3]) + bc.w) * (a3 + 1.f);
                         }
                         split_pack16(val, pk);
                         stg256(fhi + po + c0, pk);          // 16 channels = one full 32-byte sector per plane

@@ -326,22 +326,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constan
                 tc_fence_after();
                 const uint32_t D = H + 16u * (uint32_t)(h * NB);
                 const uint32_t cb = c_b1 + 512u * half + 64u * (uint32_t)(h * NB);
-                // all of this group's accumulator columns are requested at once: one TMEM-load latency per phase, not one per block
-                uint32_t v[NB][16];
-#pragma unroll
-                for (int b = 0; b < NB; ++b) tmem_ld16_async(D + 16u * b, v[b]);
+                uint32_t v[2][16];
+                tmem_ld16_async(D, v[0]);
 #pragma unroll
                 for (int b = 0; b < NB; ++b) {
-                    tmem_wait_ld16(v[b]);
+                    tmem_wait_ld16(v[b & 1]);
+                    if (b < NB - 1) tmem_ld16_async(D + 16u * (b + 1), v[(b + 1) & 1]);
                     float val[16];
                     uint32_t pk[16];
 #pragma unroll
                     for (int g = 0; g < 4; ++g) {
                         const float4 bb = lds4(cb + 64u * b + 16u * g);
-                        val[4 * g + 0] = gelu_as(__uint_as_float(v[b][4 * g + 0]) + bb.x);
-                        val[4 * g + 1] = gelu_as(__uint_as_float(v[b][4 * g + 1]) + bb.y);
-                        val[4 * g + 2] = gelu_as(__uint_as_float(v[b][4 * g + 2]) + bb.z);
-                        val[4 * g + 3] = gelu_as(__uint_as_float(v[b][4 * g + 3]) + bb.w);
+                        val[4 * g + 0] = gelu_as(__uint_as_float(v[b & 1][4 * g + 0]) + bb.x);
+                        val[4 * g + 1] = gelu_as(__uint_as_float(v[b & 1][4 * g + 1]) + bb.y);
+                        val[4 * g + 2] = gelu_as(__uint_as_float(v[b & 1][4 * g + 2]) + bb.z);
+                        val[4 * g + 3] = gelu_as(__uint_as_float(v[b & 1][4 * g + 3]) + bb.w);
                     }
                     split_pack16(val, pk);
                     tmem_st16(D + 16u * b, pk);
