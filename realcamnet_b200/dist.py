@@ -94,7 +94,7 @@ def compress_frame_sharded(tiles_on_src: torch.Tensor | None, num_tiles: int, ti
 
 
 def compress_frame_distributed(model, frame: torch.Tensor | None, height: int, width: int, tile: int, device, model_id: int = 0,
-                               max_batch: int = 8) -> bytes | None:
+                               max_batch: int = 0) -> bytes | None:
     """BASELINE config 4: one packed-Bayer frame (4,height,width), held by rank 0, -> RCNB container bytes on rank 0.
 
     Rank 0 uploads the frame, tiles it on the device and scatters tile t to rank t mod G (point-to-point); the frame-level colour

@@ -55,20 +55,9 @@ def main():
     mine = rdist.my_tiles(ntiles, rank, world)
 
     def one_frame():
-        tiles = tiler.split_frame(fr.to(dev, non_blocking=True), T)[0] if rank == 0 else None   # H2D of the frame, tiling on the device
-        local_tiles = rdist.scatter_tiles(tiles, ntiles, (4, T, T), device=dev)
-        ys, zs = [], []
-        for i, t in enumerate(mine):
-            c = m.compress([local_tiles[i:i + 1], cond, tiler.tile_coords(meta, T, t, device=dev)])
-            ys.append(c["strings"][0][0])
-            zs.append(c["strings"][1][0])
-            shape = tuple(int(v) for v in c["shape"])
-        all_y = rdist.gather_bitstreams(ys, ntiles, device=dev)
-        all_z = rdist.gather_bitstreams(zs, ntiles, device=dev)
-        if rank != 0:
-            return None
-        recs = [container.TileStreams(t, shape, all_y[t], all_z[t]) for t in range(ntiles)]
-        return container.pack(container.FrameHeader(0, H, W, T, ny, nx, ntiles), recs)
+        # the maintained path (what bench.py's `frame4k` times): H2D of the frame, tiling on the device, NCCL scatter, batched graph
+        # replays with the host range coder overlapped, bitstream gather, RCNB container on rank 0
+        return rdist.compress_frame_distributed(m, fr, args.height, args.width, T, dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -93,6 +82,7 @@ def main():
     if rank == 0:
         assert blob2 == blob, "frame bitstream is not deterministic"
         hdr, recs = container.unpack(blob)
+        assert len(recs) == ntiles
         mp = 4.0 * args.height * args.width / 1e6
         line = {"config": f"BASELINE configs[3]: packed 4x{args.height}x{args.width} RAW frame, {ntiles} tiles of 4x{T}x{T}, tile t -> rank t mod {world}, "
                           "compress() per tile + scatter/gather + RCNB container", "n_gpus": world, "tiles": ntiles,
