@@ -77,6 +77,21 @@ class SpatialFeatureTransform(nn.Module):
                                         Conv2d(n_features, n_features, 3, stride=1, padding=1))
         self.residual = residual
 
+    def _merged_first(self):
+        """cond_scale[0] and cond_shift[0] as one packed conv (weights / biases concatenated on the output axis), re-packed when
+        either changes."""
+        a, b = self.cond_scale[0], self.cond_shift[0]
+        if a.bias is None or b.bias is None or a.weight.shape != b.weight.shape:
+            return None
+        key = tuple((t._version, t.data_ptr()) for t in (a.weight, a.bias, b.weight, b.bias))
+        hit = self.__dict__.get("_rcn_merged")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                pc = ops.pack_weight(torch.cat([a.weight.detach(), b.weight.detach()], 0).contiguous(),
+                                     torch.cat([a.bias.detach(), b.bias.detach()], 0).contiguous())
+            hit = self.__dict__["_rcn_merged"] = (key, pc)
+        return hit[1]
+
     def _f(self, x, cond, extra=None, out=None, cond_split=None, split_out=None, keep_fp32=True):
         """x*scale + shift + x (+ extra); both element-wise steps are conv epilogues.
         cond_split: operand planes of cond (shared by every block of a level); split_out / keep_fp32: write the result as
@@ -85,9 +100,17 @@ class SpatialFeatureTransform(nn.Module):
             raise NotImplementedError("residual=False is never used by the reference")
         sp = cond_split if cond_split is not None else \
             ops.shared_split(cond, [ops.pack(self.cond_scale[0]), ops.pack(self.cond_shift[0])])
-        s, ssp = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+        pcm = self._merged_first() if ops.bf16_planes_enabled() else None
+        if pcm is not None and pcm.cout == 128:
+            # both first layers read cond: ONE 3x3 conv with the two weight sets stacked on the output axis (N = 128 fills the MMA
+            # width, the cond planes are fetched once); the second layers read their half of its planes
+            _, both = ops.conv2d(cond, pcm, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+            s = h = None
+            ssp, hsp = both.channels(0, 64), both.channels(64, 128)
+        else:
+            s, ssp = self.cond_scale[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
+            h, hsp = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
         t = self.cond_scale[2]._f(s, epi=EPI_MULP1_AUX, aux=x, res=extra, presplit=ssp)      # (scale + 1) * x (+ extra)
-        h, hsp = self.cond_shift[0]._f(cond, act=ACT_RELU, presplit=sp, emit_split=True, keep_fp32=False)
         if split_out is None:
             return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp)                    # shift + ...
         return self.cond_shift[2]._f(h, res=t, out=out, presplit=hsp, split_out=split_out, keep_fp32=keep_fp32)[0]
