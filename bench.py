@@ -171,6 +171,12 @@ def run_cpu_reference(T, steps, warmup, budget_s=150.0):
     return {"value": mp / dt, "dt": dt, "threads": best, "steps_timed": done, "kind": kind, "note": note, "sym": sym}
 
 
+def workload_name(T):
+    """the same string in both arms' `config.workload` (the driver compares the arms' configurations)"""
+    return (f"raw_compression_tcm_final.forward + range coder on one 4x{T}x{T} packed-Bayer tile per GPU (BASELINE config[1]), "
+            "random-init weights (name-keyed, seed 0)")
+
+
 # --------------------------------------------------------------------------------------------- BASELINE config 4
 def measure_frame4k(model, dev, rank, world, height=2160, width=3840, tile=512, reps=2):
     """Frames/s of the tiled-frame path on the ranks of this run (wall time incl. all host work, max over ranks)."""
@@ -253,8 +259,7 @@ def main():
         line = {"metric": METRIC, "value": v, "unit": "MP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "steps_timed": r["steps_timed"], "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "impl": "reference",
-                "config": {"workload": f"raw_compression_tcm_final.forward + range coder on one 4x{Tc}x{Tc} packed-Bayer tile "
-                                       "(BASELINE config[1]), random-init weights (name-keyed, seed 0)", "tile": Tc},
+                "config": {"workload": workload_name(Tc), "tile": Tc, "tiles_per_gpu": 1},
                 "cpu_baseline": {"value": v, "unit": "MP/s", "cores": r["threads"], "kind": r["kind"], "sample": sample},
                 "e2e": {"value": v, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -518,8 +523,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "MP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": dtype, "data": "synthetic",
-                "config": {"workload": f"raw_compression_tcm_final.forward + range coder on one 4x{T}x{T} packed-Bayer tile per GPU "
-                                       "(BASELINE config[1]), random-init weights (name-keyed, seed 0)",
+                "config": {"workload": workload_name(T),
                            "tile": T, "tiles_per_gpu": 1, "conv_engine": args.engine, "tail_engine": tail or args.engine,
                            "cuda_graphs": not args.no_graphs, "parallelism": f"tile-sharded x{world}",
                            "l2_policy": "inputs and activations (>2 GB per layer) exceed the 126 MB L2; no explicit flush",
