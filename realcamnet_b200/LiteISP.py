@@ -126,7 +126,7 @@ class Res_GFM(nn.Module):
         return ops.to_nchw(fea), x[1]
 
 
-class LiteISPNet_GFM_LSC(nn.Module):
+class LiteISPNet_GFM_LSC(ops.GraphReplay, nn.Module):
     """models/LiteISP.py:1924-2035."""
 
     def __init__(self):
@@ -156,6 +156,10 @@ class LiteISPNet_GFM_LSC(nn.Module):
         self.tail = N.seq(N.conv(ch_1, ch_1 * 4, mode='C'), nn.PixelShuffle(upscale_factor=2), N.conv(ch_1, 3, mode='C'))
 
     def forward(self, x):
+        """forward([raw, cond, coord]); replayed as one CUDA graph after enable_cuda_graphs() (ops.GraphReplay)"""
+        return self._graph_call(self._forward, list(x))
+
+    def _forward(self, x):
         raw, cond, coord = ops.to_nhwc(x[0]), ops.to_nhwc(x[1]), ops.to_nhwc(x[2])
         lsc_fea = self.lsc._f(coord)
         h = self.head._f(raw, epi=EPI_MUL_AUXP1, aux=lsc_fea)              # head(x) * (lsc + 1)
@@ -173,7 +177,7 @@ class LiteISPNet_GFM_LSC(nn.Module):
         return self.tail[2]._f(t, store=ops.STORE_NCHW)
 
 
-class LiteISPNet(nn.Module):
+class LiteISPNet(ops.GraphReplay, nn.Module):
     """models/LiteISP.py:2322-2412: the plain LiteISP UNet -- LiteISPNet_GFM_LSC without colour condition, lens shading and
     modulation blocks (ch_1 = 64).  forward(x) reads x[0], the packed RAW tile (N,4,H,W), and returns (N,3,2H,2W)."""
 
@@ -198,6 +202,9 @@ class LiteISPNet(nn.Module):
         self.tail = N.seq(N.conv(ch_1, ch_1 * 4, mode='C'), nn.PixelShuffle(upscale_factor=2), N.conv(ch_1, 3, mode='C'))
 
     def forward(self, x):
+        return self._graph_call(self._forward, list(x))
+
+    def _forward(self, x):
         h = self.head._f(ops.to_nhwc(x[0]))
         d1 = self.down1._f(h)
         d2 = self.down2._f(d1)
@@ -218,7 +225,7 @@ def _modulate(mods, x, vec):
     return x
 
 
-class _UNetISP(nn.Module):
+class _UNetISP(ops.GraphReplay, nn.Module):
     """Shared wiring of ISPUNet_GFM_LSC and ResUNet: 3-level UNet of RCAGroups with learned 2x2 stride-2 down-samplers and
     1x1 conv + PixelShuffle up-samplers, chan = 32 -> 64 -> 128 -> 256."""
 
@@ -262,6 +269,9 @@ class _UNetISP(nn.Module):
         self._modulated = bool(modulation)
 
     def forward(self, x):
+        return self._graph_call(self._forward, list(x))
+
+    def _forward(self, x):
         raw = ops.to_nhwc(x[0])
         vec = None
         if self._modulated:
@@ -303,7 +313,7 @@ class ResUNet(_UNetISP):
         self._build(32, 2, None)
 
 
-class MWISP(nn.Module):
+class MWISP(ops.GraphReplay, nn.Module):
     """models/LiteISP.py:2149-2218 (multi-level wavelet ISP: Haar DWT / IDWT around RCAGroups of 20 blocks, PReLU activations).
     forward(x, c=None) reads x[0] (N,4,H,W) and returns (N,3,2H,2W)."""
 
@@ -321,6 +331,9 @@ class MWISP(nn.Module):
         self.tail = N.seq(N.DWTInverse_(), Conv2d(4, 12, 3, 1, 1), nn.PixelShuffle(upscale_factor=2))
 
     def forward(self, x, c=None):
+        return self._graph_call(self._forward, list(x))
+
+    def _forward(self, x):
         c1 = self.head._f(ops.to_nhwc(x[0]))
         c2 = self.down1._f(c1)
         c3 = self.down2._f(c2)

@@ -486,6 +486,55 @@ def wmsa(qkv, relpos, head_dim, ws, shifted, out=None, emit_split=False):
 
 # ----------------------------------------------------------------------------- layout
 
+# ----------------------------------------------------------------------------- CUDA-graph replay of a fixed launch sequence
+class GraphReplay:
+    """Mixin for nn.Modules whose inference forward is a fixed sequence of C-ABI launches (the ISP networks: ~250-1350 launches per
+    tile, 20 us of host time each when issued eagerly -- a 256^2 tile is host-bound by 4x).  enable_cuda_graphs() makes
+    `_graph_call(fn, inputs)` capture fn(inputs) once per (input shapes, engine) and replay it afterwards; a fingerprint of every
+    parameter / buffer version invalidates the captures (in-place weight edits, load_state_dict), moving the module does too.
+    The tensor returned in graph mode lives in the graph's memory pool and is OVERWRITTEN by the next call (clone what must survive)."""
+
+    def enable_cuda_graphs(self, flag=True):
+        self.__dict__["_use_graphs"] = bool(flag)
+        self.__dict__["_graphs"] = {}
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__["_graphs"] = {}
+        return super()._apply(fn, *args, **kwargs)
+
+    def _graph_fingerprint(self):
+        return sum(t._version for t in list(self.parameters()) + list(self.buffers()))
+
+    def _graph_call(self, fn, inputs):
+        if not self.__dict__.get("_use_graphs") or not inputs[0].is_cuda:
+            return fn(inputs)
+        cache = self.__dict__.setdefault("_graphs", {})
+        fp = self._graph_fingerprint()
+        if cache.get("_fp") != fp:
+            cache.clear()
+            cache["_fp"] = fp
+        key = (_ENGINE,) + tuple((tuple(t.shape), str(t.device)) for t in inputs)
+        e = cache.get(key)
+        if e is None:
+            static_in = [t.detach().clone() for t in inputs]
+            fn(static_in)                                  # eager warm-up: weight packing and every other lazy initialisation
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = launch_count()
+            with torch.cuda.graph(g):
+                out = fn(static_in)
+            e = cache[key] = (g, static_in, out, launch_count() - n0)
+            cache["_fp"] = self._graph_fingerprint()
+        g, static_in, out, n = e
+        for dst, src in zip(static_in, inputs):
+            if dst.data_ptr() != src.data_ptr():
+                dst.copy_(src, non_blocking=True)
+        g.replay()
+        count_replayed(n)
+        return out
+
+
 # ----------------------------------------------------------------------------- independent branches on two streams
 # 0: branches run one after the other (triage / A-B)
 _CONCURRENT_BRANCHES = os.environ.get("RCN_CONCURRENT_BRANCHES", "1") != "0"

@@ -610,6 +610,29 @@ def test_liteisp_plain_matches_fixture(dev, engine, golden_dir):
     assert abs(float(out.double().abs().sum()) - float(gold["out_abs_sum"])) / float(gold["out_abs_sum"]) < 1e-4
 
 
+@pytest.mark.parametrize("name", ["LiteISPNet_GFM_LSC", "ResUNet"])
+def test_isp_graph_replay_is_bit_identical_and_follows_weight_edits(dev, name):
+    """ops.GraphReplay on the ISP networks: replay == eager bit for bit, new inputs are picked up, an in-place weight edit
+    invalidates the capture."""
+    from realcamnet_b200 import LiteISP
+
+    m = getattr(LiteISP, name)()
+    weights.fill_(m, seed=3)
+    m = m.to(dev).eval()
+    xa = [t.to(dev) for t in inputs.make_inputs(128, seed=77)]
+    xb = [t.to(dev) for t in inputs.make_inputs(128, seed=78)]
+    ea, eb = m(xa).clone(), m(xb).clone()
+    m.enable_cuda_graphs(True)
+    ga = m(xa).clone()
+    gb = m(xb).clone()
+    assert torch.equal(ga, ea) and torch.equal(gb, eb)
+    with torch.no_grad():
+        next(p for n, p in m.named_parameters() if n.endswith("weight")).mul_(1.01)
+    g2 = m(xa).clone()
+    m.enable_cuda_graphs(False)
+    assert torch.equal(g2, m(xa)) and not torch.equal(g2, ea)
+
+
 @pytest.mark.parametrize("name,seed,fn", [("ISPUNet_GFM_LSC", 1241, "ispunet_gfm_lsc_forward"), ("ResUNet", 1242, "resunet_forward"),
                                           ("MWISP", 1243, "mwisp_forward")])
 def test_isp_variants_match_oracle_and_fixture(dev, engine, golden_dir, name, seed, fn):

@@ -2,7 +2,7 @@
 
   python tools/liteisp_bench.py [T=256] [T2=1024]   -> one JSON line per (model, tile): sensor MP/s, ms per tile
 
-Inputs resident on the device, eager launches, CUDA events, median of 7 after 3 warm-ups.  1 MP = 1e6 sensor photosites (4*T*T per tile).
+Inputs resident on the device, eager launches and CUDA-graph replay (enable_cuda_graphs), CUDA events, median of 7 after 3 warm-ups.  1 MP = 1e6 sensor photosites (4*T*T per tile).
 """
 import json
 import os
@@ -19,7 +19,8 @@ for name in ("LiteISPNet_GFM_LSC", "LiteISPNet", "ISPUNet_GFM_LSC", "ResUNet", "
     m = getattr(LiteISP, name)()
     synthetic.fill_(m, seed=0)
     m = m.to(dev).eval()
-    for T in tiles:
+    for T, graphs in [(T, g) for T in tiles for g in (False, True)]:
+        m.enable_cuda_graphs(graphs)
         x = [t.to(dev) for t in synthetic.make_inputs(T, seed=1235)]
         with torch.no_grad():
             for _ in range(3):
@@ -36,4 +37,4 @@ for name in ("LiteISPNet_GFM_LSC", "LiteISPNet", "ISPUNet_GFM_LSC", "ResUNet", "
                 launches = ops.launch_count() - n0
         ms = sorted(ts)[len(ts) // 2]
         print(json.dumps({"model": name, "tile": T, "ms_per_tile": ms, "sensor_mp_per_s": 4.0 * T * T / 1e6 / (ms / 1e3),
-                          "launches": launches, "engine": ops.get_engine()}), flush=True)
+                          "launches": launches, "engine": ops.get_engine(), "cuda_graph": graphs}), flush=True)
