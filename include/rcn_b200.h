@@ -161,6 +161,8 @@ int rcn_scale_add(const float* x, int ldx, int N, long long HW, int C, const flo
 int rcn_avgpool3s2_lrelu(const float* x, int N, int H, int W, int C, int ldx, float slope, float* y, int ldy, void* stream);
 /* nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True): HyCondModDecBlock, models/raw2bit.py:793-796 */
 int rcn_upsample_bilinear2x(const float* x, int N, int H, int W, int C, int ldx, float* y, int ldy, void* stream);
+/* same, written as the bf16 hi/lo operand planes (pixel stride ldp) of the conv that follows (HyCondModDecBlock.up[1]) */
+int rcn_upsample_bilinear2x_planes(const float* x, int N, int H, int W, int C, int ldx, void* y_hi, void* y_lo, int ldp, void* stream);
 /* Haar DWTForward / DWTInverse as fixed 2x2 stride-2 (transposed) grouped convs, channel order
  * [LL,LH,HL,HH] per input channel: models/networks.py:224-249 */
 int rcn_dwt_forward(const float* x, int N, int H, int W, int C, int ldx, float* y, int ldy, void* stream);

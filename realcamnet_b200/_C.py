@@ -95,6 +95,7 @@ PROTOTYPES = {
     "rcn_scale_add": (_I, [_P, _I, _I, _L, _I, _P, _P, _I, _P, _I, _P, _I, _I, _P]),
     "rcn_avgpool3s2_lrelu": (_I, [_P, _I, _I, _I, _I, _I, _F, _P, _I, _P]),
     "rcn_upsample_bilinear2x": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
+    "rcn_upsample_bilinear2x_planes": (_I, [_P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
     "rcn_dwt_forward": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_dwt_inverse": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),
     "rcn_space_to_depth2": (_I, [_P, _I, _I, _I, _I, _I, _P, _I, _P]),

@@ -1,5 +1,7 @@
 // Bandwidth-bound helper kernels of the RAW->bitstream path (NHWC fp32): layout changes,
 // pooling / normalisation statistics, gating, resampling, Haar DWT, depthwise convolutions.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace rcn {
@@ -266,6 +268,44 @@ __global__ void upsample2x_vec4_kernel(const float* __restrict__ x, int H, int W
         v.z = hl0 * (wl0 * a00.z + wl1 * a01.z) + hl1 * (wl0 * a10.z + wl1 * a11.z);
         v.w = hl0 * (wl0 * a00.w + wl1 * a01.w) + hl1 * (wl0 * a10.w + wl1 * a11.w);
         *reinterpret_cast<float4*>(y + ((long long)(n * Ho + ho) * Wo + wo) * ldy + c) = v;
+    }
+}
+
+// same interpolation, result written as the bf16 hi / lo operand planes of the conv that reads it (pixel stride ldp): the fp32 map of
+// the condition UNet's up path (32 channels at 2048^2) and its rcn_split_bf16 pass disappear
+__global__ void upsample2x_planes_kernel(const float* __restrict__ x, int H, int W, int C4, int ldx, long long total,
+                                         __nv_bfloat16* __restrict__ y_hi, __nv_bfloat16* __restrict__ y_lo, int ldp) {
+    const int Ho = 2 * H, Wo = 2 * W;
+    const float sh = (Ho > 1) ? (float)(H - 1) / (float)(Ho - 1) : 0.f;
+    const float sw = (Wo > 1) ? (float)(W - 1) / (float)(Wo - 1) : 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C4) * 4;
+        long long t = i / C4;
+        const int wo = (int)(t % Wo); t /= Wo;
+        const int ho = (int)(t % Ho);
+        const int n = (int)(t / Ho);
+        const float hr = sh * ho, wr = sw * wo;
+        const int h1 = (int)hr, w1 = (int)wr;
+        const int hp = (h1 < H - 1) ? 1 : 0, wp = (w1 < W - 1) ? 1 : 0;
+        const float hl1 = hr - h1, hl0 = 1.f - hl1, wl1 = wr - w1, wl0 = 1.f - wl1;
+        const float* b = x + ((long long)(n * H + h1) * W + w1) * ldx + c;
+        const float4 a00 = *reinterpret_cast<const float4*>(b), a01 = *reinterpret_cast<const float4*>(b + (long long)wp * ldx);
+        const float4 a10 = *reinterpret_cast<const float4*>(b + (long long)hp * W * ldx),
+                     a11 = *reinterpret_cast<const float4*>(b + ((long long)hp * W + wp) * ldx);
+        float v[4];   // same expression (and rounding) as the fp32 kernels
+        v[0] = hl0 * (wl0 * a00.x + wl1 * a01.x) + hl1 * (wl0 * a10.x + wl1 * a11.x);
+        v[1] = hl0 * (wl0 * a00.y + wl1 * a01.y) + hl1 * (wl0 * a10.y + wl1 * a11.y);
+        v[2] = hl0 * (wl0 * a00.z + wl1 * a01.z) + hl1 * (wl0 * a10.z + wl1 * a11.z);
+        v[3] = hl0 * (wl0 * a00.w + wl1 * a01.w) + hl1 * (wl0 * a10.w + wl1 * a11.w);
+        __nv_bfloat16 hb[4], lb[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {     // rounding of rcn_split_bf16: hi = rn(v), lo = rn(v - hi)
+            hb[e] = __float2bfloat16_rn(v[e]);
+            lb[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hb[e]));
+        }
+        const long long po = ((long long)(n * Ho + ho) * Wo + wo) * ldp + c;
+        *reinterpret_cast<uint2*>(y_hi + po) = *reinterpret_cast<uint2*>(hb);
+        *reinterpret_cast<uint2*>(y_lo + po) = *reinterpret_cast<uint2*>(lb);
     }
 }
 
@@ -552,6 +592,20 @@ extern "C" int rcn_upsample_bilinear2x(const float* x, int N, int H, int W, int 
         upsample2x_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C, ldx, total, y, ldy);
     count_launch();
     RCN_CHECK_LAUNCH("rcn_upsample_bilinear2x");
+    return RCN_OK;
+}
+
+extern "C" int rcn_upsample_bilinear2x_planes(const float* x, int N, int H, int W, int C, int ldx, void* y_hi, void* y_lo, int ldp,
+                                              void* stream) {
+    RCN_CHECK_ARG(x && y_hi && y_lo, "rcn_upsample_bilinear2x_planes: null pointer");
+    RCN_CHECK_ARG(C % 4 == 0 && ldx % 4 == 0 && ldp >= C && ldp % 4 == 0 && (uintptr_t)x % 16 == 0 && (uintptr_t)y_hi % 8 == 0 &&
+                      (uintptr_t)y_lo % 8 == 0,
+                  "rcn_upsample_bilinear2x_planes: needs C %% 4 == 0, 16-byte aligned rows and 8-byte aligned planes");
+    const long long total = (long long)N * 4 * H * W * (C / 4);
+    upsample2x_planes_kernel<<<ew_blocks(total), 256, 0, (cudaStream_t)stream>>>(x, H, W, C / 4, ldx, total, (__nv_bfloat16*)y_hi,
+                                                                                 (__nv_bfloat16*)y_lo, ldp);
+    count_launch();
+    RCN_CHECK_LAUNCH("rcn_upsample_bilinear2x_planes");
     return RCN_OK;
 }
 

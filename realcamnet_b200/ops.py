@@ -797,8 +797,18 @@ def avgpool3s2_lrelu(x, slope):
     return out
 
 
-def upsample_bilinear2x(x, out=None):
+def upsample_bilinear2x(x, out=None, emit_split=False):
+    """emit_split=True: returns (None, SplitOperand) -- the result only exists as the consumer conv's operand planes -- when the
+    bf16 plane engine is active and C is a plane width; else (fp32 tensor, None)."""
     N, H, W, C, ldx = geom(x)
+    if emit_split and out is None and bf16_planes_enabled() and _mode()[0] == 3 and plane_channels(C) == C and ldx % 4 == 0 and \
+            x.data_ptr() % 16 == 0:
+        sp = alloc_planes(N, 2 * H, 2 * W, C, x.device)
+        _C.check(_C.lib().rcn_upsample_bilinear2x_planes(_ptr(x), N, H, W, C, ldx, _ptr(sp.hi), _ptr(sp.lo), plane_ld(sp.hi), _stream()),
+                 "rcn_upsample_bilinear2x_planes")
+        return None, sp
+    if emit_split:
+        return upsample_bilinear2x(x, out=out), None
     if out is None:
         out = empty(N, 2 * H, 2 * W, C, like=x)
     assert tuple(out.shape) == (N, 2 * H, 2 * W, C)

@@ -195,8 +195,12 @@ class HyCondModEncBlock(nn.Module):
         self.down = HyCondModConvBlock(in_channels, out_channels, stride=2)
         self.conv = HyCondModConvBlock(out_channels, out_channels)
 
-    def _f(self, x, out=None):
+    def _f(self, x, out=None, split_out=None):
+        """split_out: also write the result as operand planes (its half of a decoder concat's planes)"""
         t, sp = self.down.conv._f(x, act=self.down._act[0], slope=self.down._act[1], emit_split=True, keep_fp32=False)
+        if split_out is not None:
+            return self.conv.conv._f(t, act=self.conv._act[0], slope=self.conv._act[1], out=out, presplit=sp, split_out=split_out,
+                                     keep_fp32=True)[0]
         return self.conv.conv._f(t, act=self.conv._act[0], slope=self.conv._act[1], out=out, presplit=sp)
 
 
@@ -210,9 +214,16 @@ class HyCondModDecBlock(nn.Module):
                                 HyCondModConvBlock(in_channels, out_channels))
         self.conv = HyCondModConvBlock(in_channels, out_channels)
 
-    def _f(self, x1, cat, out=None):
-        """cat: (N,2H,2W,2*out) buffer whose first half already holds the skip tensor x2."""
-        oc = cat.shape[-1] // 2
+    def _f(self, x1, cat, out=None, cat_planes=None):
+        """cat: (N,2H,2W,2*out) buffer whose first half already holds the skip tensor x2.
+        cat_planes: operand planes of the concat whose first half the skip's producer has written: the up-sampled map, the up
+        conv's half of the concat and the concat itself then only exist as operand planes (no fp32 maps, no rcn_split_bf16 passes)."""
+        oc = self.up[1].conv.out_channels
+        if cat_planes is not None:
+            u, usp = ops.upsample_bilinear2x(x1, emit_split=True)
+            up = self.up[1]
+            up.conv._f(u, act=up._act[0], slope=up._act[1], presplit=usp, split_out=cat_planes.channels(oc, 2 * oc), keep_fp32=False)
+            return self.conv.conv._f(None, act=self.conv._act[0], slope=self.conv._act[1], out=out, presplit=cat_planes)
         self.up[1]._f(ops.upsample_bilinear2x(x1), out=cat[..., oc:])
         return self.conv._f(cat, out=out)
 
@@ -242,16 +253,32 @@ class HybridConditionModule(nn.Module):
         N, H, W, _ = x.shape
         m = self._m
         # skip tensors are produced straight into the first half of the decoder concat buffers
-        cat3 = ops.empty(N, H, W, 2 * m, like=x)
-        cat2 = ops.empty(N, H // 2, W // 2, 4 * m, like=x)
-        cat1 = ops.empty(N, H // 4, W // 4, 8 * m, like=x)
-        x1 = self.in_conv.conv._f(x, act=self.in_conv._act[0], slope=self.in_conv._act[1], out=cat3[..., :m], presplit=presplit)
-        x2 = self.enc_1._f(x1, out=cat2[..., :2 * m])
-        x3 = self.enc_2._f(x2, out=cat1[..., :4 * m])
-        x4 = self.enc_3._f(x3)
-        y = self.dec_1._f(x4, cat1)
-        y = self.dec_2._f(y, cat2)
-        y = self.dec_3._f(y, cat3)
+        planes = ops.bf16_planes_enabled() and ops.get_engine() == "bf16x3" and all(ops.plane_channels(c) == c for c in (m, 2 * m, 4 * m, 8 * m))
+        if planes:
+            # tcgen05 engine: the decoder concats only exist as operand planes, written half by half by the skip's producer and by the
+            # up conv (whose own input comes as planes from the up-sampling kernel); the skips keep an fp32 copy for the encoder
+            p3 = ops.alloc_planes(N, H, W, 2 * m, x.device)
+            p2 = ops.alloc_planes(N, H // 2, W // 2, 4 * m, x.device)
+            p1 = ops.alloc_planes(N, H // 4, W // 4, 8 * m, x.device)
+            x1 = self.in_conv.conv._f(x, act=self.in_conv._act[0], slope=self.in_conv._act[1], presplit=presplit,
+                                      split_out=p3.channels(0, m), keep_fp32=True)[0]
+            x2 = self.enc_1._f(x1, split_out=p2.channels(0, 2 * m))
+            x3 = self.enc_2._f(x2, split_out=p1.channels(0, 4 * m))
+            x4 = self.enc_3._f(x3)
+            y = self.dec_1._f(x4, None, cat_planes=p1)
+            y = self.dec_2._f(y, None, cat_planes=p2)
+            y = self.dec_3._f(y, None, cat_planes=p3)
+        else:
+            cat3 = ops.empty(N, H, W, 2 * m, like=x)
+            cat2 = ops.empty(N, H // 2, W // 2, 4 * m, like=x)
+            cat1 = ops.empty(N, H // 4, W // 4, 8 * m, like=x)
+            x1 = self.in_conv.conv._f(x, act=self.in_conv._act[0], slope=self.in_conv._act[1], out=cat3[..., :m], presplit=presplit)
+            x2 = self.enc_1._f(x1, out=cat2[..., :2 * m])
+            x3 = self.enc_2._f(x2, out=cat1[..., :4 * m])
+            x4 = self.enc_3._f(x3)
+            y = self.dec_1._f(x4, cat1)
+            y = self.dec_2._f(y, cat2)
+            y = self.dec_3._f(y, cat3)
         # the three CondNets read y through a stride-2 3x3 conv only: out_conv writes their (shared) polyphase operand planes itself
         y, sp = self.out_conv.conv._f(y, act=self.out_conv._act[0], slope=self.out_conv._act[1], emit_split=True, keep_fp32=False,
                                       emit_stride=2)
