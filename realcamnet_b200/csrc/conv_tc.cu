@@ -1419,8 +1419,10 @@ extern "C" int rcn_conv2d_tc(const rcn_conv_desc* d, const void* x_hi, const voi
                       "rcn_conv2d_tc: operand-plane emission needs an NHWC / pixel-shuffle store, a plane pixel stride Cp_out >= the "
                       "stored channels (multiple of 8) and 16-byte aligned tensors");
     }
-    RCN_CHECK_ARG(!d->planes_s2 || (d->y_hi && d->store == RCN_STORE_NHWC && d->stride == 1 && d->H % 2 == 0 && d->W % 2 == 0),
-                  "rcn_conv2d_tc: polyphase plane emission needs a stride-1 NHWC layer with even H and W");
+    // the polyphase layout is that of the OUTPUT map (the epilogue works in output geometry): a stride-2 layer feeding another one
+    // (CondNet2 / CondNet3 of the condition module, raw2bit.py:842-849) needs H, W divisible by 4
+    RCN_CHECK_ARG(!d->planes_s2 || (d->y_hi && d->store == RCN_STORE_NHWC && d->H % (2 * d->stride) == 0 && d->W % (2 * d->stride) == 0),
+                  "rcn_conv2d_tc: polyphase plane emission needs an NHWC layer whose output map has even H and W");
     RCN_CHECK_ARG(passes == 1 || (passes == 3 && x_lo && w_lo), "rcn_conv2d_tc: passes must be 1 or 3 (3 needs the lo planes)");
     RCN_CHECK_ARG(d->k == 1 || d->k == 3, "rcn_conv2d_tc: kernel size %d unsupported", d->k);
     RCN_CHECK_ARG(d->Cout <= BIAS_MAX, "rcn_conv2d_tc: Cout %d > %d unsupported", d->Cout, BIAS_MAX);

@@ -354,7 +354,7 @@ def conv2d(x, pc: PackedConv, stride=1, act=ACT_NONE, slope=0.0, out=None, store
     can_emit = (emit_split and use_tc and store in (STORE_NHWC, STORE_PS2) and plane_channels(Cs) == Cs and
                 (store != STORE_PS2 or (epi == EPI_NONE and cscale is None and pc.cout % 64 == 0)) and pc.cout % 16 == 0)
     if emit_stride == 2:
-        can_emit = can_emit and store == STORE_NHWC and stride == 1 and Ho % 2 == 0 and Wo % 2 == 0
+        can_emit = can_emit and store == STORE_NHWC and Ho % 2 == 0 and Wo % 2 == 0
     if split_out is not None and not can_emit:
         raise ValueError("conv2d: split_out given but this layer cannot emit operand planes")
     want_out = keep_fp32 or not can_emit or out is not None

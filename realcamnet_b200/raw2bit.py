@@ -287,10 +287,12 @@ class HybridConditionModule(nn.Module):
             sp = ops.shared_split(y, [ops.pack(h) for h in heads], stride=2)
         t, tsp = self.CondNet1[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False)
         c1 = self.CondNet1[2]._f(t, presplit=tsp)
-        c2 = self.CondNet2[2]._f(self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp))
-        c3 = self.CondNet3[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp)
-        c3 = self.CondNet3[2]._f(c3, act=ACT_LRELU, slope=0.1)
-        c3 = self.CondNet3[4]._f(c3)
+        # stride-2 -> stride-2 chains: each layer writes the next one's polyphase operand planes itself
+        t2, sp2 = self.CondNet2[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False, emit_stride=2)
+        c2 = self.CondNet2[2]._f(t2, presplit=sp2)
+        t3, sp3 = self.CondNet3[0]._f(y, act=ACT_LRELU, slope=0.1, presplit=sp, emit_split=True, keep_fp32=False, emit_stride=2)
+        t3, sp3 = self.CondNet3[2]._f(t3, act=ACT_LRELU, slope=0.1, presplit=sp3, emit_split=True, keep_fp32=False, emit_stride=2)
+        c3 = self.CondNet3[4]._f(t3, presplit=sp3)
         return [c1, c2, c3]
 
     def forward(self, x):
