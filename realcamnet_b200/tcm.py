@@ -167,12 +167,15 @@ class SwinBlock(nn.Module):
         self.block_2 = Block(input_dim, output_dim, head_dim, window_size, drop_path, type='SW')
         self.window_size = window_size
 
-    def _f(self, x):
+    def _f(self, x, split_out=None):
+        """split_out: also write the result as the operand planes of the layer that reads it"""
         N, H, W, C = x.shape
         if W <= self.window_size or H <= self.window_size:
             # the reference pads such maps and never crops them back (models/tcm.py:301-312), which then
             # fails inside WMSA's window rearrange; same condition -> same kind of error here
             raise ValueError(f"SwinBlock: {H}x{W} map must be larger than the window {self.window_size}")
+        if split_out is not None:
+            return self.block_2._f(self.block_1._f(x), split_out=split_out, keep_fp32=True)
         return self.block_2._f(self.block_1._f(x))
 
     def forward(self, x):
@@ -194,12 +197,15 @@ class SWAtten(AttentionBlock):
         self._has_io = inter_dim is not None
 
     def _f(self, x, out=None):
+        xsp = None
         if self._has_io:
-            x = self.in_conv._f(x)
+            x, xsp = self.in_conv._f(x, emit_split=True, keep_fp32=True)     # planes for the first unit of branch a
+        N, H, W, C = x.shape
+        planes = ops.bf16_planes_enabled() and ops.get_engine() == "bf16x3" and ops.plane_channels(C) == C
 
-        # ResidualUnit -> ResidualUnit -> 1x1 hand their results over as operand planes (no rcn_split_bf16 pass in between)
+        # in_conv / SwinBlock -> ResidualUnit -> ResidualUnit -> 1x1 hand their results over as operand planes (no rcn_split_bf16 pass)
         def branch_a():                     # conv_a(x): three ResidualUnits
-            a, sp = x, None
+            a, sp = x, xsp
             for i in range(3):
                 if i < 2:
                     a, sp = self.conv_a[i]._f(a, presplit=sp, emit_split=True)
@@ -208,7 +214,11 @@ class SWAtten(AttentionBlock):
             return a
 
         def branch_b():                     # conv_b(non_local_block(x)) up to the gate: independent of branch a (ops.fork_join)
-            b, sp = self.non_local_block._f(x), None
+            if planes:
+                sp = ops.alloc_planes(N, H, W, C, x.device)
+                b = self.non_local_block._f(x, split_out=sp)
+            else:
+                b, sp = self.non_local_block._f(x), None
             for i in range(3):
                 b, sp = self.conv_b[i]._f(b, presplit=sp, emit_split=True)
             return b, sp

@@ -110,7 +110,7 @@ for key, nb, fl, e0, e1 in records:
 ksum = sum(a[1] for a in agg.values())
 print(f"T={T} engine={eng} mode={mode}: step {total:.2f} ms on the stream; {len(records)} calls, {ksum:.2f} ms inside calls")
 print(f"{'ms':>8s} {'share':>6s} {'n':>4s} {'ms/call':>8s} {'GB/s':>7s} {'TF/s':>7s}  call")
-for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get("RCN_TRACE_ROWS", "70"))]:
     gbs = a[2] / a[1] / 1e6 if a[2] else 0.0
     tfs = a[3] / a[1] / 1e9 if a[3] else 0.0
     print(f"{a[1]:8.3f} {100 * a[1] / total:5.1f}% {a[0]:4d} {a[1] / a[0]:8.4f} {gbs:7.0f} {tfs:7.1f}  {key}")
