@@ -20,8 +20,8 @@
 //     output of forward()) and the product once (the 16-bit operand planes of conv_down, polyphase layout).
 //
 // Tensor memory: 2 tile slots x 256 columns.  A slot's regions X and Y (128 columns each) alternate between "A operand" and
-// "accumulator" from layer to layer; two tiles are in flight per CTA, one per epilogue warp group, so the tensor pipe works on
-// one tile while the other tile's epilogue runs.  The conv accumulator has no 128 free columns left in a slot: it is produced
+// "accumulator" from layer to layer; two tiles are in flight per CTA, each served by IG_EWG epilogue warp groups (which split the
+// channel blocks of every phase), so the tensor pipe works on one tile while the other tile's epilogue runs.  The conv accumulator has no 128 free columns left in a slot: it is produced
 // in two 64-channel halves into X[64..128) after layer 3 has consumed X.
 //
 // Arithmetic = the bf16x3 engine's (a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, fp32 accumulate); layer 0 is plain fp32.
